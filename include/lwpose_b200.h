@@ -1,0 +1,166 @@
+/*
+ * lwpose_b200.h -- C ABI of the B200-native (sm_100a) Lightweight OpenPose inference hot path.
+ *
+ * The reference (vivek87799/lightweight-human-pose-estimation.pytorch) is pure Python and defines no
+ * FFI; every entry point below names the reference call it replaces (paths relative to the reference
+ * root).  INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library never allocates device
+ *     memory after lwp_plan_create / lwp_plan_add_* returned;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, they never synchronise;
+ *   - return value 0 = ok, otherwise an LWP_E* code; lwp_last_error() gives a thread-local message;
+ *   - activations are NHWC ("pixels x channels") inside the library; the public tensors at the module
+ *     boundary keep the reference's NCHW float32 layout.
+ */
+#ifndef LWPOSE_B200_H
+#define LWPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LWP_OK 0
+#define LWP_EINVAL 1   /* bad argument */
+#define LWP_ECUDA 2    /* CUDA runtime / driver error (see lwp_last_error) */
+#define LWP_ECAP 3     /* a capacity given by the caller is too small for the kernels' shared memory etc. */
+#define LWP_EARCH 4    /* device is not sm_100 */
+
+#define LWP_NUM_KPT_TYPES 18   /* Pose.num_kpts, modules/pose.py:9 */
+#define LWP_NUM_LIMBS 19       /* len(BODY_PARTS_PAF_IDS), modules/keypoints.py:7-8 */
+#define LWP_POSE_ENTRY 20      /* pose_entry_size, modules/keypoints.py:51 */
+
+/* element type of activations/weights inside a plan */
+#define LWP_DTYPE_BF16 0   /* bf16 storage, tcgen05 kind::f16, fp32 accumulate */
+#define LWP_DTYPE_TF32 1   /* fp32 storage, tcgen05 kind::tf32, fp32 accumulate ("fp32 mode") */
+
+/* epilogue activation */
+#define LWP_ACT_NONE 0
+#define LWP_ACT_RELU 1     /* nn.ReLU, modules/conv.py:9,17,21 */
+#define LWP_ACT_ELU 2      /* nn.ELU(alpha=1), modules/conv.py:28,31 */
+
+int lwp_version(void);
+const char *lwp_last_error(void);
+/* 0 if device `dev` can run this library (compute capability 10.x). */
+int lwp_check_device(int dev);
+
+/* ---------------------------------------------------------------------------------------------
+ * Post-processing
+ * ------------------------------------------------------------------------------------------- */
+
+/* One detected key-point: the tuple (x, y, score, id) that extract_keypoints appends
+ * (modules/keypoints.py:43-45). */
+typedef struct lwp_keypoint {
+  int32_t x;
+  int32_t y;
+  float score;
+  int32_t id; /* global id, consecutive over the 18 channels of one image (demo.py:95-98) */
+} lwp_keypoint;
+
+/*
+ * Replaces cv2.resize(maps, (0,0), fx=r, fy=r, INTER_CUBIC) at demo.py:72,76 / val.py:98,105 and
+ * cv2.resize(maps, (W,H), INTER_CUBIC) at val.py:100,107 -- bit-exact with OpenCV's float path.
+ * src: [n][h][w] pixels, `c` used channels per pixel, pixel stride src_ld floats.
+ * dst: [n][H][W][c] contiguous.  inv_scale_* is OpenCV's inv_scale: fx (fy) when the caller gives
+ * factors, (double)W / w ((double)H / h) when the caller gives dsize.
+ */
+int lwp_upsample_cubic(const float *src, int n, int h, int w, int c, int src_ld, float *dst, int H, int W,
+                       double inv_scale_x, double inv_scale_y, void *stream);
+
+/* bytes of scratch lwp_extract_keypoints needs */
+size_t lwp_extract_workspace_bytes(int n, int n_ch, int cap_candidates);
+
+/*
+ * Replaces the loop `for k in range(18): extract_keypoints(heatmaps[:, :, k], ...)`
+ * (demo.py:95-98, val.py:129-132; modules/keypoints.py:16-48) for n images at once.
+ * hm: [n][H][W] pixels, channels 0..n_ch-1 scanned, pixel stride ld floats (read only: the
+ *     reference's in-place threshold is re-done by the Python wrapper on its own host array).
+ * kpts: [n][n_ch][cap_kpts]; counts: [n][n_ch]; kpt_start: [n][n_ch+1] exclusive prefix of counts
+ * (global id of key-point j of channel c = kpt_start[c] + j).
+ * overflow: [n] ints, set non-zero when an image exceeded cap_candidates (peak candidates per channel
+ * before suppression) or cap_kpts (key-points per channel) -- results for that image are then invalid.
+ */
+int lwp_extract_keypoints(const float *hm, int n, int H, int W, int ld, int n_ch, lwp_keypoint *kpts,
+                          int32_t *counts, int32_t *kpt_start, int cap_kpts, int cap_candidates,
+                          void *workspace, size_t workspace_bytes, int32_t *overflow, void *stream);
+
+size_t lwp_group_workspace_bytes(int n, int cap_kpts, int cap_connections, int cap_poses);
+
+/*
+ * Replaces group_keypoints(all_keypoints_by_type, pafs, 20, min_paf_score, demo)
+ * (modules/keypoints.py:51-201) for n images at once.
+ * kpts/counts/kpt_start: as written by lwp_extract_keypoints (18 channels).
+ * pafs: [n][H][W] pixels x 38 used channels, pixel stride paf_ld floats (the UPSAMPLED maps).
+ * demo != 0: sample coordinates are truncated (demo.py:100 passes demo=True), else rounded half-to-even.
+ * pose_entries: [n][cap_poses][20] doubles (18 key-point ids or -1, [18] score, [19] count);
+ * n_poses: [n].  overflow: [n], non-zero when cap_connections / cap_poses was exceeded.
+ */
+int lwp_group_keypoints(const lwp_keypoint *kpts, const int32_t *counts, const int32_t *kpt_start, int cap_kpts,
+                        const float *pafs, int n, int H, int W, int paf_ld, int demo, double min_paf_score,
+                        double *pose_entries, int32_t *n_poses, int cap_poses, int cap_connections,
+                        void *workspace, size_t workspace_bytes, int32_t *overflow, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Network forward: a "plan" is a recorded list of layer launches with pre-built TMA descriptors
+ * for one (batch, height, width, dtype).  It replaces PoseEstimationWithMobileNet.forward
+ * (models/with_mobilenet.py:114-123); the layer list itself is built by the Python module mirror
+ * from the same state_dict the reference uses.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lwp_plan lwp_plan;
+
+int lwp_plan_create(int dtype, lwp_plan **out);
+void lwp_plan_destroy(lwp_plan *p);
+int lwp_plan_num_ops(const lwp_plan *p);
+
+/*
+ * Stem conv(3, 32, stride=2, bias=False) + BN + ReLU (models/with_mobilenet.py:93, modules/conv.py:4-10).
+ * Input is taken at run time (lwp_plan_run's x): NCHW float32 [n][3][H][W].
+ * w: [32][3][3][3] float32 (OIHW, as in the state_dict); scale/shift: folded BN, float32 [32].
+ * out: NHWC [n][H/2][W/2][32] of the plan dtype.
+ */
+int lwp_plan_add_stem(lwp_plan *p, const float *w, const float *scale, const float *shift, void *out, int n, int H,
+                      int W);
+
+/*
+ * Depthwise 3x3 conv (groups == channels, bias=False) + per-channel scale/shift + activation
+ * (modules/conv.py:15-17 conv_dw, :27-28 conv_dw_no_bn).  NHWC in / NHWC out, plan dtype.
+ * w: [C][3][3] float32; pad == dilation (the reference always uses padding=dilation for 3x3).
+ */
+int lwp_plan_add_depthwise(lwp_plan *p, const void *in, void *out, const float *w, const float *scale,
+                           const float *shift, int n, int H, int W, int C, int stride, int dilation, int act);
+
+/*
+ * Dense convolution as an implicit GEMM on tcgen05 tensor cores: 1x1 (taps == 1) or 3x3 (taps == 9,
+ * pad == dilation), stride 1 (modules/conv.py:4-10,19,30; models/with_mobilenet.py:10,16,28-38,51-54,74-79).
+ *   in : NHWC [n][H][W] pixels, Cin channels (multiple of the 128-byte K block), pixel stride in_ld elements
+ *   w  : [Cout_pad][taps][Cin] elements of the plan dtype, K-major (packed by the host mirror), Cout_pad
+ *        a multiple of 16
+ *   y = act(acc * scale[c] + shift[c]) (+ residual[pixel][c] if residual != NULL), c < Cout
+ *   out: plan dtype, pixel stride out_ld elements (may be NULL)
+ *   out_f32: optional float32 copy of the result, pixel stride out_f32_ld floats (heads feed the
+ *        post-processing in float32 whatever the plan dtype)
+ */
+int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, const void *w, const float *scale,
+                           const float *shift, const void *residual, int res_ld, void *out, int out_ld,
+                           float *out_f32, int out_f32_ld, int n, int H, int W, int Cin, int Cout, int taps,
+                           int dilation, int act);
+
+/* NHWC (plan dtype or float32) -> NCHW float32, for the tensors `forward` returns at the module boundary. */
+int lwp_plan_add_nhwc_to_nchw(lwp_plan *p, const void *in, int in_ld, int in_is_f32, int c0, int c, float *out, int n,
+                              int H, int W);
+
+/* Enqueue every recorded op on `stream`.  x: NCHW float32 input of the stem (may be NULL if no stem). */
+int lwp_plan_run(lwp_plan *p, const float *x, void *stream);
+/* Enqueue ops [first, last) only (per-layer timing / parity tests). */
+int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int last, void *stream);
+/* number of kernel launches one lwp_plan_run issues */
+int lwp_plan_num_launches(const lwp_plan *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LWPOSE_B200_H */

@@ -1,0 +1,42 @@
+// Error string, device queries and version of the lwpose_b200 C-ABI library.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace lwp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace lwp
+
+extern "C" int lwp_version(void) { return 100; }
+
+extern "C" const char *lwp_last_error(void) { return lwp::g_err; }
+
+extern "C" int lwp_check_device(int dev) {
+  int major = 0;
+  LWP_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    lwp::set_error("device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+    return LWP_EARCH;
+  }
+  return LWP_OK;
+}

@@ -1,0 +1,648 @@
+// Post-processing kernels: bit-exact cubic upsample, key-point extraction, PAF grouping.
+//
+// Everything here must produce the reference's bits, so all floating point goes through the
+// explicitly rounded intrinsics (__fmul_rn, __dadd_rn, ...) which nvcc never contracts into FMAs.
+//
+// Reference (paths relative to the reference root):
+//   upsample_cubic_kernel      cv2.resize INTER_CUBIC at demo.py:72,76; val.py:98-107
+//   peak_candidates_kernel,
+//   peak_nms_kernel,
+//   keypoint_ids_kernel        modules/keypoints.py:16-48 (extract_keypoints) + id bookkeeping demo.py:95-98
+//   paf_score_kernel           modules/keypoints.py:94-139 (line integral over the PAF)
+//   limb_match_kernel          modules/keypoints.py:140-157 (sort + greedy one-to-one assignment)
+//   pose_assemble_kernel       modules/keypoints.py:63-92,159-200 (sequential pose assembly + filter)
+#include "common.cuh"
+
+#include <float.h>
+#include <limits.h>
+
+namespace lwp {
+
+// modules/keypoints.py:5-8
+__constant__ int c_kpt_ids[LWP_NUM_LIMBS][2] = {
+    {1, 2}, {1, 5}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {1, 8}, {8, 9}, {9, 10}, {1, 11},
+    {11, 12}, {12, 13}, {1, 0}, {0, 14}, {14, 16}, {0, 15}, {15, 17}, {2, 16}, {5, 17}};
+__constant__ int c_paf_ids[LWP_NUM_LIMBS][2] = {
+    {12, 13}, {20, 21}, {14, 15}, {16, 17}, {22, 23}, {24, 25}, {0, 1}, {2, 3}, {4, 5},
+    {6, 7}, {8, 9}, {10, 11}, {28, 29}, {30, 31}, {34, 35}, {32, 33}, {36, 37}, {18, 19}, {26, 27}};
+
+// ------------------------------------------------------------------------------------------------
+// cubic upsample
+// ------------------------------------------------------------------------------------------------
+
+// OpenCV interpolateCubic(): A = -0.75, float, each operation rounded on its own.
+__device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
+  const float A = -0.75f;
+  float t1 = __fadd_rn(t, 1.f);
+  float v = __fsub_rn(__fmul_rn(A, t1), -3.75f);         // A*(t+1) - 5A
+  v = __fadd_rn(__fmul_rn(v, t1), -6.0f);                // (..)*(t+1) + 8A
+  c[0] = __fsub_rn(__fmul_rn(v, t1), -3.0f);             // (..)*(t+1) - 4A
+  v = __fsub_rn(__fmul_rn(1.25f, t), 2.25f);             // (A+2)*t - (A+3)
+  c[1] = __fadd_rn(__fmul_rn(__fmul_rn(v, t), t), 1.f);  // (..)*t*t + 1
+  float u = __fsub_rn(1.f, t);
+  v = __fsub_rn(__fmul_rn(1.25f, u), 2.25f);
+  c[2] = __fadd_rn(__fmul_rn(__fmul_rn(v, u), u), 1.f);
+  c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c[0]), c[1]), c[2]);
+}
+
+// source tap index (un-clamped, tap 1) and weights of destination coordinate d
+__device__ __forceinline__ int cubic_axis(int d, double scale, float c[4]) {
+  float f = __double2float_rn(__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5));
+  float fl = floorf(f);
+  cubic_coeffs(__fsub_rn(f, fl), c);
+  return (int)fl;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__global__ void __launch_bounds__(256)
+upsample_cubic_kernel(const float *__restrict__ src, int h, int w, int c, int src_ld, float *__restrict__ dst,
+                      int H, int W, double scale_x, double scale_y, long long total) {
+  const int rowlen = W * c;
+  const int body = rowlen - (rowlen & 3);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(idx % rowlen);
+    long long t = idx / rowlen;
+    int e = (int)(t % H);
+    int img = (int)(t / H);
+    int d = q / c, ch = q - d * c;
+    float cx[4], cy[4];
+    int sx = cubic_axis(d, scale_x, cx);
+    int sy = cubic_axis(e, scale_y, cy);
+    bool border = (sx < 1) || (sx + 2 >= w);
+    int i0 = clampi(sx - 1, 0, w - 1) * src_ld, i1 = clampi(sx, 0, w - 1) * src_ld;
+    int i2 = clampi(sx + 1, 0, w - 1) * src_ld, i3 = clampi(sx + 2, 0, w - 1) * src_ld;
+    float T[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int row = clampi(sy - 1 + r, 0, h - 1);
+      const float *p = src + ((size_t)img * h + row) * (size_t)w * src_ld + ch;
+      float p0 = __fmul_rn(__ldg(p + i0), cx[0]);
+      float p1 = __fmul_rn(__ldg(p + i1), cx[1]);
+      float p2 = __fmul_rn(__ldg(p + i2), cx[2]);
+      float p3 = __fmul_rn(__ldg(p + i3), cx[3]);
+      // HResizeCubic: border columns start from v = 0 and add the four products in turn
+      float v = border ? __fadd_rn(0.f, p0) : p0;
+      v = __fadd_rn(v, p1);
+      v = __fadd_rn(v, p2);
+      T[r] = __fadd_rn(v, p3);
+    }
+    float o;
+    if (q < body) {  // VResizeCubicVec_32f body: S0*b0 + (S1*b1 + (S2*b2 + S3*b3))
+      o = __fadd_rn(__fmul_rn(T[2], cy[2]), __fmul_rn(T[3], cy[3]));
+      o = __fadd_rn(__fmul_rn(T[1], cy[1]), o);
+      o = __fadd_rn(__fmul_rn(T[0], cy[0]), o);
+    } else {         // scalar tail: left to right
+      o = __fadd_rn(__fmul_rn(T[0], cy[0]), __fmul_rn(T[1], cy[1]));
+      o = __fadd_rn(o, __fmul_rn(T[2], cy[2]));
+      o = __fadd_rn(o, __fmul_rn(T[3], cy[3]));
+    }
+    dst[idx] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// extract_keypoints
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float thr01(float v) { return v < 0.1f ? 0.f : v; }  // heatmap[heatmap < 0.1] = 0
+
+// One thread per (pixel, channel): thresholded value strictly greater than its 4 axial neighbours
+// (zero outside the image).  Candidates go to an unordered per-(image, channel) list.
+__global__ void __launch_bounds__(256)
+peak_candidates_kernel(const float *__restrict__ hm, int H, int W, int ld, int n_ch,
+                       unsigned long long *__restrict__ cand, int *__restrict__ cand_count, int cap,
+                       long long total) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(idx % n_ch);
+    long long t = idx / n_ch;
+    int x = (int)(t % W);
+    t /= W;
+    int y = (int)(t % H);
+    int img = (int)(t / H);
+    const float *p = hm + (((size_t)img * H + y) * W + x) * (size_t)ld + ch;
+    float v = thr01(__ldg(p));
+    if (!(v > 0.f)) continue;  // a peak must beat neighbours that are >= 0
+    float l = x > 0 ? thr01(__ldg(p - ld)) : 0.f;
+    float r = x + 1 < W ? thr01(__ldg(p + ld)) : 0.f;
+    float u = y > 0 ? thr01(__ldg(p - (size_t)W * ld)) : 0.f;
+    float dn = y + 1 < H ? thr01(__ldg(p + (size_t)W * ld)) : 0.f;
+    if (v > l && v > r && v > u && v > dn) {
+      int slot = atomicAdd(&cand_count[img * n_ch + ch], 1);
+      if (slot < cap) {
+        unsigned long long key = ((unsigned long long)(((unsigned)x << 16) | (unsigned)y) << 32) | __float_as_uint(v);
+        cand[((size_t)img * n_ch + ch) * cap + slot] = key;
+      }
+    }
+  }
+}
+
+template <typename T, typename Less>
+__device__ void bitonic_sort_smem(T *a, int n_pow2, Less less) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          T x = a[i], y = a[ixj];
+          bool up = (i & k) == 0;
+          if (up ? less(y, x) : less(x, y)) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct U64Less {
+  __device__ bool operator()(unsigned long long a, unsigned long long b) const { return a < b; }
+};
+
+// One block per (image, channel): sort candidates by (x, y), greedy radius-6 suppression in that
+// order (suppressed points never suppress), emit survivors in order.
+__global__ void __launch_bounds__(256)
+peak_nms_kernel(const unsigned long long *__restrict__ cand, const int *__restrict__ cand_count, int cap_cand,
+                int n_ch, lwp_keypoint *__restrict__ kpts, int *__restrict__ counts, int cap_kpts,
+                int *__restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int slot = blockIdx.x;  // img * n_ch + ch
+  const int img = slot / n_ch;
+  int cnt = cand_count[slot];
+  if (cnt > cap_cand) {
+    if (threadIdx.x == 0) overflow[img] = 1;
+    cnt = cap_cand;
+  }
+  int P = 32;
+  while (P < cnt) P <<= 1;
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
+  unsigned char *sup = reinterpret_cast<unsigned char *>(keys + P);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    keys[i] = i < cnt ? cand[(size_t)slot * cap_cand + i] : ~0ull;
+    sup[i] = 0;
+  }
+  __syncthreads();
+  bitonic_sort_smem(keys, P, U64Less());
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  for (int i = 0; i < cnt; ++i) {
+    if (sup[i]) continue;  // warp-uniform: written before the last __syncwarp
+    unsigned ki = (unsigned)(keys[i] >> 32);
+    int xi = ki >> 16, yi = ki & 0xffff;
+    for (int j = i + 1 + lane; j < cnt; j += 32) {
+      unsigned kj = (unsigned)(keys[j] >> 32);
+      int dx = (int)(kj >> 16) - xi;
+      if (dx >= 6) break;  // sorted by x: nothing further can be within radius 6
+      int dy = (int)(kj & 0xffff) - yi;
+      if (dx * dx + dy * dy < 36) sup[j] = 1;
+    }
+    __syncwarp();
+  }
+  int out_n = 0;
+  lwp_keypoint *out = kpts + (size_t)slot * cap_kpts;
+  for (int base = 0; base < cnt; base += 32) {
+    int j = base + lane;
+    bool alive = j < cnt && !sup[j];
+    unsigned m = __ballot_sync(0xffffffffu, alive);
+    int pos = out_n + __popc(m & ((1u << lane) - 1));
+    if (alive && pos < cap_kpts) {
+      unsigned long long k = keys[j];
+      unsigned kk = (unsigned)(k >> 32);
+      lwp_keypoint kp;
+      kp.x = kk >> 16; kp.y = kk & 0xffff; kp.score = __uint_as_float((unsigned)k); kp.id = 0;
+      out[pos] = kp;
+    }
+    out_n += __popc(m);
+  }
+  if (lane == 0) {
+    if (out_n > cap_kpts) { overflow[img] = 1; out_n = cap_kpts; }
+    counts[slot] = out_n;
+  }
+}
+
+// One block per image: exclusive prefix of the per-channel counts, then global ids.
+__global__ void keypoint_ids_kernel(lwp_keypoint *__restrict__ kpts, const int *__restrict__ counts,
+                                    int *__restrict__ kpt_start, int n_ch, int cap_kpts) {
+  __shared__ int s_start[65];
+  const int img = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int c = 0; c < n_ch; ++c) { s_start[c] = acc; acc += counts[img * n_ch + c]; }
+    s_start[n_ch] = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c <= n_ch; c += blockDim.x) kpt_start[img * (n_ch + 1) + c] = s_start[c];
+  for (int c = 0; c < n_ch; ++c) {
+    int cnt = s_start[c + 1] - s_start[c];
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x)
+      kpts[((size_t)img * n_ch + c) * cap_kpts + j].id = s_start[c] + j;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// group_keypoints
+// ------------------------------------------------------------------------------------------------
+
+struct Conn {   // candidate connection of one limb: indices into the A / B key-point lists
+  double ratio;
+  int i, j;
+};
+struct Match {  // accepted connection: global key-point ids, their scores, the PAF ratio
+  double ratio;
+  int ida, idb;
+  float sa, sb;
+};
+
+struct ConnBefore {  // ratio descending; ties keep (i, j) generation order (stable sort, reverse=True)
+  __device__ bool operator()(const Conn &a, const Conn &b) const {
+    if (a.ratio > b.ratio) return true;
+    if (a.ratio < b.ratio) return false;
+    if (a.i != b.i) return a.i < b.i;
+    return a.j < b.j;
+  }
+};
+
+// PAF line integral: a warp scores 3 candidate pairs at a time, 10 lanes per pair, lane k takes
+// sample k of linspace2d; the sum is then re-done in k order so the float64 result is the
+// reference's.  grid = (blocks per limb, 19 limbs, images).
+__global__ void __launch_bounds__(256)
+paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ counts, int cap_kpts,
+                 const float *__restrict__ pafs, int H, int W, int ld, int demo, double min_paf_score,
+                 Conn *__restrict__ conn, int *__restrict__ conn_count, int cap_conn) {
+  const int limb = blockIdx.y, img = blockIdx.z;
+  const int ka = c_kpt_ids[limb][0], kb = c_kpt_ids[limb][1];
+  const int nA = counts[img * LWP_NUM_KPT_TYPES + ka], nB = counts[img * LWP_NUM_KPT_TYPES + kb];
+  if (nA == 0 || nB == 0) return;
+  const lwp_keypoint *A = kpts + ((size_t)img * LWP_NUM_KPT_TYPES + ka) * cap_kpts;
+  const lwp_keypoint *B = kpts + ((size_t)img * LWP_NUM_KPT_TYPES + kb) * cap_kpts;
+  const int cx = c_paf_ids[limb][0], cy = c_paf_ids[limb][1];
+  const float *paf = pafs + (size_t)img * H * W * ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int g = lane / 10, k = lane - g * 10;
+  const int total = nA * nB;
+  const double height_n = (double)(H / 2);  // pafs.shape[0] // 2
+  Conn *out = conn + ((size_t)img * LWP_NUM_LIMBS + limb) * cap_conn;
+  int *out_count = conn_count + img * LWP_NUM_LIMBS + limb;
+
+  for (int base = (blockIdx.x * wpb + warp) * 3; base < total; base += gridDim.x * wpb * 3) {
+    const int p = base + g;
+    const bool active = g < 3 && p < total;
+    int i = 0, j = 0;
+    double v = 0.0, ux = 0.0, uy = 0.0, norm = 0.0;
+    bool pass = false;
+    if (active) {
+      i = p / nB; j = p - i * nB;
+      lwp_keypoint a = A[i], b = B[j];
+      int vx = b.x - a.x, vy = b.y - a.y;
+      norm = __dsqrt_rn((double)((long long)vx * vx + (long long)vy * vy));
+      if (norm != 0.0) {
+        ux = __ddiv_rn((double)vx, norm);
+        uy = __ddiv_rn((double)vy, norm);
+        double fx = __dadd_rn(__dmul_rn(__dmul_rn(1.0 / 9, (double)vx), (double)k), (double)a.x);
+        double fy = __dadd_rn(__dmul_rn(__dmul_rn(1.0 / 9, (double)vy), (double)k), (double)a.y);
+        int ix = demo ? __double2int_rz(fx) : __double2int_rn(fx);
+        int iy = demo ? __double2int_rz(fy) : __double2int_rn(fy);
+        const float *pp = paf + ((size_t)iy * W + ix) * ld;
+        v = __dadd_rn(__dmul_rn(ux, (double)__ldg(pp + cx)), __dmul_rn(uy, (double)__ldg(pp + cy)));
+        pass = v > min_paf_score;
+      }
+    }
+    double sum = 0.0;
+    int cnt = 0;
+#pragma unroll
+    for (int kk = 0; kk < 10; ++kk) {
+      int srcl = (g * 10 + kk) & 31;
+      double vk = __shfl_sync(0xffffffffu, v, srcl);
+      int pk = __shfl_sync(0xffffffffu, (int)pass, srcl);
+      if (pk) { sum = __dadd_rn(sum, vk); ++cnt; }
+    }
+    if (active && k == 0 && norm != 0.0) {
+      double ratio = cnt > 0 ? __ddiv_rn(sum, (double)cnt) : 0.0;
+      double pen = __dsub_rn(__ddiv_rn(height_n, norm), 1.0);
+      if (pen < 0.0) ratio = __dadd_rn(ratio, pen);
+      if (ratio > 0.0 && cnt >= 9) {  // success_ratio = cnt / 10 > 0.8
+        int slot = atomicAdd(out_count, 1);
+        if (slot < cap_conn) { Conn c; c.ratio = ratio; c.i = i; c.j = j; out[slot] = c; }
+      }
+    }
+  }
+}
+
+// One block per (limb, image): order the candidate connections, then greedy one-to-one matching
+// with warp ballots.  grid = (19, images).
+__global__ void __launch_bounds__(256)
+limb_match_kernel(const Conn *__restrict__ conn, const int *__restrict__ conn_count, int cap_conn,
+                  const lwp_keypoint *__restrict__ kpts, const int *__restrict__ counts,
+                  const int *__restrict__ kpt_start, int cap_kpts, Match *__restrict__ match,
+                  int *__restrict__ match_count, int *__restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int limb = blockIdx.x, img = blockIdx.y;
+  const int slot = img * LWP_NUM_LIMBS + limb;
+  const int ka = c_kpt_ids[limb][0], kb = c_kpt_ids[limb][1];
+  const int nA = counts[img * LWP_NUM_KPT_TYPES + ka], nB = counts[img * LWP_NUM_KPT_TYPES + kb];
+  int cnt = (nA == 0 || nB == 0) ? 0 : conn_count[slot];
+  if (cnt > cap_conn) {
+    if (threadIdx.x == 0) overflow[img] = 1;
+    cnt = cap_conn;
+  }
+  if (cnt == 0) {
+    if (threadIdx.x == 0) match_count[slot] = 0;
+    return;
+  }
+  int P = 32;
+  while (P < cnt) P <<= 1;
+  Conn *cs = reinterpret_cast<Conn *>(smem_raw);
+  unsigned char *usedA = reinterpret_cast<unsigned char *>(cs + P);
+  unsigned char *usedB = usedA + cap_kpts;
+  for (int t = threadIdx.x; t < P; t += blockDim.x) {
+    Conn c;
+    if (t < cnt) c = conn[(size_t)slot * cap_conn + t];
+    else { c.ratio = -DBL_MAX; c.i = INT_MAX; c.j = INT_MAX; }
+    cs[t] = c;
+  }
+  for (int t = threadIdx.x; t < cap_kpts; t += blockDim.x) { usedA[t] = 0; usedB[t] = 0; }
+  __syncthreads();
+  bitonic_sort_smem(cs, P, ConnBefore());
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  const lwp_keypoint *A = kpts + ((size_t)img * LWP_NUM_KPT_TYPES + ka) * cap_kpts;
+  const lwp_keypoint *B = kpts + ((size_t)img * LWP_NUM_KPT_TYPES + kb) * cap_kpts;
+  const int a0 = kpt_start[img * (LWP_NUM_KPT_TYPES + 1) + ka], b0 = kpt_start[img * (LWP_NUM_KPT_TYPES + 1) + kb];
+  Match *out = match + (size_t)slot * cap_kpts;
+  const int limit = nA < nB ? nA : nB;
+  int accepted = 0;
+  for (int base = 0; base < cnt && accepted < limit; base += 32) {
+    int idx = base + lane;
+    bool valid = idx < cnt;
+    Conn c;
+    c.ratio = 0; c.i = 0; c.j = 0;
+    if (valid) c = cs[idx];
+    bool freeij = valid && !usedA[c.i] && !usedB[c.j];
+    unsigned m = __ballot_sync(0xffffffffu, freeij);
+    while (m != 0 && accepted < limit) {
+      int b = __ffs(m) - 1;
+      m &= m - 1;
+      int ok = 0;
+      if (lane == b) ok = !usedA[c.i] && !usedB[c.j];  // earlier lanes of this chunk may have taken i or j
+      ok = __shfl_sync(0xffffffffu, ok, b);
+      if (ok) {
+        if (lane == b) {
+          usedA[c.i] = 1; usedB[c.j] = 1;
+          Match mt;
+          mt.ratio = c.ratio; mt.ida = a0 + c.i; mt.idb = b0 + c.j;
+          mt.sa = A[c.i].score; mt.sb = B[c.j].score;
+          out[accepted] = mt;
+        }
+        ++accepted;
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) match_count[slot] = accepted;
+}
+
+// One warp per image walks the 19 limbs in table order and builds the pose entries exactly like the
+// reference's sequential code; lanes parallelise the "for every pose" scans.
+__global__ void __launch_bounds__(32)
+pose_assemble_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ counts,
+                     const int *__restrict__ kpt_start, int cap_kpts, const Match *__restrict__ match,
+                     const int *__restrict__ match_count, double *__restrict__ scratch,
+                     double *__restrict__ pose_entries, int *__restrict__ n_poses, int cap_poses,
+                     int *__restrict__ overflow) {
+  const int img = blockIdx.x, lane = threadIdx.x;
+  double *poses = scratch + (size_t)img * cap_poses * LWP_POSE_ENTRY;
+#define POSE(jj) (poses + (size_t)(jj) * LWP_POSE_ENTRY)
+  int np = 0;
+  bool ovf = false;
+  const int *cnts = counts + img * LWP_NUM_KPT_TYPES;
+  const int *starts = kpt_start + img * (LWP_NUM_KPT_TYPES + 1);
+
+  // append a pose holding up to two key-points; all lanes call it, lanes 0..19 write one field each
+  auto append = [&](int slot_a, double id_a, int slot_b, double id_b, double score, double count) {
+    if (np >= cap_poses) { ovf = true; return; }
+    if (lane < LWP_POSE_ENTRY) {
+      double v = -1.0;
+      if (lane == slot_a) v = id_a;
+      if (lane == slot_b) v = id_b;
+      if (lane == 18) v = score;
+      if (lane == 19) v = count;
+      POSE(np)[lane] = v;
+    }
+    ++np;
+    __syncwarp();
+  };
+
+  for (int limb = 0; limb < LWP_NUM_LIMBS; ++limb) {
+    const int ka = c_kpt_ids[limb][0], kb = c_kpt_ids[limb][1];
+    const int nA = cnts[ka], nB = cnts[kb];
+    if (nA == 0 && nB == 0) continue;
+    if (nA == 0 || nB == 0) {  // :66-92 singleton poses for key-points no pose holds yet
+      const int slot = nA == 0 ? kb : ka, cnt = nA == 0 ? nB : nA;
+      const lwp_keypoint *K = kpts + ((size_t)img * LWP_NUM_KPT_TYPES + slot) * cap_kpts;
+      for (int i = 0; i < cnt; ++i) {
+        double id = (double)(starts[slot] + i);
+        bool found = false;
+        for (int j = lane; j < np; j += 32) found |= (POSE(j)[slot] == id);
+        if (!__any_sync(0xffffffffu, found)) append(slot, id, -1, 0.0, (double)K[i].score, 1.0);
+      }
+      continue;
+    }
+    const int m = match_count[img * LWP_NUM_LIMBS + limb];
+    if (m == 0) continue;
+    const Match *M = match + ((size_t)img * LWP_NUM_LIMBS + limb) * cap_kpts;
+    if (limb == 0) {  // :159-165 replaces the list
+      np = 0;
+      for (int c = 0; c < m; ++c) {
+        Match mt = M[c];
+        append(ka, (double)mt.ida, kb, (double)mt.idb,
+               __dadd_rn(__dadd_rn((double)mt.sa, (double)mt.sb), mt.ratio), 2.0);
+      }
+    } else if (limb == 17 || limb == 18) {  // :166-175
+      for (int c = 0; c < m; ++c) {
+        Match mt = M[c];
+        double ia = (double)mt.ida, ib = (double)mt.idb;
+        for (int j = lane; j < np; j += 32) {
+          double *p = POSE(j);
+          if (p[ka] == ia && p[kb] == -1.0) p[kb] = ib;
+          else if (p[kb] == ib && p[ka] == -1.0) p[ka] = ia;
+        }
+        __syncwarp();
+      }
+    } else {  // :176-193
+      for (int c = 0; c < m; ++c) {
+        Match mt = M[c];
+        double ia = (double)mt.ida, ib = (double)mt.idb;
+        bool found = false;
+        for (int j = lane; j < np; j += 32) {
+          double *p = POSE(j);
+          if (p[ka] == ia) {
+            p[kb] = ib;
+            p[19] = __dadd_rn(p[19], 1.0);
+            p[18] = __dadd_rn(p[18], __dadd_rn((double)mt.sb, mt.ratio));
+            found = true;
+          }
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, found))
+          append(ka, ia, kb, ib, __dadd_rn(__dadd_rn((double)mt.sa, (double)mt.sb), mt.ratio), 2.0);
+      }
+    }
+  }
+  __syncwarp();
+  // :195-200 final filter, order preserved
+  double *outp = pose_entries + (size_t)img * cap_poses * LWP_POSE_ENTRY;
+  int kept = 0;
+  for (int base = 0; base < np; base += 32) {
+    int j = base + lane;
+    bool keep = false;
+    if (j < np) {
+      double cnt = POSE(j)[19], sc = POSE(j)[18];
+      keep = !(cnt < 3.0 || __ddiv_rn(sc, cnt) < 0.2);
+    }
+    unsigned mk = __ballot_sync(0xffffffffu, keep);
+    int pos = kept + __popc(mk & ((1u << lane) - 1));
+    if (keep)
+      for (int q = 0; q < LWP_POSE_ENTRY; ++q) outp[(size_t)pos * LWP_POSE_ENTRY + q] = POSE(j)[q];
+    kept += __popc(mk);
+  }
+  if (lane == 0) {
+    n_poses[img] = kept;
+    if (ovf) overflow[img] = 1;
+  }
+#undef POSE
+}
+
+static int grid_for(long long total, int block) {
+  long long b = (total + block - 1) / block;
+  long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+static int next_pow2(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace lwp
+
+using namespace lwp;
+
+extern "C" int lwp_upsample_cubic(const float *src, int n, int h, int w, int c, int src_ld, float *dst, int H, int W,
+                                  double inv_scale_x, double inv_scale_y, void *stream) {
+  LWP_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c > 0 && src_ld >= c && H > 0 && W > 0,
+              "lwp_upsample_cubic: bad shape");
+  LWP_REQUIRE(inv_scale_x > 0 && inv_scale_y > 0, "lwp_upsample_cubic: bad scale");
+  long long total = (long long)n * H * W * c;
+  LWP_REQUIRE((long long)W * c < INT_MAX, "lwp_upsample_cubic: row too long");
+  double sx = 1. / inv_scale_x, sy = 1. / inv_scale_y;
+  upsample_cubic_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, h, w, c, src_ld, dst, H, W, sx,
+                                                                                sy, total);
+  LWP_LAUNCH_CHECK();
+  return LWP_OK;
+}
+
+extern "C" size_t lwp_extract_workspace_bytes(int n, int n_ch, int cap_candidates) {
+  size_t slots = (size_t)n * n_ch;
+  return align_up(slots * sizeof(int), 256) + slots * (size_t)cap_candidates * sizeof(unsigned long long);
+}
+
+extern "C" int lwp_extract_keypoints(const float *hm, int n, int H, int W, int ld, int n_ch, lwp_keypoint *kpts,
+                                     int32_t *counts, int32_t *kpt_start, int cap_kpts, int cap_candidates,
+                                     void *workspace, size_t workspace_bytes, int32_t *overflow, void *stream) {
+  LWP_REQUIRE(hm && kpts && counts && kpt_start && workspace && overflow, "lwp_extract_keypoints: null pointer");
+  LWP_REQUIRE(n > 0 && H > 0 && W > 0 && H < 65536 && W < 65536 && n_ch > 0 && n_ch <= 64 && ld >= n_ch,
+              "lwp_extract_keypoints: bad shape");
+  LWP_REQUIRE(cap_kpts > 0 && cap_candidates >= cap_kpts, "lwp_extract_keypoints: bad capacities");
+  LWP_REQUIRE(workspace_bytes >= lwp_extract_workspace_bytes(n, n_ch, cap_candidates),
+              "lwp_extract_keypoints: workspace too small");
+  size_t smem = (size_t)next_pow2(cap_candidates) * 9;
+  if (smem > 200 * 1024) { set_error("lwp_extract_keypoints: cap_candidates %d too large", cap_candidates); return LWP_ECAP; }
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t slots = (size_t)n * n_ch;
+  int *cand_count = (int *)workspace;
+  unsigned long long *cand = (unsigned long long *)((char *)workspace + align_up(slots * sizeof(int), 256));
+  LWP_CUDA_CHECK(cudaMemsetAsync(cand_count, 0, slots * sizeof(int), st));
+  LWP_CUDA_CHECK(cudaMemsetAsync(overflow, 0, (size_t)n * sizeof(int), st));
+  long long total = (long long)n * H * W * n_ch;
+  peak_candidates_kernel<<<grid_for(total, 256), 256, 0, st>>>(hm, H, W, ld, n_ch, cand, cand_count, cap_candidates,
+                                                               total);
+  LWP_LAUNCH_CHECK();
+  static bool attr_set = false;
+  if (!attr_set) {
+    LWP_CUDA_CHECK(cudaFuncSetAttribute(peak_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  peak_nms_kernel<<<(unsigned)slots, 256, smem, st>>>(cand, cand_count, cap_candidates, n_ch, kpts, counts, cap_kpts,
+                                                      overflow);
+  LWP_LAUNCH_CHECK();
+  keypoint_ids_kernel<<<n, 128, 0, st>>>(kpts, counts, kpt_start, n_ch, cap_kpts);
+  LWP_LAUNCH_CHECK();
+  return LWP_OK;
+}
+
+namespace {
+struct GroupWs {
+  int *conn_count;
+  int *match_count;
+  Conn *conn;
+  Match *match;
+  double *poses;
+  size_t bytes;
+};
+GroupWs carve_group_ws(void *base, int n, int cap_kpts, int cap_conn, int cap_poses) {
+  GroupWs w;
+  size_t off = 0;
+  size_t slots = (size_t)n * LWP_NUM_LIMBS;
+  char *b = (char *)base;
+  w.conn_count = (int *)(b + off); off += align_up(slots * sizeof(int), 256);
+  w.match_count = (int *)(b + off); off += align_up(slots * sizeof(int), 256);
+  w.conn = (Conn *)(b + off); off += align_up(slots * (size_t)cap_conn * sizeof(Conn), 256);
+  w.match = (Match *)(b + off); off += align_up(slots * (size_t)cap_kpts * sizeof(Match), 256);
+  w.poses = (double *)(b + off); off += align_up((size_t)n * cap_poses * LWP_POSE_ENTRY * sizeof(double), 256);
+  w.bytes = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t lwp_group_workspace_bytes(int n, int cap_kpts, int cap_connections, int cap_poses) {
+  return carve_group_ws(nullptr, n, cap_kpts, cap_connections, cap_poses).bytes;
+}
+
+extern "C" int lwp_group_keypoints(const lwp_keypoint *kpts, const int32_t *counts, const int32_t *kpt_start,
+                                   int cap_kpts, const float *pafs, int n, int H, int W, int paf_ld, int demo,
+                                   double min_paf_score, double *pose_entries, int32_t *n_poses, int cap_poses,
+                                   int cap_connections, void *workspace, size_t workspace_bytes, int32_t *overflow,
+                                   void *stream) {
+  LWP_REQUIRE(kpts && counts && kpt_start && pafs && pose_entries && n_poses && workspace && overflow,
+              "lwp_group_keypoints: null pointer");
+  LWP_REQUIRE(n > 0 && H > 0 && W > 0 && paf_ld >= 38 && cap_kpts > 0 && cap_poses > 0 && cap_connections > 0,
+              "lwp_group_keypoints: bad shape");
+  LWP_REQUIRE(workspace_bytes >= lwp_group_workspace_bytes(n, cap_kpts, cap_connections, cap_poses),
+              "lwp_group_keypoints: workspace too small");
+  size_t smem = (size_t)next_pow2(cap_connections) * sizeof(Conn) + 2 * (size_t)cap_kpts;
+  if (smem > 200 * 1024) { set_error("lwp_group_keypoints: cap_connections %d too large", cap_connections); return LWP_ECAP; }
+  cudaStream_t st = (cudaStream_t)stream;
+  GroupWs w = carve_group_ws(workspace, n, cap_kpts, cap_connections, cap_poses);
+  LWP_CUDA_CHECK(cudaMemsetAsync(w.conn_count, 0, (size_t)n * LWP_NUM_LIMBS * sizeof(int), st));
+  int bx = 1184 / (LWP_NUM_LIMBS * n);
+  bx = bx < 2 ? 2 : (bx > 32 ? 32 : bx);
+  paf_score_kernel<<<dim3(bx, LWP_NUM_LIMBS, n), 256, 0, st>>>(kpts, counts, cap_kpts, pafs, H, W, paf_ld, demo,
+                                                               min_paf_score, w.conn, w.conn_count, cap_connections);
+  LWP_LAUNCH_CHECK();
+  static bool attr_set = false;
+  if (!attr_set) {
+    LWP_CUDA_CHECK(cudaFuncSetAttribute(limb_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  limb_match_kernel<<<dim3(LWP_NUM_LIMBS, n), 256, smem, st>>>(w.conn, w.conn_count, cap_connections, kpts, counts,
+                                                              kpt_start, cap_kpts, w.match, w.match_count, overflow);
+  LWP_LAUNCH_CHECK();
+  pose_assemble_kernel<<<n, 32, 0, st>>>(kpts, counts, kpt_start, cap_kpts, w.match, w.match_count, w.poses,
+                                         pose_entries, n_poses, cap_poses, overflow);
+  LWP_LAUNCH_CHECK();
+  return LWP_OK;
+}

@@ -1,0 +1,134 @@
+"""Batched device API of the post-processing half of the hot path (torch tensors on cuda in, torch
+tensors on cuda out; all compute in the C-ABI kernels of csrc/postproc.cu).
+
+  upsample_cubic              cv2.resize(..., INTER_CUBIC)  (reference demo.py:72,76; val.py:98-107)
+  extract_keypoints_batched   18 x extract_keypoints        (reference modules/keypoints.py:16-48)
+  group_keypoints_batched     group_keypoints               (reference modules/keypoints.py:51-201)
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+NUM_KPT_TYPES = 18
+NUM_LIMBS = 19
+POSE_ENTRY = 20
+
+
+class CapacityOverflow(_lib.LwpError):
+    """A fixed-capacity device buffer was too small for some image; results for it are invalid."""
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def upsample_cubic(src, channels=None, fx=None, fy=None, dsize=None, out=None):
+    """src: float32 cuda tensor [n, h, w, ld] (NHWC, `channels` <= ld used).  Either fx/fy (like
+    cv2.resize(src, (0, 0), fx=, fy=)) or dsize=(W, H).  Returns [n, H, W, channels] float32."""
+    L = _lib.load()
+    assert src.is_cuda and src.dtype == torch.float32 and src.dim() == 4 and src.is_contiguous()
+    n, h, w, ld = src.shape
+    c = ld if channels is None else int(channels)
+    if dsize is None:
+        inv_x, inv_y = float(fx), float(fy)
+        W, H = int(np.rint(w * inv_x)), int(np.rint(h * inv_y))
+    else:
+        W, H = int(dsize[0]), int(dsize[1])
+        inv_x, inv_y = W / w, H / h
+    if out is None:
+        out = torch.empty((n, H, W, c), dtype=torch.float32, device=src.device)
+    else:
+        assert out.shape == (n, H, W, c) and out.is_contiguous() and out.dtype == torch.float32
+    _lib.check(L.lwp_upsample_cubic(_ptr(src), n, h, w, c, ld, _ptr(out), H, W, inv_x, inv_y, _lib.current_stream()),
+               "lwp_upsample_cubic")
+    return out
+
+
+class KeypointBatch:
+    """Device-side result of extract_keypoints_batched."""
+
+    def __init__(self, n, n_ch, cap_kpts, device):
+        self.n, self.n_ch, self.cap_kpts = n, n_ch, cap_kpts
+        self.kpts = torch.empty((n, n_ch, cap_kpts, 4), dtype=torch.int32, device=device)  # lwp_keypoint
+        self.counts = torch.empty((n, n_ch), dtype=torch.int32, device=device)
+        self.kpt_start = torch.empty((n, n_ch + 1), dtype=torch.int32, device=device)
+        self.overflow = torch.zeros((n,), dtype=torch.int32, device=device)
+
+    def to_host(self):
+        """(kpts int32 [n,n_ch,cap,4] with column 2 = float32 bits, counts, kpt_start, overflow) as numpy."""
+        return (self.kpts.cpu().numpy(), self.counts.cpu().numpy(), self.kpt_start.cpu().numpy(),
+                self.overflow.cpu().numpy())
+
+
+def keypoint_lists(kpts_h, counts_h, kpt_start_h, img):
+    """Rebuild the reference's all_keypoints_by_type for image `img`: per channel a list of
+    (np.int64 x, np.int64 y, np.float32 score, int id) tuples (modules/keypoints.py:43-47)."""
+    out = []
+    n_ch = counts_h.shape[1]
+    for c in range(n_ch):
+        cnt = int(counts_h[img, c])
+        rows = kpts_h[img, c, :cnt]
+        scores = rows[:, 2].copy().view(np.float32)
+        base = int(kpt_start_h[img, c])
+        out.append([(np.int64(rows[j, 0]), np.int64(rows[j, 1]), scores[j], base + j) for j in range(cnt)])
+    return out
+
+
+def extract_keypoints_batched(hm, n_ch=NUM_KPT_TYPES, cap_kpts=128, cap_candidates=2048, workspace=None, out=None):
+    """hm: float32 cuda [n, H, W, ld]; channels 0..n_ch-1 are scanned.  Returns a KeypointBatch.
+    The caller must check `overflow` (see `raise_on_overflow`)."""
+    L = _lib.load()
+    assert hm.is_cuda and hm.dtype == torch.float32 and hm.dim() == 4 and hm.is_contiguous()
+    n, H, W, ld = hm.shape
+    kb = out if out is not None else KeypointBatch(n, n_ch, cap_kpts, hm.device)
+    assert kb.n == n and kb.n_ch == n_ch and kb.cap_kpts == cap_kpts
+    ws_bytes = L.lwp_extract_workspace_bytes(n, n_ch, cap_candidates)
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=hm.device)
+    _lib.check(L.lwp_extract_keypoints(_ptr(hm), n, H, W, ld, n_ch, _ptr(kb.kpts), _ptr(kb.counts),
+                                       _ptr(kb.kpt_start), cap_kpts, cap_candidates, _ptr(workspace),
+                                       workspace.numel(), _ptr(kb.overflow), _lib.current_stream()),
+               "lwp_extract_keypoints")
+    kb._ws = workspace  # keep alive until the stream has consumed it
+    return kb
+
+
+def group_keypoints_batched(kb, pafs, demo=False, min_paf_score=0.05, cap_poses=128, cap_connections=2048,
+                            workspace=None, out=None):
+    """kb: KeypointBatch with 18 channels; pafs: float32 cuda [n, H, W, ld>=38] (up-sampled).
+    Returns (pose_entries float64 [n, cap_poses, 20], n_poses int32 [n]); overflow is OR-ed into kb.overflow."""
+    L = _lib.load()
+    assert kb.n_ch == NUM_KPT_TYPES
+    assert pafs.is_cuda and pafs.dtype == torch.float32 and pafs.dim() == 4 and pafs.is_contiguous()
+    n, H, W, ld = pafs.shape
+    assert n == kb.n
+    if out is None:
+        pose_entries = torch.empty((n, cap_poses, POSE_ENTRY), dtype=torch.float64, device=pafs.device)
+        n_poses = torch.empty((n,), dtype=torch.int32, device=pafs.device)
+    else:
+        pose_entries, n_poses = out
+    ws_bytes = L.lwp_group_workspace_bytes(n, kb.cap_kpts, cap_connections, cap_poses)
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=pafs.device)
+    _lib.check(L.lwp_group_keypoints(_ptr(kb.kpts), _ptr(kb.counts), _ptr(kb.kpt_start), kb.cap_kpts, _ptr(pafs), n,
+                                     H, W, ld, int(bool(demo)), float(min_paf_score), _ptr(pose_entries),
+                                     _ptr(n_poses), cap_poses, cap_connections, _ptr(workspace), workspace.numel(),
+                                     _ptr(kb.overflow), _lib.current_stream()),
+               "lwp_group_keypoints")
+    kb._gws = workspace
+    return pose_entries, n_poses
+
+
+def raise_on_overflow(overflow_h):
+    bad = np.nonzero(np.asarray(overflow_h))[0]
+    if bad.size:
+        raise CapacityOverflow("capacity exceeded for image(s) %s; raise cap_kpts / cap_candidates / "
+                               "cap_connections / cap_poses" % bad.tolist()[:8])
+
+
+def pose_entries_array(pose_entries_h, n_poses_h, img):
+    """The reference's return value: float64 [P, 20], or shape (0,) when no pose survives
+    (np.asarray([]) at modules/keypoints.py:200)."""
+    cnt = int(n_poses_h[img])
+    return np.asarray([pose_entries_h[img, j].copy() for j in range(cnt)])

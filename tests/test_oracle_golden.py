@@ -1,0 +1,102 @@
+"""Pins the oracle (oracle/) to the reference: golden vectors made by the real reference + cv2
+(tests/golden/make_golden.py), and -- when /root/reference is present -- the live reference on extra
+seeded inputs.  CPU only."""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+import refimport
+from oracle import postproc as orc
+
+
+@pytest.mark.parametrize("idx,case", gc.resize_cases())
+def test_resize_matches_cv2_golden(idx, case):
+    g = gc.load("resize_golden.npz")
+    h, w, C, mode, arg = case
+    src = gc.resize_input(idx, h, w, C)
+    dst = orc.resize_cubic(src, fx=arg, fy=arg) if mode == "f" else orc.resize_cubic(src, dsize=tuple(arg))
+    assert tuple(dst.shape) == tuple(g["resize_%d_shape" % idx])
+    assert gc.sha(dst) == str(g["resize_%d_sha" % idx])
+    key = "resize_%d_out" % idx
+    if key in g:
+        assert np.array_equal(dst.view(np.int32), g[key].view(np.int32))
+
+
+def _oracle_postproc(hm, paf, demo):
+    heat = orc.resize_cubic(np.ascontiguousarray(hm.transpose(1, 2, 0)), fx=4, fy=4)
+    pafs = orc.resize_cubic(np.ascontiguousarray(paf.transpose(1, 2, 0)), fx=4, fy=4)
+    total, by_type = 0, []
+    for k in range(18):
+        total += orc.extract_keypoints(heat[:, :, k], by_type, total)
+    poses, allk = orc.group_keypoints(by_type, pafs, demo=demo)
+    return by_type, poses, allk
+
+
+@pytest.mark.parametrize("case", gc.postproc_cases(), ids=lambda c: c[0])
+@pytest.mark.parametrize("demo", [True, False])
+def test_postproc_matches_reference_golden(case, demo):
+    g = gc.load("postproc_golden.npz")
+    hm, paf = gc.postproc_maps(case)
+    assert gc.sha(hm) + gc.sha(paf) == str(g["pp_%s_in_sha" % case[0]]), "synthetic generator drifted"
+    by_type, poses, allk = _oracle_postproc(hm, paf, demo)
+    tag = "pp_%s_%s" % (case[0], "demo" if demo else "val")
+    assert np.array_equal(gc.pack_keypoints(by_type), g[tag + "_kpts"])
+    poses = np.asarray(poses, np.float64).reshape(-1, 20)
+    assert poses.shape == g[tag + "_poses"].shape
+    assert np.array_equal(poses.view(np.int64), g[tag + "_poses"].view(np.int64))
+    allk = np.asarray(allk, np.float64).reshape(-1, 4)
+    assert np.array_equal(allk.view(np.int64), g[tag + "_allk"].view(np.int64))
+
+
+def test_empty_outputs_have_reference_shapes():
+    hm = np.zeros((19, 8, 8), np.float32)
+    paf = np.zeros((38, 8, 8), np.float32)
+    by_type, poses, allk = _oracle_postproc(hm, paf, True)
+    assert [len(l) for l in by_type] == [0] * 18
+    assert poses.shape == (0,) and allk.shape == (0,)
+
+
+@pytest.mark.skipif(not refimport.available(), reason="live reference not present (GPU box)")
+@pytest.mark.parametrize("seed", range(6))
+def test_postproc_matches_live_reference(seed):
+    import cv2
+    from lwpose_b200 import synth
+    ref = refimport.load()
+    rng = np.random.default_rng(seed)
+    persons = int(rng.integers(0, 7))
+    hm, paf, _ = synth.synthetic_pose_maps(1, 24, 31, seed=100 + seed, noise=float(rng.uniform(0, 0.08)),
+                                           persons=persons)
+    hm, paf = hm[0], paf[0]
+    for demo in (True, False):
+        heat = cv2.resize(np.ascontiguousarray(hm.transpose(1, 2, 0)), (0, 0), fx=4, fy=4,
+                          interpolation=cv2.INTER_CUBIC)
+        pafs = cv2.resize(np.ascontiguousarray(paf.transpose(1, 2, 0)), (0, 0), fx=4, fy=4,
+                          interpolation=cv2.INTER_CUBIC)
+        total, ref_by_type = 0, []
+        for k in range(18):
+            total += ref.keypoints.extract_keypoints(heat[:, :, k], ref_by_type, total)
+        ref_poses, ref_allk = ref.keypoints.group_keypoints(ref_by_type, pafs, demo=demo)
+        by_type, poses, allk = _oracle_postproc(hm, paf, demo)
+        assert np.array_equal(gc.pack_keypoints(by_type), gc.pack_keypoints(ref_by_type))
+        assert np.asarray(poses).shape == np.asarray(ref_poses).shape
+        assert np.array_equal(np.asarray(poses, np.float64).view(np.int64),
+                              np.asarray(ref_poses, np.float64).view(np.int64))
+
+
+@pytest.mark.skipif(not refimport.available(), reason="live cv2 cross-check runs in the build container")
+@pytest.mark.parametrize("seed", range(12))
+def test_resize_matches_live_cv2(seed):
+    import cv2
+    rng = np.random.default_rng(seed)
+    h, w, C = int(rng.integers(3, 40)), int(rng.integers(3, 40)), int(rng.choice([2, 5, 6, 7, 19, 38]))
+    src = rng.standard_normal((h, w, C)).astype(np.float32)
+    if seed % 2:
+        W, H = int(rng.integers(w, 4 * w)), int(rng.integers(h, 4 * h))
+        ref = cv2.resize(src, (W, H), interpolation=cv2.INTER_CUBIC)
+        got = orc.resize_cubic(src, dsize=(W, H))
+    else:
+        f = float(rng.choice([2, 3, 4, 8, 1.5]))
+        ref = cv2.resize(src, (0, 0), fx=f, fy=f, interpolation=cv2.INTER_CUBIC)
+        got = orc.resize_cubic(src, fx=f, fy=f)
+    ref = ref.reshape(got.shape)
+    assert np.array_equal(got.view(np.int32), ref.view(np.int32)), (h, w, C, got.shape)
