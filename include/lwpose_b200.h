@@ -128,7 +128,8 @@ int lwp_plan_add_stem(lwp_plan *p, const float *w, const float *scale, const flo
 /*
  * Depthwise 3x3 conv (groups == channels, bias=False) + per-channel scale/shift + activation
  * (modules/conv.py:15-17 conv_dw, :27-28 conv_dw_no_bn).  NHWC in / NHWC out, plan dtype.
- * w: [C][3][3] float32; pad == dilation (the reference always uses padding=dilation for 3x3).
+ * w: [9][C] float32, tap-major (tap = ky*3 + kx; the host mirror transposes the state_dict's [C][1][3][3]);
+ * pad == dilation (the reference always uses padding=dilation for 3x3).  C must be a multiple of 8.
  */
 int lwp_plan_add_depthwise(lwp_plan *p, const void *in, void *out, const float *w, const float *scale,
                            const float *shift, int n, int H, int W, int C, int stride, int dilation, int act);
@@ -159,6 +160,9 @@ int lwp_plan_run(lwp_plan *p, const float *x, void *stream);
 int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int last, void *stream);
 /* number of kernel launches one lwp_plan_run issues */
 int lwp_plan_num_launches(const lwp_plan *p);
+/* Synchronising read of the plan's device error flag: 0 = ok, else the id of the pipeline wait that timed
+ * out inside a tcgen05 GEMM kernel (the kernels never spin forever). */
+int lwp_plan_error_flag(lwp_plan *p);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,7 @@ SIGNATURES = {
     "lwp_plan_run": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
     "lwp_plan_run_range": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "lwp_plan_num_launches": (_c_int, [_c_void_p]),
+    "lwp_plan_error_flag": (_c_int, [_c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,260 @@
+// Dense convolution (1x1 and 3x3, stride 1, any dilation) as an implicit GEMM on tcgen05 tensor cores.
+//
+//   D[pixel, cout] = sum_{tap, cin} A[pixel + offset(tap), cin] * Wt[cout, tap, cin]
+//
+// * A (activations, NHWC) is fetched by TMA through a 4-D tensor map (C, W, H, N): a tile is a
+//   tile_h x tile_w rectangle of 128 pixels, a tap is the same rectangle shifted by (dy, dx); TMA
+//   zero-fills whatever falls outside the image, which IS the convolution's zero padding.  1x1 convs
+//   use the same path with the whole batch flattened to one row of pixels.
+// * B (weights, [Cout][taps*Cin], K-major) is fetched by a 2-D tensor map.
+// * Both land in shared memory in the canonical K-major SWIZZLE_128B layout; one elected thread issues
+//   tcgen05.mma (M = 128, N = block_n, K = 32 bytes per instruction), accumulating fp32 in TMEM.
+// * Persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue;
+//   a ring of smem stages (full/empty mbarriers) and two TMEM accumulator stages (tmem_full/empty) so
+//   the epilogue of tile i overlaps the main loop of tile i+1.
+// * Epilogue: tcgen05.ld -> y = act(acc*scale[c] + shift[c]) (+ residual) -> plan dtype and/or fp32.
+//
+// Replaces nn.Conv2d (+ BatchNorm2d + ReLU/ELU + residual add) of modules/conv.py:4-10,19,30 and
+// models/with_mobilenet.py:10,16,20,28-38,51-54,60,74-79 of the reference.
+#include "common.cuh"
+#include "conv_gemm.cuh"
+#include "tcgen05.cuh"
+
+namespace lwp {
+
+struct SmemLayout {
+  uint32_t stage_bytes;
+  uint32_t stages_off;   // 0 (after 1024-alignment)
+  uint32_t scale_off, shift_off, bars_off, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int num_stages, int cout_pad) {
+  SmemLayout L;
+  L.stage_bytes = kATileBytes + (uint32_t)block_n * kKBlockBytes;
+  L.stages_off = 0;
+  L.scale_off = L.stage_bytes * (uint32_t)num_stages;
+  L.shift_off = L.scale_off + (uint32_t)cout_pad * 4;
+  L.bars_off = (L.shift_off + (uint32_t)cout_pad * 4 + 15u) & ~15u;
+  L.total = L.bars_off + (2 * kMaxStages + 4) * 8 + 16;
+  return L;
+}
+
+size_t conv_gemm_smem_bytes(const GemmParams &p) {
+  return (size_t)smem_layout(p.block_n, p.num_stages, p.cout_pad).total + 1024;  // + alignment slack
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == LWP_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == LWP_ACT_ELU) return v > 0.f ? v : expm1f(v);
+  return v;
+}
+
+struct TileCoord {
+  int img, y0, x0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams &p, int t) {
+  TileCoord c;
+  int m_tile = t / p.n_tiles;
+  c.n0 = (t - m_tile * p.n_tiles) * p.block_n;
+  int per_img = p.tiles_x * p.tiles_y;
+  c.img = m_tile / per_img;
+  int rem = m_tile - c.img * per_img;
+  int ty = rem / p.tiles_x;
+  c.y0 = ty * p.tile_h;
+  c.x0 = (rem - ty * p.tiles_x) * p.tile_w;
+  return c;
+}
+
+template <bool kTf32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const SmemLayout L = smem_layout(p.block_n, p.num_stages, p.cout_pad);
+  float *s_scale = reinterpret_cast<float *>(smem + L.scale_off);
+  float *s_shift = reinterpret_cast<float *>(smem + L.shift_off);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L.bars_off);
+  uint64_t *empty_bar = full_bar + kMaxStages;
+  uint64_t *tfull_bar = empty_bar + kMaxStages;
+  uint64_t *tempty_bar = tfull_bar + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.taps * p.kblocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < p.num_stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+  for (int i = threadIdx.x; i < p.cout_pad; i += kGemmThreads) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        for (int tap = 0; tap < p.taps && ok; ++tap) {
+          const int dy = p.taps == 1 ? 0 : (tap / 3 - 1) * p.dil;
+          const int dx = p.taps == 1 ? 0 : (tap % 3 - 1) * p.dil;
+          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
+            if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; atomicExch(p.err_flag, 1); break; }
+            uint8_t *sa = smem + (size_t)stage * L.stage_bytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], L.stage_bytes);
+            ptx::tma_load_4d(sa, &tmA, &full_bar[stage], kb * p.kb_elems, tc.x0 + dx, tc.y0 + dy, tc.img);
+            ptx::tma_load_2d(sa + kATileBytes, &tmB, &full_bar[stage], tap * p.cin + kb * p.kb_elems, tc.n0);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
+        if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u)) { atomicExch(p.err_flag, 2); break; }
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+        for (int it = 0; it < k_iters; ++it) {
+          if (!ptx::mbar_wait(&full_bar[stage], phase)) { ok = false; atomicExch(p.err_flag, 3); break; }
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * L.stage_bytes);
+          const uint64_t da = ptx::umma_desc_k_sw128(sa);
+          const uint64_t db = ptx::umma_desc_k_sw128(sa + kATileBytes);
+#pragma unroll
+          for (int k = 0; k < kKBlockBytes / 32; ++k)  // 32 bytes of K per instruction: advance start address by 2
+            ptx::umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (uint32_t)((it | k) != 0));
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+        if (!ok) break;
+        ptx::umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ty = row / p.tile_w, tx = row - ty * p.tile_w;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase)) { atomicExch(p.err_flag, 4); break; }
+      ptx::tc_fence_after();
+      const TileCoord tc = decode_tile(p, t);
+      const int y = tc.y0 + ty, x = tc.x0 + tx;
+      const bool valid = y < p.H && x < p.W;
+      const size_t pix = ((size_t)tc.img * p.H + y) * (size_t)p.W + x;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_row + (uint32_t)c, r);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int cg = tc.n0 + c + g8 * 8;
+            if (cg + 8 <= p.n_store) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                v[j] = apply_act(fmaf(__uint_as_float(r[g8 * 8 + j]), s_scale[cg + j], s_shift[cg + j]), p.act);
+              if (p.residual != nullptr) {
+                if constexpr (kTf32) {
+                  const float4 *rp = reinterpret_cast<const float4 *>(
+                      reinterpret_cast<const float *>(p.residual) + pix * p.res_ld + cg);
+                  float4 a = __ldg(rp), b = __ldg(rp + 1);
+                  v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+                  v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+                } else {
+                  const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(
+                      reinterpret_cast<const __nv_bfloat16 *>(p.residual) + pix * p.res_ld + cg));
+                  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float2 f = __bfloat1622float2(h[j]);
+                    v[2 * j] += f.x; v[2 * j + 1] += f.y;
+                  }
+                }
+              }
+              if (p.out != nullptr) {
+                if constexpr (kTf32) {
+                  float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + pix * p.out_ld + cg);
+                  op[0] = make_float4(v[0], v[1], v[2], v[3]);
+                  op[1] = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+                  uint4 pk;
+                  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                  *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_ld + cg) = pk;
+                }
+              }
+              if (p.out_f32 != nullptr) {
+                float4 *op = reinterpret_cast<float4 *>(p.out_f32 + pix * p.out_f32_ld + cg);
+                op[0] = make_float4(v[0], v[1], v[2], v[3]);
+                op[1] = make_float4(v[4], v[5], v[6], v[7]);
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);  // accumulator stage drained
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+int conv_gemm_init() {
+  static bool done = false;
+  if (done) return LWP_OK;
+  LWP_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  LWP_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  done = true;
+  return LWP_OK;
+}
+
+int conv_gemm_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int grid,
+                     cudaStream_t st) {
+  size_t smem = conv_gemm_smem_bytes(p);
+  if (tf32)
+    conv_gemm_kernel<true><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+  else
+    conv_gemm_kernel<false><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+  LWP_LAUNCH_CHECK();
+  return LWP_OK;
+}
+
+}  // namespace lwp

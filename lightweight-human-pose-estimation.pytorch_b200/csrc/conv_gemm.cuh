@@ -1,0 +1,45 @@
+// Parameter block shared by the tcgen05 implicit-GEMM convolution kernel and the plan that launches it.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace lwp {
+
+constexpr int kGemmThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kBlockM = 128;        // pixels per tile == UMMA M == TMEM lanes
+constexpr int kKBlockBytes = 128;   // one SWIZZLE_128B row of K per pipeline stage
+constexpr int kATileBytes = kBlockM * kKBlockBytes;
+constexpr int kMaxStages = 8;
+constexpr int kMaxCout = 1024;
+
+struct GemmParams {
+  int H, W, NIMG;          // geometry the A tensor map was built with (flattened 1x1: H = NIMG = 1, W = pixels)
+  int tile_w, tile_h;      // tile_w * tile_h == 128
+  int tiles_x, tiles_y;    // tiles per image
+  int m_tiles, n_tiles;    // total M tiles, Cout_pad / block_n
+  int block_n;             // UMMA N (multiple of 32, <= 256)
+  int taps, dil;           // 1 or 9; tap offset = (k - 1) * dil
+  int kblocks_per_tap;     // ceil(Cin * elem_size / 128)
+  int kb_elems;            // elements per K block: 64 (bf16) or 32 (tf32)
+  int cin;                 // B's K coordinate of tap t, block b = t * cin + b * kb_elems
+  int cout_pad, n_store;   // columns computed / columns written (multiple of 8)
+  uint32_t idesc;          // UMMA instruction descriptor (M = 128, N = block_n)
+  int act;                 // LWP_ACT_*
+  int num_stages;
+  uint32_t tmem_cols;      // power of two >= 2 * block_n
+  const float *scale, *shift;
+  const void *residual;    // plan dtype, pixel stride res_ld, or nullptr
+  int res_ld;
+  void *out;               // plan dtype, pixel stride out_ld, or nullptr
+  int out_ld;
+  float *out_f32;          // optional float32 copy, pixel stride out_f32_ld
+  int out_f32_ld;
+  int *err_flag;           // set non-zero if a pipeline wait timed out
+};
+
+size_t conv_gemm_smem_bytes(const GemmParams &p);
+int conv_gemm_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int grid,
+                     cudaStream_t st);
+int conv_gemm_init();
+
+}  // namespace lwp

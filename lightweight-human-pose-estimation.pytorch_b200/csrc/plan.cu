@@ -1,0 +1,257 @@
+// lwp_plan: a recorded list of layer launches (stem, depthwise, tcgen05 implicit-GEMM convs, layout
+// hand-off) with pre-built TMA tensor maps for one (batch, H, W, dtype).  Replaces
+// PoseEstimationWithMobileNet.forward (reference models/with_mobilenet.py:114-123); the Python mirror
+// walks its own module tree (same state_dict as the reference) and records one op per layer.
+#include "common.cuh"
+#include "conv_direct.cuh"
+#include "conv_gemm.cuh"
+#include "tcgen05.cuh"
+
+#include <cuda.h>
+#include <vector>
+
+namespace lwp {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+enum OpKind { OP_STEM, OP_DW, OP_GEMM, OP_NCHW };
+
+struct Op {
+  OpKind kind;
+  // stem / dw / nchw
+  const void *in = nullptr;
+  void *out = nullptr;
+  const float *w = nullptr, *scale = nullptr, *shift = nullptr;
+  int n = 0, H = 0, W = 0, C = 0, stride = 1, dil = 1, act = 0;
+  int ld = 0, c0 = 0, in_f32 = 0;
+  // gemm
+  CUtensorMap tmA, tmB;
+  GemmParams gp;
+  int grid = 0;
+};
+
+}  // namespace lwp
+
+struct lwp_plan {
+  int dtype;
+  std::vector<lwp::Op> ops;
+  int *err_flag = nullptr;
+};
+
+using namespace lwp;
+
+extern "C" int lwp_plan_create(int dtype, lwp_plan **out) {
+  LWP_REQUIRE(out != nullptr, "lwp_plan_create: null out");
+  LWP_REQUIRE(dtype == LWP_DTYPE_BF16 || dtype == LWP_DTYPE_TF32, "lwp_plan_create: bad dtype %d", dtype);
+  int dev = 0;
+  LWP_CUDA_CHECK(cudaGetDevice(&dev));
+  int rc = lwp_check_device(dev);
+  if (rc != LWP_OK) return rc;
+  if (get_encode_fn() == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return LWP_ECUDA; }
+  rc = conv_gemm_init();
+  if (rc != LWP_OK) return rc;
+  lwp_plan *p = new lwp_plan();
+  p->dtype = dtype;
+  cudaError_t e = cudaMalloc(&p->err_flag, sizeof(int));
+  if (e != cudaSuccess) { delete p; set_error("cudaMalloc err_flag: %s", cudaGetErrorString(e)); return LWP_ECUDA; }
+  cudaMemset(p->err_flag, 0, sizeof(int));
+  *out = p;
+  return LWP_OK;
+}
+
+extern "C" void lwp_plan_destroy(lwp_plan *p) {
+  if (p == nullptr) return;
+  if (p->err_flag) cudaFree(p->err_flag);
+  delete p;
+}
+
+extern "C" int lwp_plan_num_ops(const lwp_plan *p) { return p ? (int)p->ops.size() : 0; }
+
+extern "C" int lwp_plan_num_launches(const lwp_plan *p) { return p ? (int)p->ops.size() : 0; }  // one kernel per op
+
+extern "C" int lwp_plan_error_flag(lwp_plan *p) {
+  LWP_REQUIRE(p != nullptr, "lwp_plan_error_flag: null plan");
+  int v = 0;
+  LWP_CUDA_CHECK(cudaMemcpy(&v, p->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  return v;
+}
+
+extern "C" int lwp_plan_add_stem(lwp_plan *p, const float *w, const float *scale, const float *shift, void *out, int n,
+                                 int H, int W) {
+  LWP_REQUIRE(p && w && scale && shift && out, "lwp_plan_add_stem: null pointer");
+  LWP_REQUIRE(n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "lwp_plan_add_stem: bad shape %dx%dx%d", n, H, W);
+  Op op;
+  op.kind = OP_STEM;
+  op.w = w; op.scale = scale; op.shift = shift; op.out = out; op.n = n; op.H = H; op.W = W;
+  p->ops.push_back(op);
+  return LWP_OK;
+}
+
+extern "C" int lwp_plan_add_depthwise(lwp_plan *p, const void *in, void *out, const float *w, const float *scale,
+                                      const float *shift, int n, int H, int W, int C, int stride, int dilation,
+                                      int act) {
+  LWP_REQUIRE(p && in && out && w && scale && shift, "lwp_plan_add_depthwise: null pointer");
+  LWP_REQUIRE(n > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "lwp_plan_add_depthwise: bad shape");
+  LWP_REQUIRE((stride == 1 && (dilation == 1 || dilation == 2)) || (stride == 2 && dilation == 1),
+              "lwp_plan_add_depthwise: unsupported stride %d dilation %d", stride, dilation);
+  Op op;
+  op.kind = OP_DW;
+  op.in = in; op.out = out; op.w = w; op.scale = scale; op.shift = shift;
+  op.n = n; op.H = H; op.W = W; op.C = C; op.stride = stride; op.dil = dilation; op.act = act;
+  p->ops.push_back(op);
+  return LWP_OK;
+}
+
+extern "C" int lwp_plan_add_nhwc_to_nchw(lwp_plan *p, const void *in, int in_ld, int in_is_f32, int c0, int c,
+                                         float *out, int n, int H, int W) {
+  LWP_REQUIRE(p && in && out && n > 0 && H > 0 && W > 0 && c > 0 && c0 >= 0 && c0 + c <= in_ld,
+              "lwp_plan_add_nhwc_to_nchw: bad arguments");
+  Op op;
+  op.kind = OP_NCHW;
+  op.in = in; op.out = out; op.ld = in_ld; op.in_f32 = in_is_f32 || p->dtype == LWP_DTYPE_TF32; op.c0 = c0; op.C = c;
+  op.n = n; op.H = H; op.W = W;
+  p->ops.push_back(op);
+  return LWP_OK;
+}
+
+extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, const void *w, const float *scale,
+                                      const float *shift, const void *residual, int res_ld, void *out, int out_ld,
+                                      float *out_f32, int out_f32_ld, int n, int H, int W, int Cin, int Cout, int taps,
+                                      int dilation, int act) {
+  LWP_REQUIRE(p && in && w && scale && shift && (out || out_f32), "lwp_plan_add_conv_gemm: null pointer");
+  LWP_REQUIRE(taps == 1 || taps == 9, "lwp_plan_add_conv_gemm: taps must be 1 or 9");
+  LWP_REQUIRE(n > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && dilation >= 1, "lwp_plan_add_conv_gemm: bad shape");
+  const bool tf32 = p->dtype == LWP_DTYPE_TF32;
+  const int es = tf32 ? 4 : 2;
+  const int kb_elems = kKBlockBytes / es;
+  LWP_REQUIRE(Cin % 8 == 0 && in_ld % 8 == 0 && in_ld >= Cin, "lwp_plan_add_conv_gemm: Cin/in_ld must be multiples of 8");
+  LWP_REQUIRE(taps == 1 || Cin % kb_elems == 0, "lwp_plan_add_conv_gemm: 3x3 needs Cin %% %d == 0", kb_elems);
+  const int cout_pad = (Cout + 63) / 64 * 64;
+  LWP_REQUIRE(cout_pad <= kMaxCout, "lwp_plan_add_conv_gemm: Cout too large");
+  LWP_REQUIRE(((uintptr_t)in % 16) == 0 && ((uintptr_t)w % 16) == 0, "lwp_plan_add_conv_gemm: unaligned pointer");
+  LWP_REQUIRE(!out || (out_ld % 8 == 0 && (uintptr_t)out % 16 == 0), "lwp_plan_add_conv_gemm: bad out_ld/alignment");
+  LWP_REQUIRE(!out_f32 || (out_f32_ld % 4 == 0 && (uintptr_t)out_f32 % 16 == 0), "lwp_plan_add_conv_gemm: bad out_f32_ld");
+  LWP_REQUIRE(!residual || (res_ld % 8 == 0 && (uintptr_t)residual % 16 == 0), "lwp_plan_add_conv_gemm: bad res_ld");
+
+  Op op;
+  op.kind = OP_GEMM;
+  GemmParams &g = op.gp;
+  g.taps = taps; g.dil = dilation; g.cin = Cin; g.kb_elems = kb_elems;
+  g.kblocks_per_tap = (Cin + kb_elems - 1) / kb_elems;
+  g.cout_pad = cout_pad;
+  g.block_n = cout_pad % 128 == 0 ? 128 : 64;
+  g.n_tiles = cout_pad / g.block_n;
+  // columns actually written: whole 8-groups that fit the narrowest destination row
+  int n_store = cout_pad;
+  if (out && out_ld < n_store) n_store = out_ld / 8 * 8;
+  if (out_f32 && out_f32_ld < n_store) n_store = out_f32_ld / 8 * 8;
+  if (residual) {
+    int lim = (Cout + 7) / 8 * 8;  // residual only covers real channels
+    if (lim < n_store) n_store = lim;
+  }
+  g.n_store = n_store;
+  g.idesc = make_umma_idesc(tf32, kBlockM, g.block_n);
+  g.act = act;
+  g.scale = scale; g.shift = shift;
+  g.residual = residual; g.res_ld = res_ld;
+  g.out = out; g.out_ld = out_ld; g.out_f32 = out_f32; g.out_f32_ld = out_f32_ld;
+  g.err_flag = p->err_flag;
+  const int stage_bytes = kATileBytes + g.block_n * kKBlockBytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  g.num_stages = stages;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * g.block_n)) cols <<= 1;
+  g.tmem_cols = cols;
+
+  // geometry: 1x1 -> whole batch flattened to one row of pixels; 3x3 -> best rectangular tile
+  if (taps == 1) {
+    g.H = 1; g.NIMG = 1; g.W = n * H * W;
+    g.tile_w = 128; g.tile_h = 1;
+  } else {
+    g.H = H; g.W = W; g.NIMG = n;
+    long long best = -1;
+    for (int th = 1; th <= 128; th <<= 1) {
+      int tw = 128 / th;
+      long long area = (long long)ceil_div(H, th) * th * (long long)ceil_div(W, tw) * tw;
+      if (best < 0 || area < best) { best = area; g.tile_h = th; g.tile_w = tw; }
+    }
+  }
+  g.tiles_x = ceil_div(g.W, g.tile_w);
+  g.tiles_y = ceil_div(g.H, g.tile_h);
+  g.m_tiles = g.NIMG * g.tiles_x * g.tiles_y;
+  long long total_tiles = (long long)g.m_tiles * g.n_tiles;
+  op.grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+
+  EncodeTiledFn enc = get_encode_fn();
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.NIMG};
+    cuuint64_t strides[3] = {(cuuint64_t)in_ld * es, (cuuint64_t)in_ld * es * g.W, (cuuint64_t)in_ld * es * g.W * g.H};
+    cuuint32_t box[4] = {(cuuint32_t)kb_elems, (cuuint32_t)g.tile_w, (cuuint32_t)g.tile_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&op.tmA, dt, 4, const_cast<void *>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return LWP_ECUDA; }
+  }
+  {
+    const cuuint64_t ktot = (cuuint64_t)taps * Cin;
+    cuuint64_t dims[2] = {ktot, (cuuint64_t)cout_pad};
+    cuuint64_t strides[1] = {ktot * es};
+    cuuint32_t box[2] = {(cuuint32_t)kb_elems, (cuuint32_t)g.block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&op.tmB, dt, 2, const_cast<void *>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return LWP_ECUDA; }
+  }
+  p->ops.push_back(op);
+  return LWP_OK;
+}
+
+extern "C" int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int last, void *stream) {
+  LWP_REQUIRE(p != nullptr, "lwp_plan_run: null plan");
+  LWP_REQUIRE(first >= 0 && last <= (int)p->ops.size() && first <= last, "lwp_plan_run_range: bad range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool f32 = p->dtype == LWP_DTYPE_TF32;
+  for (int i = first; i < last; ++i) {
+    const Op &op = p->ops[i];
+    int rc = LWP_OK;
+    switch (op.kind) {
+      case OP_STEM:
+        LWP_REQUIRE(x != nullptr, "lwp_plan_run: the plan has a stem but x is NULL");
+        rc = stem_launch(f32, x, op.w, op.scale, op.shift, op.out, op.n, op.H, op.W, st);
+        break;
+      case OP_DW:
+        rc = depthwise_launch(f32, op.in, op.out, op.w, op.scale, op.shift, op.n, op.H, op.W, op.C, op.stride, op.dil,
+                              op.act, st);
+        break;
+      case OP_GEMM:
+        rc = conv_gemm_launch(f32, op.tmA, op.tmB, op.gp, op.grid, st);
+        break;
+      case OP_NCHW:
+        rc = nhwc_to_nchw_launch(op.in_f32 != 0, op.in, op.ld, op.c0, op.C, (float *)op.out, op.n, op.H * op.W, st);
+        break;
+    }
+    if (rc != LWP_OK) return rc;
+  }
+  return LWP_OK;
+}
+
+extern "C" int lwp_plan_run(lwp_plan *p, const float *x, void *stream) {
+  LWP_REQUIRE(p != nullptr, "lwp_plan_run: null plan");
+  return lwp_plan_run_range(p, x, 0, (int)p->ops.size(), stream);
+}

@@ -1,0 +1,348 @@
+"""Host side of the network forward: folds BatchNorm, packs weights for the tcgen05 kernels and records
+one launch plan per (precision, batch, height, width) through the C ABI (include/lwpose_b200.h).
+
+It walks the module tree of lwpose_b200.models.with_mobilenet.PoseEstimationWithMobileNet -- the same
+parameters, in the same containers, as the reference's models/with_mobilenet.py:89-123 -- and replaces
+its forward (:114-123):
+
+  model (stem + 11 depthwise-separable blocks)  -> stem kernel, depthwise kernels, 1x1 implicit GEMMs
+  cpm (:18-21)                                  -> 1x1 GEMM, 3 x (depthwise+ELU, 1x1 GEMM+ELU), residual in
+                                                   the last epilogue, 3x3 GEMM
+  initial_stage (:41-45)                        -> 3 x 3x3 GEMM, both heads merged into two GEMMs
+  refinement_stages (:57-60,82-86,119-121)      -> the 185-channel concat is never materialised by a cat:
+                                                   producers write straight into a 192-wide buffer
+PyTorch is used for device memory and one-off weight re-layout only.
+"""
+import torch
+from torch import nn
+
+from . import _lib
+
+DTYPE_BF16, DTYPE_TF32 = 0, 1
+ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
+_PREC = {"bf16": (DTYPE_BF16, torch.bfloat16), "tf32": (DTYPE_TF32, torch.float32)}
+HEAD_LD = 64      # float32 head buffer: 19 heat-map + 38 PAF channels + 7 zero pad
+CONCAT_LD = 192   # 128 backbone + 19 + 38 + 7 zero pad
+
+
+class _Unit:
+    """One Conv2d with its BatchNorm / bias folded to per-channel scale & shift and its activation."""
+
+    def __init__(self, conv_m, bn_m, act_m):
+        w = conv_m.weight.detach().float()
+        cout = w.shape[0]
+        dev = w.device
+        scale = torch.ones(cout, device=dev)
+        shift = torch.zeros(cout, device=dev)
+        if conv_m.bias is not None:
+            shift = conv_m.bias.detach().float().clone()
+        if bn_m is not None:  # eval-mode BN: y = (x - mean) / sqrt(var + eps) * gamma + beta
+            inv = bn_m.weight.detach().float() / torch.sqrt(bn_m.running_var.detach().float() + bn_m.eps)
+            shift = (shift - bn_m.running_mean.detach().float()) * inv + bn_m.bias.detach().float()
+            scale = inv
+        self.weight, self.scale, self.shift = w, scale, shift
+        self.act = ACT_RELU if isinstance(act_m, nn.ReLU) else ACT_ELU if isinstance(act_m, nn.ELU) else ACT_NONE
+        self.stride, self.dilation = conv_m.stride[0], conv_m.dilation[0]
+        self.depthwise = conv_m.groups > 1
+        self.ksize = conv_m.kernel_size[0]
+        if self.ksize == 3 and conv_m.padding[0] != self.dilation:
+            raise ValueError("3x3 conv with padding != dilation is not part of the hot path")
+
+
+def _units(seq):
+    """Split a Sequential of Conv2d [BatchNorm2d] [ReLU|ELU] ... into folded units."""
+    mods = list(seq.children())
+    out, i = [], 0
+    while i < len(mods):
+        assert isinstance(mods[i], nn.Conv2d), type(mods[i])
+        conv_m, bn_m, act_m = mods[i], None, None
+        i += 1
+        if i < len(mods) and isinstance(mods[i], nn.BatchNorm2d):
+            bn_m = mods[i]
+            i += 1
+        if i < len(mods) and isinstance(mods[i], (nn.ReLU, nn.ELU)):
+            act_m = mods[i]
+            i += 1
+        out.append(_Unit(conv_m, bn_m, act_m))
+    return out
+
+
+def _pad_rows(t, rows):
+    if t.shape[0] == rows:
+        return t
+    pad = torch.zeros((rows - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    return torch.cat([t, pad], 0)
+
+
+class _GemmW:
+    """Weights of one implicit-GEMM conv: [Cout_pad][taps*Cin] K-major in the plan dtype + fp32 scale/shift."""
+
+    def __init__(self, weight, scale, shift, act, tdtype, dilation=1, cin_pad=None):
+        cout, cin, kh, kw = weight.shape
+        self.taps = kh * kw
+        w = weight.permute(0, 2, 3, 1).reshape(cout, self.taps, cin)
+        if cin_pad is not None and cin_pad != cin:
+            w = torch.cat([w, torch.zeros(cout, self.taps, cin_pad - cin, device=w.device)], 2)
+            cin = cin_pad
+        self.cin, self.cout = cin, cout
+        self.cout_pad = (cout + 63) // 64 * 64
+        self.w = _pad_rows(w.reshape(cout, self.taps * cin), self.cout_pad).to(tdtype).contiguous()
+        self.scale = _pad_rows(scale.reshape(-1), self.cout_pad).float().contiguous()
+        self.shift = _pad_rows(shift.reshape(-1), self.cout_pad).float().contiguous()
+        self.act, self.dilation = act, dilation
+
+    @staticmethod
+    def from_unit(u, tdtype, cin_pad=None):
+        return _GemmW(u.weight, u.scale, u.shift, u.act, tdtype, u.dilation, cin_pad)
+
+
+class _DwW:
+    def __init__(self, u):
+        c = u.weight.shape[0]
+        self.w = u.weight.reshape(c, 9).t().contiguous()  # [9][C] tap-major
+        self.scale, self.shift = u.scale.contiguous(), u.shift.contiguous()
+        self.act, self.stride, self.dilation, self.c = u.act, u.stride, u.dilation, c
+
+
+def _merge_heads(hm_seq, paf_seq, tdtype):
+    """Both heads read the same trunk features: first layers stacked along Cout, second layers as one
+    block-diagonal GEMM writing [19 heat-maps | 38 PAFs | zero pad]."""
+    (h1, h2), (p1, p2) = _units(hm_seq[0]) + _units(hm_seq[1]), _units(paf_seq[0]) + _units(paf_seq[1])
+    first = _GemmW(torch.cat([h1.weight, p1.weight], 0), torch.cat([h1.scale, p1.scale]),
+                   torch.cat([h1.shift, p1.shift]), h1.act, tdtype)
+    mid_h, mid_p = h2.weight.shape[1], p2.weight.shape[1]
+    nh, np_ = h2.weight.shape[0], p2.weight.shape[0]
+    w2 = torch.zeros(nh + np_, mid_h + mid_p, 1, 1, device=h2.weight.device)
+    w2[:nh, :mid_h] = h2.weight
+    w2[nh:, mid_h:] = p2.weight
+    second = _GemmW(w2, torch.cat([h2.scale, p2.scale]), torch.cat([h2.shift, p2.shift]), h2.act, tdtype)
+    return first, second
+
+
+class _Packed:
+    """All weights of the network re-laid-out for one precision."""
+
+    def __init__(self, net, tdtype):
+        blocks = list(net.model.children())
+        stem = _units(blocks[0])[0]
+        self.stem = (stem.weight.contiguous(), stem.scale.contiguous(), stem.shift.contiguous())
+        self.backbone = []
+        for b in blocks[1:]:
+            dw, pw = _units(b)
+            self.backbone.append((_DwW(dw), _GemmW.from_unit(pw, tdtype)))
+        self.cpm_align = _GemmW.from_unit(_units(net.cpm.align)[0], tdtype)
+        self.cpm_trunk = []
+        for b in net.cpm.trunk.children():
+            dw, pw = _units(b)
+            self.cpm_trunk.append((_DwW(dw), _GemmW.from_unit(pw, tdtype)))
+        self.cpm_conv = _GemmW.from_unit(_units(net.cpm.conv)[0], tdtype)
+        self.init_trunk = [_GemmW.from_unit(_units(c)[0], tdtype) for c in net.initial_stage.trunk.children()]
+        self.init_heads = _merge_heads(net.initial_stage.heatmaps, net.initial_stage.pafs, tdtype)
+        self.refine = []
+        for st in net.refinement_stages:
+            blks = []
+            for i, blk in enumerate(st.trunk.children()):
+                ini = _GemmW.from_unit(_units(blk.initial)[0], tdtype, cin_pad=CONCAT_LD if i == 0 else None)
+                t0, t1 = [_GemmW.from_unit(_units(c)[0], tdtype) for c in blk.trunk.children()]
+                blks.append((ini, t0, t1))
+            self.refine.append((blks, _merge_heads(st.heatmaps, st.pafs, tdtype)))
+
+
+class Plan:
+    """One recorded launch list + its buffers for a fixed (precision, N, H, W)."""
+
+    def __init__(self, packed, precision, n, H, W, n_stages_out, num_heatmaps, num_pafs, device):
+        if H % 8 or W % 8:
+            raise ValueError("input height/width must be multiples of 8 (got %dx%d)" % (H, W))
+        self.lib = _lib.load()
+        self.n, self.H, self.W = n, H, W
+        self.h, self.w = H // 8, W // 8
+        self.precision = precision
+        code, tdtype = _PREC[precision]
+        self.tdtype = tdtype
+        self.device = device
+        self.packed = packed  # keeps the packed weights alive
+        handle = _lib._c_void_p()
+        _lib.check(self.lib.lwp_plan_create(code, handle), "lwp_plan_create")
+        self.handle = handle
+        self.bufs = []
+        self.op_names = []
+        self._build(packed, n_stages_out, num_heatmaps, num_pafs)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.lwp_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _buf(self, *shape, dtype=None, zero=False):
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype or self.tdtype, device=self.device)
+        self.bufs.append(t)
+        return t
+
+    def _gemm(self, name, src, src_ld, g, n, H, W, out=None, out_ld=0, out_ptr_off=0, residual=None, res_ld=0,
+              out_f32=None, out_f32_ld=0):
+        es = 2 if self.tdtype == torch.bfloat16 else 4
+        out_ptr = (out.data_ptr() + out_ptr_off * es) if out is not None else None
+        _lib.check(self.lib.lwp_plan_add_conv_gemm(
+            self.handle, src.data_ptr(), src_ld, g.w.data_ptr(), g.scale.data_ptr(), g.shift.data_ptr(),
+            residual.data_ptr() if residual is not None else None, res_ld, out_ptr, out_ld,
+            out_f32.data_ptr() if out_f32 is not None else None, out_f32_ld, n, H, W, g.cin, g.cout, g.taps,
+            g.dilation, g.act), "lwp_plan_add_conv_gemm(%s)" % name)
+        self.op_names.append(name)
+
+    def _dw(self, name, src, dst, d, n, H, W):
+        _lib.check(self.lib.lwp_plan_add_depthwise(self.handle, src.data_ptr(), dst.data_ptr(), d.w.data_ptr(),
+                                                   d.scale.data_ptr(), d.shift.data_ptr(), n, H, W, d.c, d.stride,
+                                                   d.dilation, d.act), "lwp_plan_add_depthwise(%s)" % name)
+        self.op_names.append(name)
+
+    # -- the layer walk -----------------------------------------------------------------------
+    def _build(self, P, n_stages_out, num_heatmaps, num_pafs):
+        n, H, W = self.n, self.H, self.W
+        # backbone ping-pong buffers: sized for the largest activation either of them ever holds
+        sizes = [0, 0]
+        hh, ww, c, which = H // 2, W // 2, 32, 0
+        sizes[0] = n * hh * ww * 32
+        for dw, pw in P.backbone:
+            ho, wo = (hh - 1) // dw.stride + 1, (ww - 1) // dw.stride + 1
+            which ^= 1
+            sizes[which] = max(sizes[which], n * ho * wo * c)
+            which ^= 1
+            sizes[which] = max(sizes[which], n * ho * wo * pw.cout_pad)
+            hh, ww, c = ho, wo, pw.cout
+        pp = [self._buf(sizes[0]), self._buf(sizes[1])]
+
+        w_, s_, b_ = P.stem
+        _lib.check(self.lib.lwp_plan_add_stem(self.handle, w_.data_ptr(), s_.data_ptr(), b_.data_ptr(),
+                                              pp[0].data_ptr(), n, H, W), "lwp_plan_add_stem")
+        self.op_names.append("model.0")
+        hh, ww, c, cur = H // 2, W // 2, 32, 0
+        for i, (dw, pw) in enumerate(P.backbone):
+            ho, wo = (hh - 1) // dw.stride + 1, (ww - 1) // dw.stride + 1
+            self._dw("model.%d.dw" % (i + 1), pp[cur], pp[cur ^ 1], dw, n, hh, ww)
+            self._gemm("model.%d.pw" % (i + 1), pp[cur ^ 1], c, pw, n, ho, wo, out=pp[cur], out_ld=pw.cout_pad)
+            hh, ww, c = ho, wo, pw.cout
+        assert (hh, ww) == (self.h, self.w) and c == 512
+        feat = pp[cur]
+        h, w = self.h, self.w
+        px = n * h * w
+        nc = P.cpm_align.cout  # 128
+        A, t0, t1, i0 = (self._buf(px * nc) for _ in range(4))
+        r = [self._buf(px * nc), self._buf(px * nc)]
+        concat = self._buf(px * CONCAT_LD, zero=True)
+        self.concat = concat
+        mid0 = P.init_heads[0].cout_pad
+        big = self._buf(px * mid0)
+        self.heads_f32 = [self._buf(px * HEAD_LD, dtype=torch.float32, zero=True) for _ in range(n_stages_out)]
+
+        self._gemm("cpm.align", feat, 512, P.cpm_align, n, h, w, out=A, out_ld=nc)
+        src = A
+        for i, (dw, pw) in enumerate(P.cpm_trunk):
+            self._dw("cpm.trunk.%d.dw" % i, src, t0, dw, n, h, w)
+            last = i == len(P.cpm_trunk) - 1
+            self._gemm("cpm.trunk.%d.pw" % i, t0, nc, pw, n, h, w, out=t1, out_ld=nc,
+                       residual=A if last else None, res_ld=nc)  # x + trunk(x) fused into the last epilogue
+            src = t1
+        self._gemm("cpm.conv", t1, nc, P.cpm_conv, n, h, w, out=concat, out_ld=CONCAT_LD)
+        # initial stage
+        srcs = [(concat, CONCAT_LD), (t0, nc), (t1, nc)]
+        dsts = [t0, t1, t0]
+        for i, g in enumerate(P.init_trunk):
+            self._gemm("initial_stage.trunk.%d" % i, srcs[i][0], srcs[i][1], g, n, h, w, out=dsts[i], out_ld=nc)
+        more = len(P.refine) > 0
+        self._gemm("initial_stage.heads.0", t0, nc, P.init_heads[0], n, h, w, out=big, out_ld=mid0)
+        self._gemm("initial_stage.heads.1", big, mid0, P.init_heads[1], n, h, w,
+                   out=concat if more else None, out_ld=CONCAT_LD, out_ptr_off=nc,
+                   out_f32=self.heads_f32[0], out_f32_ld=HEAD_LD)
+        # refinement stages
+        for s, (blks, heads) in enumerate(P.refine):
+            src, src_ld = concat, CONCAT_LD
+            for k, (ini, c0, c1) in enumerate(blks):
+                self._gemm("refinement_stages.%d.trunk.%d.initial" % (s, k), src, src_ld, ini, n, h, w, out=i0,
+                           out_ld=nc)
+                self._gemm("refinement_stages.%d.trunk.%d.trunk.0" % (s, k), i0, nc, c0, n, h, w, out=t0, out_ld=nc)
+                dst = r[k & 1]
+                self._gemm("refinement_stages.%d.trunk.%d.trunk.1" % (s, k), t0, nc, c1, n, h, w, out=dst, out_ld=nc,
+                           residual=i0, res_ld=nc)  # initial_features + trunk_features
+                src, src_ld = dst, nc
+            mid = heads[0].cout_pad
+            hb = big[: px * mid]
+            self._gemm("refinement_stages.%d.heads.0" % s, src, nc, heads[0], n, h, w, out=hb, out_ld=mid)
+            more = s + 1 < len(P.refine)
+            self._gemm("refinement_stages.%d.heads.1" % s, hb, mid, heads[1], n, h, w,
+                       out=concat if more else None, out_ld=CONCAT_LD, out_ptr_off=nc,
+                       out_f32=self.heads_f32[s + 1], out_f32_ld=HEAD_LD)
+        self.num_compute_ops = len(self.op_names)
+        # NCHW float32 tensors handed back by forward()
+        self.outputs = []
+        for s in range(n_stages_out):
+            hm = self._buf(n, num_heatmaps, h, w, dtype=torch.float32)
+            paf = self._buf(n, num_pafs, h, w, dtype=torch.float32)
+            for t, c0_, cc in ((hm, 0, num_heatmaps), (paf, num_heatmaps, num_pafs)):
+                _lib.check(self.lib.lwp_plan_add_nhwc_to_nchw(self.handle, self.heads_f32[s].data_ptr(), HEAD_LD, 1,
+                                                              c0_, cc, t.data_ptr(), n, h, w),
+                           "lwp_plan_add_nhwc_to_nchw")
+                self.op_names.append("to_nchw.%d" % s)
+            self.outputs += [hm, paf]
+
+    # -- execution ----------------------------------------------------------------------------
+    def run(self, x, first=0, last=None):
+        """Enqueue ops [first, last) on the current stream.  x: contiguous float32 cuda [n,3,H,W]."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (self.n, 3, self.H, self.W)
+        last = len(self.op_names) if last is None else last
+        _lib.check(self.lib.lwp_plan_run_range(self.handle, x.data_ptr(), first, last, _lib.current_stream()),
+                   "lwp_plan_run")
+
+    def run_compute(self, x):
+        """All layers, without the NCHW hand-off copies (the fused pipeline reads heads_f32 directly)."""
+        self.run(x, 0, self.num_compute_ops)
+
+    def error_flag(self):
+        return self.lib.lwp_plan_error_flag(self.handle)
+
+    @property
+    def num_launches(self):
+        return len(self.op_names)
+
+
+class NetEngine:
+    def __init__(self, net):
+        _lib.require_cuda()
+        self.net = net
+        p = next(net.parameters())
+        if not p.is_cuda:
+            raise _lib.LwpError("module parameters are on the CPU; call net.cuda() (there is no CPU path)")
+        self.device = p.device
+        self._packed = {}
+        self._plans = {}
+
+    def packed(self, precision):
+        if precision not in _PREC:
+            raise ValueError("precision must be 'bf16' or 'tf32'")
+        if precision not in self._packed:
+            with torch.no_grad():
+                self._packed[precision] = _Packed(self.net, _PREC[precision][1])
+        return self._packed[precision]
+
+    def plan(self, precision, n, H, W):
+        key = (precision, n, H, W)
+        if key not in self._plans:
+            net = self.net
+            with torch.cuda.device(self.device):
+                self._plans[key] = Plan(self.packed(precision), precision, n, H, W, 1 + len(net.refinement_stages),
+                                        net.num_heatmaps, net.num_pafs, self.device)
+        return self._plans[key]
+
+    def forward(self, x, precision="tf32"):
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected input [N,3,H,W]")
+        x = x.contiguous().float()
+        n, _, H, W = x.shape
+        plan = self.plan(precision, n, H, W)
+        with torch.cuda.device(self.device):
+            plan.run(x)
+        return [t.clone() for t in plan.outputs]

@@ -1,0 +1,212 @@
+"""GPU parity of the network kernels (through the C ABI): each kernel against a plain PyTorch fp32
+reference of the same op, then the whole network against the golden outputs of the real reference.
+
+Stated tolerances (max abs error, outputs are O(0.1..1)):
+  tf32 plans ("fp32 mode": fp32 storage, TF32 tensor-core products, fp32 accumulate)  2e-3 per layer test
+  bf16 plans (bf16 storage + products, fp32 accumulate)                              3e-2 per layer test
+  whole network vs reference CPU fp32 golden: tf32 3e-3, bf16 3e-2 (numerics)
+"""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"tf32": 2e-3, "bf16": 3e-2}
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import lwpose_b200  # noqa: F401
+    from lwpose_b200 import _lib, engine
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch, _lib, engine
+
+
+class OnePlan:
+    def __init__(self, env, precision):
+        torch, _lib, engine = env
+        self.torch, self._lib, self.engine = torch, _lib, engine
+        self.L = _lib.load()
+        self.code, self.tdtype = engine._PREC[precision]
+        self.h = _lib._c_void_p()
+        _lib.check(self.L.lwp_plan_create(self.code, self.h), "create")
+        self.keep = []
+
+    def run(self, x=None):
+        _lib = self._lib
+        _lib.check(self.L.lwp_plan_run(self.h, x.data_ptr() if x is not None else None, _lib.current_stream()), "run")
+        self.torch.cuda.synchronize()
+        assert self.L.lwp_plan_error_flag(self.h) == 0, "pipeline wait timed out inside the GEMM kernel"
+
+    def close(self):
+        self.L.lwp_plan_destroy(self.h)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max())
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("shape", [
+    # (n, H, W, Cin, Cout, taps, dil, act, residual)
+    (1, 8, 16, 64, 128, 1, 1, 1, False),      # exactly one 128-pixel tile, one K block (bf16)
+    (2, 23, 41, 128, 128, 1, 1, 1, False),    # ragged M
+    (1, 46, 82, 512, 512, 1, 1, 1, False),    # 4 N tiles, 8 K blocks
+    (1, 23, 41, 32, 64, 1, 1, 1, False),      # Cin below one bf16 K block (zero-filled by TMA)
+    (1, 12, 20, 512, 128, 1, 1, 2, True),     # ELU + residual
+    (2, 16, 16, 128, 57, 1, 1, 0, False),     # head: Cout 57 -> padded 64, no activation
+    (1, 16, 8, 128, 128, 9, 1, 1, False),     # 3x3, one exact tile
+    (2, 23, 41, 128, 128, 9, 1, 1, False),    # 3x3 ragged
+    (1, 46, 82, 128, 128, 9, 2, 1, True),     # 3x3 dilation 2 + residual
+    (3, 32, 57, 128, 128, 9, 1, 1, False),    # config-1 grid
+])
+def test_conv_gemm_vs_torch(env, precision, shape):
+    torch, _lib, engine = env
+    n, H, W, Cin, Cout, taps, dil, act, use_res = shape
+    g = torch.Generator().manual_seed(hash(shape) % (2 ** 31))
+    k = 3 if taps == 9 else 1
+    x = torch.randn(n, Cin, H, W, generator=g)
+    wt = torch.randn(Cout, Cin, k, k, generator=g) * (1.0 / np.sqrt(Cin * taps))
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g) * 0.1
+    res = torch.randn(n, Cout, H, W, generator=g) if use_res else None
+    tdtype = engine._PREC[precision][1]
+    # the kernel sees operands already rounded to the storage type; give the reference the same values
+    xq = x.to(tdtype).float()
+    wq = wt.to(tdtype).float()
+    ref = torch.nn.functional.conv2d(xq.double(), wq.double(), None, 1, dil if taps == 9 else 0, dil).float()
+    ref = ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    ref = torch.relu(ref) if act == 1 else torch.nn.functional.elu(ref) if act == 2 else ref
+    if use_res:
+        ref = ref + res.to(tdtype).float()
+
+    gw = engine._GemmW(wt.cuda(), scale.cuda(), shift.cuda(), act, tdtype, dil)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(tdtype).cuda()
+    out = torch.full((n, H, W, gw.cout_pad), 7.0, dtype=tdtype, device="cuda")
+    out32 = torch.full((n, H, W, gw.cout_pad), 7.0, dtype=torch.float32, device="cuda")
+    resd = res.permute(0, 2, 3, 1).contiguous().to(tdtype).cuda() if use_res else None
+    p = OnePlan(env, precision)
+    _lib.check(p.L.lwp_plan_add_conv_gemm(p.h, xd.data_ptr(), Cin, gw.w.data_ptr(), gw.scale.data_ptr(),
+                                          gw.shift.data_ptr(), resd.data_ptr() if use_res else None, Cout,
+                                          out.data_ptr(), gw.cout_pad, out32.data_ptr(), gw.cout_pad, n, H, W, Cin,
+                                          Cout, taps, dil, act), "add")
+    p.run()
+    got32 = out32[..., :Cout].permute(0, 3, 1, 2).float().cpu()
+    got = out[..., :Cout].permute(0, 3, 1, 2).float().cpu()
+    p.close()
+    tol = 6e-3 if precision == "tf32" else 2e-2  # products are exact in fp32 accumulate; bf16 output rounding dominates
+    assert _rel(got32, ref) < (6e-3 if precision == "tf32" else 4e-3), ("f32 out", _rel(got32, ref))
+    assert _rel(got, ref) < tol * max(1.0, float(ref.abs().max())), ("typed out", _rel(got, ref))
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("shape", [
+    # (n, H, W, C, stride, dil, act)
+    (2, 24, 40, 32, 1, 1, 1), (1, 23, 41, 64, 2, 1, 1), (2, 46, 82, 512, 1, 2, 1), (1, 13, 9, 128, 1, 1, 2),
+    (1, 184, 328, 32, 1, 1, 1), (1, 92, 164, 128, 2, 1, 1),
+])
+def test_depthwise_vs_torch(env, precision, shape):
+    torch, _lib, engine = env
+    n, H, W, C, stride, dil, act = shape
+    g = torch.Generator().manual_seed(hash(shape) % (2 ** 31))
+    tdtype = engine._PREC[precision][1]
+    x = torch.randn(n, C, H, W, generator=g)
+    wt = torch.randn(C, 1, 3, 3, generator=g) * 0.3
+    scale = torch.rand(C, generator=g) + 0.5
+    shift = torch.randn(C, generator=g) * 0.1
+    xq = x.to(tdtype).float()
+    ref = torch.nn.functional.conv2d(xq, wt, None, stride, dil, dil, groups=C)
+    ref = ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    ref = torch.relu(ref) if act == 1 else torch.nn.functional.elu(ref)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    xd = x.permute(0, 2, 3, 1).contiguous().to(tdtype).cuda()
+    w9c = wt.reshape(C, 9).t().contiguous().cuda()
+    out = torch.zeros((n, Ho, Wo, C), dtype=tdtype, device="cuda")
+    sc, sh = scale.cuda(), shift.cuda()
+    p = OnePlan(env, precision)
+    _lib.check(p.L.lwp_plan_add_depthwise(p.h, xd.data_ptr(), out.data_ptr(), w9c.data_ptr(), sc.data_ptr(),
+                                          sh.data_ptr(), n, H, W, C, stride, dil, act), "add")
+    p.run()
+    got = out.permute(0, 3, 1, 2).float().cpu()
+    p.close()
+    tol = 1e-5 if precision == "tf32" else 2e-2
+    assert _rel(got, ref) < tol * max(1.0, float(ref.abs().max())), _rel(got, ref)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_stem_vs_torch(env, precision):
+    torch, _lib, engine = env
+    g = torch.Generator().manual_seed(11)
+    tdtype = engine._PREC[precision][1]
+    n, H, W = 2, 48, 72
+    x = torch.rand(n, 3, H, W, generator=g) - 0.5
+    wt = torch.randn(32, 3, 3, 3, generator=g) * 0.3
+    scale = torch.rand(32, generator=g) + 0.5
+    shift = torch.randn(32, generator=g) * 0.1
+    ref = torch.relu(torch.nn.functional.conv2d(x, wt, None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    out = torch.zeros((n, H // 2, W // 2, 32), dtype=tdtype, device="cuda")
+    wd, sc, sh, xd = wt.cuda(), scale.cuda(), shift.cuda(), x.cuda()
+    p = OnePlan(env, precision)
+    _lib.check(p.L.lwp_plan_add_stem(p.h, wd.data_ptr(), sc.data_ptr(), sh.data_ptr(), out.data_ptr(), n, H, W), "add")
+    p.run(xd)
+    got = out.permute(0, 3, 1, 2).float().cpu()
+    p.close()
+    tol = 1e-5 if precision == "tf32" else 2e-2
+    assert _rel(got, ref) < tol * max(1.0, float(ref.abs().max()))
+
+
+def _build_net(torch, name, R, gain):
+    from lwpose_b200 import synth
+    from lwpose_b200.models.with_mobilenet import PoseEstimationWithMobileNet
+    torch.manual_seed(0)
+    net = PoseEstimationWithMobileNet(num_refinement_stages=R).eval()
+    synth.randomize_bn_(net, seed=7)
+    if gain != 1.0:
+        synth.apply_head_gain_(net, gain)
+    return net
+
+
+@pytest.mark.parametrize("case", gc.net_cases(), ids=lambda c: c[0])
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_network_vs_reference_golden(env, case, precision):
+    """Whole forward against the outputs of the REAL reference (CPU fp32) on identical seeded weights."""
+    torch, _lib, engine = env
+    from lwpose_b200 import synth
+    name, R, H, W, B, gain = case
+    g = gc.load("net_golden.npz")
+    net = _build_net(torch, name, R, gain).cuda()
+    net.precision = precision
+    x = synth.synthetic_net_input(B, H, W, seed=3).cuda()
+    outs = net(x)
+    torch.cuda.synchronize()
+    assert net.engine().plan(precision, B, H, W).error_flag() == 0
+    assert len(outs) == 2 * (1 + R)
+    tol = (3e-3 if precision == "tf32" else 3e-2) * gain
+    for i, y in enumerate(outs):
+        ref = torch.from_numpy(g["net_%s_out%d" % (name, i)])
+        assert tuple(y.shape) == tuple(ref.shape) and y.dtype == torch.float32
+        err = _rel(y.cpu(), ref)
+        assert err < tol, (i, err)
+
+
+def test_state_dict_is_the_reference_layout(env):
+    torch, _, _ = env
+    g = gc.load("net_golden.npz")
+    from lwpose_b200.models.with_mobilenet import PoseEstimationWithMobileNet
+    torch.manual_seed(0)
+    net = PoseEstimationWithMobileNet(1)
+    assert list(net.state_dict().keys()) == [str(k) for k in g["net_r1_64x96_keys"]]
+
+
+def test_forward_rejects_cpu_tensors(env):
+    torch, _, _ = env
+    from lwpose_b200.models.with_mobilenet import PoseEstimationWithMobileNet
+    net = PoseEstimationWithMobileNet(1).eval().cuda()
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 64, 64))

@@ -1,0 +1,133 @@
+"""GPU parity of the post-processing kernels (through the C ABI) against the golden vectors made by the
+real reference and against the oracle.  Bit-exact: key-point tuples, pose entries, up-sampled maps."""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import lwpose_b200  # noqa: F401
+    return torch
+
+
+@pytest.mark.parametrize("idx,case", gc.resize_cases())
+def test_upsample_bit_exact_vs_cv2_golden(torch_cuda, idx, case):
+    torch = torch_cuda
+    from lwpose_b200 import postproc
+    g = gc.load("resize_golden.npz")
+    h, w, C, mode, arg = case
+    src = gc.resize_input(idx, h, w, C)
+    d = torch.from_numpy(src).cuda().unsqueeze(0)
+    out = postproc.upsample_cubic(d, fx=arg, fy=arg) if mode == "f" else postproc.upsample_cubic(d, dsize=tuple(arg))
+    got = out[0].cpu().numpy()
+    assert tuple(got.shape) == tuple(g["resize_%d_shape" % idx])
+    assert gc.sha(got) == str(g["resize_%d_sha" % idx])
+
+
+def test_upsample_strided_source_and_batch(torch_cuda):
+    """Channels taken out of a wider pixel (ld 64) for a batch: what the fused pipeline does."""
+    torch = torch_cuda
+    from lwpose_b200 import postproc
+    from oracle import postproc as orc
+    rng = np.random.default_rng(5)
+    src = rng.standard_normal((3, 11, 13, 64)).astype(np.float32)
+    d = torch.from_numpy(src).cuda()
+    got = postproc.upsample_cubic(d, channels=57, fx=4, fy=4).cpu().numpy()
+    for b in range(3):
+        ref = orc.resize_cubic(src[b, :, :, :57], fx=4, fy=4)
+        assert np.array_equal(got[b].view(np.int32), ref.view(np.int32))
+
+
+def _device_postproc(torch, hm, paf, demo, cap_kpts=256, cap_cand=4096, cap_poses=256, cap_conn=4096):
+    from lwpose_b200 import postproc
+    hm_d = torch.from_numpy(np.ascontiguousarray(hm.transpose(0, 2, 3, 1))).cuda()
+    paf_d = torch.from_numpy(np.ascontiguousarray(paf.transpose(0, 2, 3, 1))).cuda()
+    heat = postproc.upsample_cubic(hm_d, fx=4, fy=4)
+    pafs = postproc.upsample_cubic(paf_d, fx=4, fy=4)
+    kb = postproc.extract_keypoints_batched(heat, cap_kpts=cap_kpts, cap_candidates=cap_cand)
+    poses_d, n_d = postproc.group_keypoints_batched(kb, pafs, demo=demo, cap_poses=cap_poses,
+                                                    cap_connections=cap_conn)
+    kpts_h, counts_h, start_h, ovf = kb.to_host()
+    postproc.raise_on_overflow(ovf)
+    return kpts_h, counts_h, start_h, poses_d.cpu().numpy(), n_d.cpu().numpy()
+
+
+@pytest.mark.parametrize("case", gc.postproc_cases(), ids=lambda c: c[0])
+@pytest.mark.parametrize("demo", [True, False])
+def test_postproc_bit_exact_vs_reference_golden(torch_cuda, case, demo):
+    from lwpose_b200 import postproc
+    g = gc.load("postproc_golden.npz")
+    hm, paf = gc.postproc_maps(case)
+    kpts_h, counts_h, start_h, poses_h, n_h = _device_postproc(torch_cuda, hm[None], paf[None], demo)
+    by_type = postproc.keypoint_lists(kpts_h, counts_h, start_h, 0)
+    tag = "pp_%s_%s" % (case[0], "demo" if demo else "val")
+    assert np.array_equal(gc.pack_keypoints(by_type), g[tag + "_kpts"])
+    poses = np.asarray(postproc.pose_entries_array(poses_h, n_h, 0), np.float64).reshape(-1, 20)
+    assert poses.shape == g[tag + "_poses"].shape
+    assert np.array_equal(poses.view(np.int64), g[tag + "_poses"].view(np.int64))
+
+
+def test_postproc_batch_vs_oracle(torch_cuda):
+    """A batch with 1..12 persons + noise, every frame checked against the oracle (bit-exact)."""
+    from lwpose_b200 import postproc, synth
+    from oracle import postproc as orc
+    hm, paf, _ = synth.synthetic_pose_maps(12, 46, 82, seed=3, noise=0.02, max_persons=12)
+    for demo in (True, False):
+        kpts_h, counts_h, start_h, poses_h, n_h = _device_postproc(torch_cuda, hm, paf, demo)
+        for b in range(hm.shape[0]):
+            heat = orc.resize_cubic(np.ascontiguousarray(hm[b].transpose(1, 2, 0)), fx=4, fy=4)
+            pafs = orc.resize_cubic(np.ascontiguousarray(paf[b].transpose(1, 2, 0)), fx=4, fy=4)
+            total, ref_by_type = 0, []
+            for k in range(18):
+                total += orc.extract_keypoints(heat[:, :, k], ref_by_type, total)
+            ref_poses, _ = orc.group_keypoints(ref_by_type, pafs, demo=demo)
+            got = postproc.keypoint_lists(kpts_h, counts_h, start_h, b)
+            assert np.array_equal(gc.pack_keypoints(got), gc.pack_keypoints(ref_by_type)), b
+            gp = np.asarray(postproc.pose_entries_array(poses_h, n_h, b), np.float64).reshape(-1, 20)
+            rp = np.asarray(ref_poses, np.float64).reshape(-1, 20)
+            assert gp.shape == rp.shape and np.array_equal(gp.view(np.int64), rp.view(np.int64)), b
+
+
+def test_overflow_is_reported_not_silent(torch_cuda):
+    from lwpose_b200 import postproc
+    case = [c for c in gc.postproc_cases() if c[0] == "noise_only"][0]
+    hm, paf = gc.postproc_maps(case)
+    with pytest.raises(postproc.CapacityOverflow):
+        _device_postproc(torch_cuda, hm[None], paf[None], True, cap_kpts=8, cap_cand=64)
+
+
+def test_dropin_functions_match_golden(torch_cuda):
+    """The reference-signature wrappers: host arrays in, Python lists / float64 arrays out, input
+    heat-map thresholded in place."""
+    from lwpose_b200.modules.keypoints import extract_keypoints, group_keypoints
+    from oracle import postproc as orc
+    g = gc.load("postproc_golden.npz")
+    case = [c for c in gc.postproc_cases() if c[0] == "p5n"][0]
+    hm, paf = gc.postproc_maps(case)
+    heat = orc.resize_cubic(np.ascontiguousarray(hm.transpose(1, 2, 0)), fx=4, fy=4)
+    pafs = orc.resize_cubic(np.ascontiguousarray(paf.transpose(1, 2, 0)), fx=4, fy=4)
+    before = heat.copy()
+    total, by_type = 0, []
+    for k in range(18):
+        total += extract_keypoints(heat[:, :, k], by_type, total)
+    assert np.array_equal(gc.pack_keypoints(by_type), g["pp_p5n_demo_kpts"])
+    expect = before[:, :, :18].copy()
+    expect[expect < 0.1] = 0
+    assert np.array_equal(heat[:, :, :18], expect)  # side effect of the reference (:17)
+    x, y, s, i = by_type[0][0]
+    assert isinstance(x, np.int64) and isinstance(s, np.float32) and isinstance(i, int)
+    for demo, tag in ((True, "demo"), (False, "val")):
+        poses, allk = group_keypoints(by_type, pafs, demo=demo)
+        assert poses.dtype == np.float64 and allk.dtype == np.float64
+        assert np.array_equal(poses.view(np.int64), g["pp_p5n_%s_poses" % tag].view(np.int64))
+        assert np.array_equal(allk.view(np.int64), g["pp_p5n_%s_allk" % tag].view(np.int64))
+    empty = [[] for _ in range(18)]
+    poses, allk = group_keypoints(empty, pafs, demo=True)
+    assert poses.shape == (0,) and allk.shape == (0,)
