@@ -1,0 +1,364 @@
+"""bench.py -- frames/s of the Lightweight OpenPose inference hot path (network + cubic up-sample +
+key-point extraction + PAF grouping) at 368x656, on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|tf32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch of 64 synthetic frames per GPU (BASELINE.json
+configs[1]: PoseEstimationWithMobileNet, 1 refinement stage, random-init weights, 64x3x368x656).
+Random-init weights cannot produce person-like maps, so seeded synthetic person maps (configs[2]
+generator, 1..30 persons per frame) are added to the network's head output between the network and
+the post-processing; both arms do the same.  Frames are sharded data-parallel (weak scaling, no
+collective on the compute path).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HEIGHT, WIDTH, REFINE = 368, 656, 1
+METRIC = "frames/s end-to-end (net+grouping) @368x656"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--max-persons", type=int, default=30)
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the workload timed for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], bf16=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, bf16=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) != 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:]):
+                if v.lower() == "active":
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def make_net(seed=0):
+    import torch
+    import lwpose_b200  # noqa: F401
+    from lwpose_b200 import synth
+    from lwpose_b200.models.with_mobilenet import PoseEstimationWithMobileNet
+    torch.manual_seed(seed)
+    net = PoseEstimationWithMobileNet(num_refinement_stages=REFINE).eval()
+    synth.randomize_bn_(net, seed=7)
+    return net
+
+
+def person_maps(batch, rank, max_persons):
+    """[batch, 46, 82, 64] float32: synthetic person heat-maps / PAFs in head-buffer layout."""
+    import numpy as np
+    from lwpose_b200 import synth
+    hm, paf, counts = synth.synthetic_pose_maps(batch, HEIGHT // 8, WIDTH // 8, seed=100 + rank, max_persons=max_persons)
+    m = np.zeros((batch, HEIGHT // 8, WIDTH // 8, 64), np.float32)
+    m[..., :19] = hm.transpose(0, 2, 3, 1)
+    m[..., 19:57] = paf.transpose(0, 2, 3, 1)
+    return m, counts
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's CPU path (reference itself is not on the GPU box)
+# ----------------------------------------------------------------------------------------------
+def cpu_frame(state_dict, x1, inject1):
+    """One frame through the CPU path: torch-CPU forward, cubic x4, 18 x extract, group (demo=True)."""
+    import numpy as np
+    from oracle import net as onet
+    from oracle import postproc as orc
+    outs = onet.forward(state_dict, x1)
+    hm = outs[-2][0].numpy().transpose(1, 2, 0) + inject1[..., :19]
+    paf = outs[-1][0].numpy().transpose(1, 2, 0) + inject1[..., 19:57]
+    heat = orc.resize_cubic(np.ascontiguousarray(hm), fx=4, fy=4)
+    pafs = orc.resize_cubic(np.ascontiguousarray(paf), fx=4, fy=4)
+    total, by_type = 0, []
+    for k in range(18):
+        total += orc.extract_keypoints(heat[:, :, k], by_type, total)
+    poses, _ = orc.group_keypoints(by_type, pafs, demo=True)
+    return len(poses)
+
+
+def cpu_time_frames(state_dict, x, inject, frames, warm=1):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    for i in range(warm):
+        cpu_frame(state_dict, x[i:i + 1], inject[i])
+    t0 = time.perf_counter()
+    for i in range(frames):
+        cpu_frame(state_dict, x[i % x.shape[0]:i % x.shape[0] + 1], inject[i % inject.shape[0]])
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from lwpose_b200 import synth
+    net = make_net()
+    sd = net.state_dict()
+    frames = max(1, min(args.cpu_frames, 4))
+    x = synth.synthetic_net_input(frames, HEIGHT, WIDTH, seed=1)
+    inject, _ = person_maps(frames, 0, args.max_persons)
+    for _ in range(max(0, min(args.warmup, 2))):
+        cpu_time_frames(sd, x, inject, 1, warm=0)
+    times = [cpu_time_frames(sd, x, inject, frames, warm=0) for _ in range(args.steps)]
+    total = sum(times)
+    value = frames * args.steps / total
+    cores = torch.get_num_threads()
+    sample = "%d frames/step of the %dx3x%dx%d workload, batch-1 loop (torch CPU fp32 + C oracle post-processing)" % (
+        frames, args.batch, HEIGHT, WIDTH)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, world):
+    return {"workload": "configs[1]: PoseEstimationWithMobileNet R=%d random-init (seed 0, randomised BN), %d frames/GPU "
+                        "x 3x%dx%d, + synthetic 1..%d-person maps added to the head output, cubic x4, extract, group "
+                        "(demo=True)" % (REFINE, args.batch, HEIGHT, WIDTH, args.max_persons),
+            "frames_per_gpu_per_step": args.batch, "global_batch": args.batch * world,
+            "parallelism": "dp%d (frames sharded, no collective on the compute path)" % world,
+            "l2": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (args.batch * 3 * HEIGHT * WIDTH * 4 / 1e6)}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import lwpose_b200  # noqa: F401
+    from lwpose_b200 import parallel, synth
+    from lwpose_b200.pipeline import PosePipeline
+
+    net = make_net().to(dev)
+    inject_h, persons = person_maps(args.batch, rank, args.max_persons)
+    inject = torch.from_numpy(inject_h).to(dev)
+    pipe = PosePipeline(net, args.batch, HEIGHT, WIDTH, precision=args.precision, demo=True,
+                        heads_hook=lambda heads: heads.add_(inject))
+    x_host = synth.synthetic_net_input(args.batch, HEIGHT, WIDTH, seed=1 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        pipe.run_device(x_dev)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        pipe.run_device(x_dev)
+    e1.record()
+    barrier()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev) / args.steps
+    clocks = sampler.stop() if sampler else None
+    if pipe.error_flag() != 0:
+        raise RuntimeError("GEMM pipeline wait timed out (error flag %d)" % pipe.error_flag())
+    value = world * args.batch / (ms / 1000.0)
+
+    # ---- end to end through the public API: pinned host frames in, host pose tables out ----------
+    for _ in range(2):
+        pipe(x_host)
+    barrier()
+    t_e2e = []
+    for _ in range(args.steps):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(pipe.stream):
+            s0.record()
+        res = pipe(x_host)
+        with torch.cuda.stream(pipe.stream):
+            s1.record()
+        s1.synchronize()
+        t_e2e.append(s0.elapsed_time(s1))
+    barrier()
+    res.check()
+    e2e_ms = parallel.max_over_ranks(sum(t_e2e) / len(t_e2e), device=dev)
+    e2e_value = world * args.batch / (e2e_ms / 1000.0)
+    total_poses = res.total_poses()
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": pipe.h2d_bytes,
+                "d2h_bytes_per_step": pipe.d2h_bytes},
+        "gpu_launches": pipe.launches_per_step * args.steps,
+        "clocks": clocks,
+        "poses_per_step_rank0": total_poses, "persons_injected_rank0": int(sum(persons)),
+    }
+
+    if rank == 0 and not args.no_roofline:
+        out.update(roofline_pass(pipe, x_dev, args))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"], out["postproc_parity"] = cpu_baseline(net, pipe, x_host, inject_h, res, args)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def roofline_pass(pipe, x_dev, args):
+    """Per-kernel device time (CUDA events on the launching stream, op by op, after the timed region) ->
+    achieved TFLOP/s of the tcgen05 GEMM kernel and GB/s of the depthwise kernel vs the measured peaks."""
+    import torch
+    plan = pipe.plan
+    pk = peaks()
+    reps = max(3, min(args.steps, 10))
+    nops = plan.num_compute_ops
+    times = [0.0] * nops
+    for i in range(nops):
+        plan.run(x_dev, i, i + 1)  # warm
+    torch.cuda.synchronize()
+    for _ in range(reps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(nops + 1)]
+        evs[0].record()
+        for i in range(nops):
+            plan.run(x_dev, i, i + 1)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        for i in range(nops):
+            times[i] += evs[i].elapsed_time(evs[i + 1]) / reps
+    agg = {}
+    for meta, t in zip(plan.op_meta[:nops], times):
+        a = agg.setdefault(meta["kind"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+        a["ms"] += t; a["flops"] += meta["flops"]; a["bytes"] += meta["bytes"]; a["launches"] += 1
+    gemm_ms = sum(agg[k]["ms"] for k in agg if k.startswith("gemm"))
+    gemm_flops = sum(agg[k]["flops"] for k in agg if k.startswith("gemm"))
+    gemm_launches = sum(agg[k]["launches"] for k in agg if k.startswith("gemm"))
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    peak = pk["bf16"] if args.precision == "bf16" else pk["bf16"] / 2.0
+    res = {"roofline": {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all %d launches of a step)" % gemm_launches,
+                        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                        "frac": achieved / peak, "traffic": None,
+                        "peak_source": pk["source"] + (" bf16 sustained" if args.precision == "bf16"
+                                                       else " bf16 sustained / 2 (tf32 nominal ratio)"),
+                        "ms_per_step": gemm_ms}}
+    if "depthwise" in agg:
+        d = agg["depthwise"]
+        gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        res["roofline_depthwise"] = {"kernel": "depthwise3x3_kernel (%d launches)" % d["launches"], "bound": "hbm",
+                                     "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                                     "traffic": None, "ms_per_step": d["ms"]}
+    res["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in agg.items()}
+    res["layer_ms"] = {n: round(t, 4) for n, t in zip(plan.op_names[:nops], times)}
+    return res
+
+
+def cpu_baseline(net, pipe, x_host, inject_h, res, args):
+    """The oracle port of the reference's CPU path timed on this box's host cores on a bounded sample,
+    plus a bit-exactness check of the GPU post-processing against the oracle on the GPU's own maps."""
+    import numpy as np
+    import torch
+    from lwpose_b200 import postproc
+    from oracle import postproc as orc
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    frames = max(1, min(args.cpu_frames, args.batch))
+    dt = cpu_time_frames(sd, x_host[:frames], inject_h[:frames], frames)
+    base = {"value": frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d of the %d frames of one step, batch-1 loop: torch CPU fp32 forward + C oracle cubic x4 / "
+                      "extract / group" % (frames, args.batch)}
+    # parity: oracle post-processing on the maps the GPU actually produced (heads + injected persons)
+    heads = pipe.heads.cpu().numpy()
+    checked = 0
+    for b in range(min(4, args.batch)):
+        heat = orc.resize_cubic(np.ascontiguousarray(heads[b, :, :, :19]), fx=4, fy=4)
+        pafs = orc.resize_cubic(np.ascontiguousarray(heads[b, :, :, 19:57]), fx=4, fy=4)
+        total, by_type = 0, []
+        for k in range(18):
+            total += orc.extract_keypoints(heat[:, :, k], by_type, total)
+        ref_poses, _ = orc.group_keypoints(by_type, pafs, demo=True)
+        got_poses, _ = res.frame(b)
+        rp = np.asarray(ref_poses, np.float64).reshape(-1, 20)
+        gp = np.asarray(got_poses, np.float64).reshape(-1, 20)
+        if rp.shape != gp.shape or not np.array_equal(rp.view(np.int64), gp.view(np.int64)):
+            return base, "MISMATCH on frame %d" % b
+        checked += 1
+    return base, "bit-exact pose tables vs oracle on %d frames" % checked
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,7 @@ class _GemmW:
         cout, cin, kh, kw = weight.shape
         self.taps = kh * kw
         w = weight.permute(0, 2, 3, 1).reshape(cout, self.taps, cin)
+        self.cin_real = cin
         if cin_pad is not None and cin_pad != cin:
             w = torch.cat([w, torch.zeros(cout, self.taps, cin_pad - cin, device=w.device)], 2)
             cin = cin_pad
@@ -116,6 +117,7 @@ def _merge_heads(hm_seq, paf_seq, tdtype):
     w2[:nh, :mid_h] = h2.weight
     w2[nh:, mid_h:] = p2.weight
     second = _GemmW(w2, torch.cat([h2.scale, p2.scale]), torch.cat([h2.shift, p2.shift]), h2.act, tdtype)
+    second.flops_per_px = 2.0 * (mid_h * nh + mid_p * np_)  # algorithmic: the zero blocks do not count
     return first, second
 
 
@@ -167,6 +169,7 @@ class Plan:
         self.handle = handle
         self.bufs = []
         self.op_names = []
+        self.op_meta = []  # per op: kind, algorithmic flops and bytes (real channel counts, no padding)
         self._build(packed, n_stages_out, num_heatmaps, num_pafs)
 
     def __del__(self):
@@ -193,12 +196,25 @@ class Plan:
             out_f32.data_ptr() if out_f32 is not None else None, out_f32_ld, n, H, W, g.cin, g.cout, g.taps,
             g.dilation, g.act), "lwp_plan_add_conv_gemm(%s)" % name)
         self.op_names.append(name)
+        cin_real = getattr(g, "cin_real", g.cin)
+        px = n * H * W
+        nbytes = px * (cin_real + g.cout) * es + g.taps * cin_real * g.cout * es
+        if residual is not None:
+            nbytes += px * g.cout * es
+        if out_f32 is not None:
+            nbytes += px * g.cout * 4
+        self.op_meta.append(dict(kind="gemm3x3" if g.taps == 9 else "gemm1x1", flops=px * getattr(g, "flops_per_px", 2.0 * cin_real * g.cout * g.taps),
+                                 bytes=float(nbytes)))
 
     def _dw(self, name, src, dst, d, n, H, W):
         _lib.check(self.lib.lwp_plan_add_depthwise(self.handle, src.data_ptr(), dst.data_ptr(), d.w.data_ptr(),
                                                    d.scale.data_ptr(), d.shift.data_ptr(), n, H, W, d.c, d.stride,
                                                    d.dilation, d.act), "lwp_plan_add_depthwise(%s)" % name)
         self.op_names.append(name)
+        es = 2 if self.tdtype == torch.bfloat16 else 4
+        ho, wo = (H - 1) // d.stride + 1, (W - 1) // d.stride + 1
+        self.op_meta.append(dict(kind="depthwise", flops=2.0 * 9 * n * ho * wo * d.c,
+                                 bytes=float((n * H * W * d.c + n * ho * wo * d.c) * es + 9 * d.c * 4)))
 
     # -- the layer walk -----------------------------------------------------------------------
     def _build(self, P, n_stages_out, num_heatmaps, num_pafs):
@@ -220,6 +236,9 @@ class Plan:
         _lib.check(self.lib.lwp_plan_add_stem(self.handle, w_.data_ptr(), s_.data_ptr(), b_.data_ptr(),
                                               pp[0].data_ptr(), n, H, W), "lwp_plan_add_stem")
         self.op_names.append("model.0")
+        es_ = 2 if self.tdtype == torch.bfloat16 else 4
+        self.op_meta.append(dict(kind="stem", flops=2.0 * 27 * 32 * n * (H // 2) * (W // 2),
+                                 bytes=float(n * 3 * H * W * 4 + n * (H // 2) * (W // 2) * 32 * es_)))
         hh, ww, c, cur = H // 2, W // 2, 32, 0
         for i, (dw, pw) in enumerate(P.backbone):
             ho, wo = (hh - 1) // dw.stride + 1, (ww - 1) // dw.stride + 1
@@ -287,6 +306,7 @@ class Plan:
                                                               c0_, cc, t.data_ptr(), n, h, w),
                            "lwp_plan_add_nhwc_to_nchw")
                 self.op_names.append("to_nchw.%d" % s)
+                self.op_meta.append(dict(kind="layout", flops=0.0, bytes=float(2 * n * cc * h * w * 4)))
             self.outputs += [hm, paf]
 
     # -- execution ----------------------------------------------------------------------------

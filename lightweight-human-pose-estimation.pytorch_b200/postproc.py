@@ -23,13 +23,15 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
-def upsample_cubic(src, channels=None, fx=None, fy=None, dsize=None, out=None):
-    """src: float32 cuda tensor [n, h, w, ld] (NHWC, `channels` <= ld used).  Either fx/fy (like
-    cv2.resize(src, (0, 0), fx=, fy=)) or dsize=(W, H).  Returns [n, H, W, channels] float32."""
+def upsample_cubic(src, channels=None, fx=None, fy=None, dsize=None, out=None, channel_offset=0):
+    """src: float32 cuda tensor [n, h, w, ld] (NHWC; channels [channel_offset, channel_offset + channels)
+    of every pixel are resized).  Either fx/fy (like cv2.resize(src, (0, 0), fx=, fy=)) or dsize=(W, H).
+    Returns [n, H, W, channels] float32."""
     L = _lib.load()
     assert src.is_cuda and src.dtype == torch.float32 and src.dim() == 4 and src.is_contiguous()
     n, h, w, ld = src.shape
-    c = ld if channels is None else int(channels)
+    c = ld - channel_offset if channels is None else int(channels)
+    assert 0 <= channel_offset and channel_offset + c <= ld
     if dsize is None:
         inv_x, inv_y = float(fx), float(fy)
         W, H = int(np.rint(w * inv_x)), int(np.rint(h * inv_y))
@@ -40,8 +42,8 @@ def upsample_cubic(src, channels=None, fx=None, fy=None, dsize=None, out=None):
         out = torch.empty((n, H, W, c), dtype=torch.float32, device=src.device)
     else:
         assert out.shape == (n, H, W, c) and out.is_contiguous() and out.dtype == torch.float32
-    _lib.check(L.lwp_upsample_cubic(_ptr(src), n, h, w, c, ld, _ptr(out), H, W, inv_x, inv_y, _lib.current_stream()),
-               "lwp_upsample_cubic")
+    _lib.check(L.lwp_upsample_cubic(_ptr(src) + 4 * channel_offset, n, h, w, c, ld, _ptr(out), H, W, inv_x, inv_y,
+                                    _lib.current_stream()), "lwp_upsample_cubic")
     return out
 
 

@@ -100,3 +100,29 @@ def test_resize_matches_live_cv2(seed):
         got = orc.resize_cubic(src, fx=f, fy=f)
     ref = ref.reshape(got.shape)
     assert np.array_equal(got.view(np.int32), ref.view(np.int32)), (h, w, C, got.shape)
+
+
+@pytest.mark.parametrize("case", gc.net_cases(), ids=lambda c: c[0])
+def test_net_oracle_matches_reference_golden(case):
+    """oracle/net.py (functional torch-CPU restatement) vs outputs of the real reference module."""
+    import torch
+    from lwpose_b200 import synth
+    from lwpose_b200.models.with_mobilenet import PoseEstimationWithMobileNet
+    from oracle import net as onet
+    name, R, H, W, B, gain = case
+    g = gc.load("net_golden.npz")
+    torch.manual_seed(0)
+    net = PoseEstimationWithMobileNet(num_refinement_stages=R).eval()
+    sd = net.state_dict()
+    import numpy as np
+    assert gc.sha(np.concatenate([v.numpy().astype(np.float64).ravel() for v in sd.values()])) == \
+        str(g["net_%s_init_sha" % name]), "seeded initialisation differs from the reference's"
+    synth.randomize_bn_(net, seed=7)
+    if gain != 1.0:
+        synth.apply_head_gain_(net, gain)
+    torch.set_num_threads(1)
+    outs = onet.forward(net.state_dict(), synth.synthetic_net_input(B, H, W, seed=3))
+    assert len(outs) == 2 * (1 + R)
+    for i, y in enumerate(outs):
+        ref = torch.from_numpy(g["net_%s_out%d" % (name, i)])
+        assert float((y - ref).abs().max()) < 2e-6 * gain, i

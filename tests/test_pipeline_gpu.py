@@ -1,0 +1,124 @@
+"""GPU tests of the fused batched pipeline and of the drop-in infer_fast / infer mirrors."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import lwpose_b200  # noqa: F401
+    from lwpose_b200 import synth
+    from lwpose_b200.models.with_mobilenet import PoseEstimationWithMobileNet
+    torch.manual_seed(0)
+    net = PoseEstimationWithMobileNet(num_refinement_stages=1).eval()
+    synth.randomize_bn_(net, seed=7)
+    return torch, net.cuda()
+
+
+def _oracle_post(heads_b, demo):
+    from oracle import postproc as orc
+    heat = orc.resize_cubic(np.ascontiguousarray(heads_b[:, :, :19]), fx=4, fy=4)
+    pafs = orc.resize_cubic(np.ascontiguousarray(heads_b[:, :, 19:57]), fx=4, fy=4)
+    total, by_type = 0, []
+    for k in range(18):
+        total += orc.extract_keypoints(heat[:, :, k], by_type, total)
+    return by_type, orc.group_keypoints(by_type, pafs, demo=demo)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_pipeline_end_to_end(env, precision):
+    """Host frames in -> host pose tables out; heads within tolerance of the CPU fp32 oracle, and the
+    pose tables bit-exact against the oracle run on the very maps the GPU produced."""
+    torch, net = env
+    import golden_cases as gc
+    from lwpose_b200 import synth
+    from lwpose_b200.pipeline import PosePipeline
+    from oracle import net as onet
+    B, H, W = 4, 128, 192
+    hm, paf, _ = synth.synthetic_pose_maps(B, H // 8, W // 8, seed=9, max_persons=3)
+    inj = np.zeros((B, H // 8, W // 8, 64), np.float32)
+    inj[..., :19] = hm.transpose(0, 2, 3, 1)
+    inj[..., 19:57] = paf.transpose(0, 2, 3, 1)
+    inj_d = torch.from_numpy(inj).cuda()
+    pipe = PosePipeline(net, B, H, W, precision=precision, demo=True, heads_hook=lambda t: t.add_(inj_d))
+    x = synth.synthetic_net_input(B, H, W, seed=2)
+    res = pipe(x.pin_memory()).check()
+    assert pipe.error_flag() == 0
+    heads = pipe.heads.cpu().numpy()
+    ref = onet.forward(net.state_dict(), x)
+    ref_heads = np.concatenate([ref[-2].numpy(), ref[-1].numpy()], 1).transpose(0, 2, 3, 1) + inj[..., :57]
+    tol = 3e-3 if precision == "tf32" else 3e-2
+    assert np.abs(heads[..., :57] - ref_heads).max() < tol
+    assert np.all(heads[..., 57:] == 0)
+    n_total = 0
+    for b in range(B):
+        by_type, (ref_poses, ref_allk) = _oracle_post(heads[b], True)
+        assert gc.pack_keypoints(res.keypoints_by_type(b)).tolist() == gc.pack_keypoints(by_type).tolist()
+        poses, allk = res.frame(b)
+        rp = np.asarray(ref_poses, np.float64).reshape(-1, 20)
+        gp = np.asarray(poses, np.float64).reshape(-1, 20)
+        assert rp.shape == gp.shape and np.array_equal(rp.view(np.int64), gp.view(np.int64))
+        assert np.array_equal(np.asarray(allk, np.float64), np.asarray(ref_allk, np.float64))
+        n_total += len(rp)
+    assert n_total >= B  # the injected persons were found
+    # device-resident entry point gives the same tables
+    pipe.run_device(x.cuda())
+    torch.cuda.synchronize()
+    assert int(pipe.n_poses.sum()) == n_total
+
+
+def test_infer_fast_matches_oracle(env):
+    """demo.infer_fast mirror: same return signature; maps = cubic x4 of the network output (bit-exact
+    resize of our own heads, heads within tolerance of the CPU oracle)."""
+    torch, net = env
+    from lwpose_b200 import demo
+    from oracle import postproc as orc
+    net.precision = "tf32"
+    img = np.random.default_rng(0).integers(0, 256, (180, 320, 3), dtype=np.uint8)
+    heat, pafs, scale, pad = demo.infer_fast(net, img, 128, 8, 4, False)
+    assert heat.dtype == np.float32 and heat.shape[2] == 19 and pafs.shape[2] == 38
+    assert scale == 128 / 180 and len(pad) == 4
+    H, W = heat.shape[0] // 4 * 8, heat.shape[1] // 4 * 8
+    plan = net.engine().plan("tf32", 1, H, W)
+    heads = plan.heads_f32[-1].view(1, H // 8, W // 8, 64).cpu().numpy()[0]
+    assert np.array_equal(heat.view(np.int32), orc.resize_cubic(heads[:, :, :19].copy(), fx=4, fy=4).view(np.int32))
+    assert np.array_equal(pafs.view(np.int32), orc.resize_cubic(heads[:, :, 19:57].copy(), fx=4, fy=4).view(np.int32))
+    with pytest.raises(RuntimeError):
+        demo.infer_fast(net, img, 128, 8, 4, True)
+    poses, allk = demo.run_frame(net, img, 128)
+    assert poses.shape == (0,) or poses.shape[1] == 20
+
+
+def test_val_infer_multiscale_matches_oracle(env):
+    """val.infer mirror (multi-scale, x8 cubic, crop, resize to the image size, average)."""
+    torch, net = env
+    import cv2
+    from lwpose_b200 import val
+    from oracle import net as onet
+    from oracle import postproc as orc
+    net.precision = "tf32"
+    img = np.random.default_rng(1).integers(0, 256, (96, 128, 3), dtype=np.uint8)
+    scales, base = [0.5, 1.0], 64
+    got_h, got_p = val.infer(net, img, scales, base, 8)
+    assert got_h.shape == (96, 128, 19) and got_p.shape == (96, 128, 38) and got_h.dtype == np.float32
+    # oracle restatement of val.py:81-110 with the CPU fp32 network
+    normed = val.normalize(img, (128, 128, 128), 1 / 256)
+    avg_h = np.zeros((96, 128, 19), np.float32)
+    avg_p = np.zeros((96, 128, 38), np.float32)
+    for s in scales:
+        ratio = s * base / 96.0
+        scaled = cv2.resize(normed, (0, 0), fx=ratio, fy=ratio, interpolation=cv2.INTER_CUBIC)
+        padded, pad = val.pad_width(scaled, 8, (0, 0, 0), [base, max(scaled.shape[1], base)])
+        x = torch.from_numpy(padded).permute(2, 0, 1).unsqueeze(0).float()
+        outs = onet.forward(net.state_dict(), x)
+        for o, avg in ((outs[-2], avg_h), (outs[-1], avg_p)):
+            m = np.ascontiguousarray(o[0].numpy().transpose(1, 2, 0))
+            m = orc.resize_cubic(m, fx=8, fy=8)
+            m = m[pad[0]:m.shape[0] - pad[2], pad[1]:m.shape[1] - pad[3], :]
+            m = orc.resize_cubic(np.ascontiguousarray(m), dsize=(128, 96))
+            avg += m / len(scales)
+    assert np.abs(got_h - avg_h).max() < 3e-3 and np.abs(got_p - avg_p).max() < 3e-3

@@ -65,7 +65,8 @@ def test_postproc_bit_exact_vs_reference_golden(torch_cuda, case, demo):
     from lwpose_b200 import postproc
     g = gc.load("postproc_golden.npz")
     hm, paf = gc.postproc_maps(case)
-    kpts_h, counts_h, start_h, poses_h, n_h = _device_postproc(torch_cuda, hm[None], paf[None], demo)
+    kpts_h, counts_h, start_h, poses_h, n_h = _device_postproc(torch_cuda, hm[None], paf[None], demo,
+                                                               cap_poses=2048, cap_conn=8192)
     by_type = postproc.keypoint_lists(kpts_h, counts_h, start_h, 0)
     tag = "pp_%s_%s" % (case[0], "demo" if demo else "val")
     assert np.array_equal(gc.pack_keypoints(by_type), g[tag + "_kpts"])
