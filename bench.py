@@ -14,9 +14,7 @@ collective on the compute path).  One JSON line is printed by rank 0.
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -51,48 +49,58 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML in a background thread DURING the timed region."""
 
-    def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, index, period_s=0.002):
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.p = None
+            self.nv = None
+            return
+        self.period = period_s
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for nm, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        if self._thread is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) != 6:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[2:]):
-                if v.lower() == "active":
-                    reasons.add(nm)
-        self.f.close()
-        os.unlink(self.f.name)
-        if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if self.samples:
+            sm = sorted(self.samples)
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                   "samples": len(sm)}
         return out
 
 
@@ -270,10 +278,10 @@ def main():
         "poses_per_step_rank0": total_poses, "persons_injected_rank0": int(sum(persons)),
     }
 
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # before the roofline pass re-runs single layers
+        out["cpu_baseline"], out["postproc_parity"] = cpu_baseline(net, pipe, x_host, inject_h, res, args)
     if rank == 0 and not args.no_roofline:
         out.update(roofline_pass(pipe, x_dev, args))
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"], out["postproc_parity"] = cpu_baseline(net, pipe, x_host, inject_h, res, args)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -324,8 +332,40 @@ def roofline_pass(pipe, x_dev, args):
                                      "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                                      "traffic": None, "ms_per_step": d["ms"]}
     res["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in agg.items()}
+    res["kernel_ms_per_step"].update(postproc_stage_ms(pipe, x_dev, reps))
     res["layer_ms"] = {n: round(t, 4) for n, t in zip(plan.op_names[:nops], times)}
     return res
+
+
+def postproc_stage_ms(pipe, x_dev, reps):
+    """Device time of the post-processing stages of one step (events on the launching stream)."""
+    import torch
+    from lwpose_b200 import postproc
+    pipe.run_device(x_dev)  # leaves net output + injected persons in the head buffer
+    heads = pipe.heads
+    ck, cc, cp, cn = pipe.caps
+    stages = {
+        "upsample": lambda: (postproc.upsample_cubic(heads, channels=19, fx=4, fy=4, out=pipe.heat_up),
+                             postproc.upsample_cubic(heads, channels=38, fx=4, fy=4, out=pipe.paf_up,
+                                                     channel_offset=19)),
+        "extract": lambda: postproc.extract_keypoints_batched(pipe.heat_up, cap_kpts=ck, cap_candidates=cc,
+                                                              workspace=pipe.ws_extract, out=pipe.kb),
+        "group": lambda: postproc.group_keypoints_batched(pipe.kb, pipe.paf_up, demo=pipe.demo, cap_poses=cp,
+                                                          cap_connections=cn, workspace=pipe.ws_group,
+                                                          out=(pipe.pose_entries, pipe.n_poses)),
+    }
+    out = {}
+    for name, fn in stages.items():
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        out[name] = round(a.elapsed_time(b) / reps, 4)
+    return out
 
 
 def cpu_baseline(net, pipe, x_host, inject_h, res, args):
