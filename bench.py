@@ -36,6 +36,7 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the workload timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--unfused-postproc", action="store_true", help="materialise the up-sampled maps like the reference")
     return ap.parse_args()
 
 
@@ -219,7 +220,7 @@ def main():
     inject_h, persons = person_maps(args.batch, rank, args.max_persons)
     inject = torch.from_numpy(inject_h).to(dev)
     pipe = PosePipeline(net, args.batch, HEIGHT, WIDTH, precision=args.precision, demo=True,
-                        heads_hook=lambda heads: heads.add_(inject))
+                        heads_hook=lambda heads: heads.add_(inject), fused=not args.unfused_postproc)
     x_host = synth.synthetic_net_input(args.batch, HEIGHT, WIDTH, seed=1 + rank).pin_memory()
     x_dev = x_host.to(dev)
 
@@ -344,16 +345,26 @@ def postproc_stage_ms(pipe, x_dev, reps):
     pipe.run_device(x_dev)  # leaves net output + injected persons in the head buffer
     heads = pipe.heads
     ck, cc, cp, cn = pipe.caps
-    stages = {
-        "upsample": lambda: (postproc.upsample_cubic(heads, channels=19, fx=4, fy=4, out=pipe.heat_up),
-                             postproc.upsample_cubic(heads, channels=38, fx=4, fy=4, out=pipe.paf_up,
-                                                     channel_offset=19)),
-        "extract": lambda: postproc.extract_keypoints_batched(pipe.heat_up, cap_kpts=ck, cap_candidates=cc,
-                                                              workspace=pipe.ws_extract, out=pipe.kb),
-        "group": lambda: postproc.group_keypoints_batched(pipe.kb, pipe.paf_up, demo=pipe.demo, cap_poses=cp,
-                                                          cap_connections=cn, workspace=pipe.ws_group,
-                                                          out=(pipe.pose_entries, pipe.n_poses)),
-    }
+    if pipe.fused:
+        stages = {
+            "extract_fused": lambda: postproc.extract_keypoints_fused(heads, pipe.ratio, cap_kpts=ck, cap_candidates=cc,
+                                                                      workspace=pipe.ws_extract, out=pipe.kb),
+            "group_fused": lambda: postproc.group_keypoints_fused(pipe.kb, heads, pipe.ratio, demo=pipe.demo,
+                                                                  cap_poses=cp, cap_connections=cn,
+                                                                  workspace=pipe.ws_group,
+                                                                  out=(pipe.pose_entries, pipe.n_poses)),
+        }
+    else:
+        stages = {
+            "upsample": lambda: (postproc.upsample_cubic(heads, channels=19, fx=4, fy=4, out=pipe.heat_up),
+                                 postproc.upsample_cubic(heads, channels=38, fx=4, fy=4, out=pipe.paf_up,
+                                                         channel_offset=19)),
+            "extract": lambda: postproc.extract_keypoints_batched(pipe.heat_up, cap_kpts=ck, cap_candidates=cc,
+                                                                  workspace=pipe.ws_extract, out=pipe.kb),
+            "group": lambda: postproc.group_keypoints_batched(pipe.kb, pipe.paf_up, demo=pipe.demo, cap_poses=cp,
+                                                              cap_connections=cn, workspace=pipe.ws_group,
+                                                              out=(pipe.pose_entries, pipe.n_poses)),
+        }
     out = {}
     for name, fn in stages.items():
         fn()

@@ -88,6 +88,19 @@ int lwp_extract_keypoints(const float *hm, int n, int H, int W, int ld, int n_ch
                           int32_t *counts, int32_t *kpt_start, int cap_kpts, int cap_candidates,
                           void *workspace, size_t workspace_bytes, int32_t *overflow, void *stream);
 
+/*
+ * Same as lwp_extract_keypoints, but the up-sampled heat-maps are never materialised: peaks are found
+ * on tiles rebuilt in shared memory straight from the stride-8 network output, with the bits
+ * lwp_upsample_cubic would have produced (demo.py:72 + :95-98 in one pass).
+ * src: [n][h][w] pixels, pixel stride ld floats, heat-map channels start at the pointer; c_layout = channel
+ * count of the cv2.resize call being reproduced (19); H, W = up-sampled size; inv_scale_* as for
+ * lwp_upsample_cubic (must be >= 3).
+ */
+int lwp_extract_keypoints_fused(const float *src, int n, int h, int w, int ld, int n_ch, int c_layout, int H, int W,
+                                double inv_scale_x, double inv_scale_y, lwp_keypoint *kpts, int32_t *counts,
+                                int32_t *kpt_start, int cap_kpts, int cap_candidates, void *workspace,
+                                size_t workspace_bytes, int32_t *overflow, void *stream);
+
 size_t lwp_group_workspace_bytes(int n, int cap_kpts, int cap_connections, int cap_poses);
 
 /*
@@ -103,6 +116,18 @@ int lwp_group_keypoints(const lwp_keypoint *kpts, const int32_t *counts, const i
                         const float *pafs, int n, int H, int W, int paf_ld, int demo, double min_paf_score,
                         double *pose_entries, int32_t *n_poses, int cap_poses, int cap_connections,
                         void *workspace, size_t workspace_bytes, int32_t *overflow, void *stream);
+
+/*
+ * Same as lwp_group_keypoints, but every PAF sample is computed on the fly from the stride-8 network
+ * output (4x4 source patch, OpenCV's operation order) instead of being read from a materialised
+ * up-sampled map (demo.py:76 + :100 in one pass).  src: [n][h][w] pixels, pixel stride ld floats, the 38 PAF
+ * channels start at the pointer.  lwp_group_keypoints* only SET overflow flags; lwp_extract_keypoints* clear them.
+ */
+int lwp_group_keypoints_fused(const lwp_keypoint *kpts, const int32_t *counts, const int32_t *kpt_start, int cap_kpts,
+                              const float *src, int n, int h, int w, int ld, int H, int W, double inv_scale_x,
+                              double inv_scale_y, int demo, double min_paf_score, double *pose_entries,
+                              int32_t *n_poses, int cap_poses, int cap_connections, void *workspace,
+                              size_t workspace_bytes, int32_t *overflow, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Network forward: a "plan" is a recorded list of layer launches with pre-built TMA descriptors

@@ -5,6 +5,7 @@
 // models/with_mobilenet.py:93-105.
 #include "common.cuh"
 #include "conv_direct.cuh"
+#include "tcgen05.cuh"
 
 namespace lwp {
 
@@ -179,6 +180,141 @@ depthwise3x3_kernel(const T *__restrict__ in, T *__restrict__ out, const float *
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3, NHWC, shared-memory halo tiles fed by TMA.
+// A tile = TH x TW output pixels x CB channels (CB*sizeof(T) <= 128 bytes per pixel).  One elected thread
+// TMA-loads the (IH x IW x CB) input halo box of the NEXT tile into the other smem buffer while all
+// 256 threads compute the current one; out-of-image parts of the box are zero-filled by TMA, which is
+// the convolution's zero padding.  A thread owns 8 channels x 4 consecutive output columns of one row
+// and slides a register window over the 3 x NCOL smem vectors it needs.
+// ------------------------------------------------------------------------------------------------
+struct DwTileParams {
+  int n, H, W, C, Ho, Wo;
+  int tw, th;          // output tile (tw multiple of 4, (tw/4)*th*cv == 256)
+  int iw, ih;          // input box
+  int cb, cv;          // channels per tile, 8-channel vectors per pixel (cb/8)
+  int tiles_x, tiles_y, cblocks, num_tiles;
+  int act;
+  uint32_t stage_bytes;
+};
+
+template <typename T> struct SmemVec8;
+template <> struct SmemVec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const uint8_t *p, float (&v)[8]) {
+    uint4 raw = *reinterpret_cast<const uint4 *>(p);
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __bfloat1622float2(h[j]);
+      v[2 * j] = f.x; v[2 * j + 1] = f.y;
+    }
+  }
+};
+template <> struct SmemVec8<float> {
+  static __device__ __forceinline__ void load(const uint8_t *p, float (&v)[8]) {
+    float4 a = reinterpret_cast<const float4 *>(p)[0], b = reinterpret_cast<const float4 *>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+template <typename T, int S, int D>
+__global__ void __launch_bounds__(256)
+depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict__ out,
+                        const float *__restrict__ w9c, const float *__restrict__ scale,
+                        const float *__restrict__ shift, const DwTileParams p) {
+  constexpr int TWT = 4;                                  // outputs per thread along x
+  constexpr int NCOL = (TWT - 1) * S + 2 * D + 1;
+  extern __shared__ uint8_t dw_smem_raw[];
+  uint8_t *smem = dw_smem_raw + ((128u - (ptx::smem_u32(dw_smem_raw) & 127u)) & 127u);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);   // 2 "full" barriers
+  uint8_t *bufs = smem + 128;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tm_in);
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int cv = tid % p.cv, pt = tid / p.cv;
+  const int xgroups = p.tw / TWT;
+  const int xg = pt % xgroups, ty = pt / xgroups;
+  const int per_img = p.tiles_x * p.tiles_y * p.cblocks;
+
+  auto issue = [&](int tile, int buf) {
+    const int img = tile / per_img;
+    int rem = tile - img * per_img;
+    const int cblk = rem % p.cblocks;
+    rem /= p.cblocks;
+    const int tx = rem % p.tiles_x, tyy = rem / p.tiles_x;
+    ptx::mbar_arrive_expect_tx(&bars[buf], p.stage_bytes);
+    ptx::tma_load_4d(bufs + (size_t)buf * p.stage_bytes, &tm_in, &bars[buf], cblk * p.cb, tx * p.tw * S - D,
+                     tyy * p.th * S - D, img);
+  };
+
+  int it = 0;
+  if (tid == 0 && (int)blockIdx.x < p.num_tiles) issue(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = tile + gridDim.x;
+    if (tid == 0 && next < p.num_tiles) issue(next, buf ^ 1);  // buffer buf^1 was released by the previous __syncthreads
+    if (!ptx::mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1))) return;  // never spin forever
+    const int img = tile / per_img;
+    int rem = tile - img * per_img;
+    const int cblk = rem % p.cblocks;
+    rem /= p.cblocks;
+    const int tx = rem % p.tiles_x, tyy = rem / p.tiles_x;
+    const int c0 = cblk * p.cb + cv * 8;
+    const int yo = tyy * p.th + ty, xo0 = tx * p.tw + xg * TWT;
+    const uint8_t *sbuf = bufs + (size_t)buf * p.stage_bytes;
+    const int pix_bytes = p.cb * (int)sizeof(T);
+    float acc[TWT][8];
+#pragma unroll
+    for (int a = 0; a < TWT; ++a)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      float wk[3][8];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) Vec8<float>::load(w9c + (size_t)(ky * 3 + kx) * p.C + c0, wk[kx]);
+      const uint8_t *rowp = sbuf + ((size_t)(ty * S + ky * D) * p.iw + (size_t)xg * TWT * S) * pix_bytes +
+                            cv * 8 * (int)sizeof(T);
+#pragma unroll
+      for (int ci = 0; ci < NCOL; ++ci) {
+        float v[8];
+        SmemVec8<T>::load(rowp + (size_t)ci * pix_bytes, v);
+#pragma unroll
+        for (int a = 0; a < TWT; ++a) {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            if (a * S + kx * D == ci) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[a][j] = fmaf(v[j], wk[kx][j], acc[a][j]);
+            }
+          }
+        }
+      }
+    }
+    if (yo < p.Ho) {
+      float sc[8], sh[8];
+      Vec8<float>::load(scale + c0, sc);
+      Vec8<float>::load(shift + c0, sh);
+#pragma unroll
+      for (int a = 0; a < TWT; ++a) {
+        const int xo = xo0 + a;
+        if (xo < p.Wo) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = act_apply(fmaf(acc[a][j], sc[j], sh[j]), p.act);
+          Vec8<T>::store(out + (((size_t)img * p.Ho + yo) * p.Wo + xo) * p.C + c0, o);
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with buffer `buf` before it is refilled two tiles from now
+  }
+}
+
 // NHWC (T or float, pixel stride ld, channels [c0, c0 + c)) -> NCHW float32 [n][c][H][W]
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -241,6 +377,74 @@ int depthwise_launch(bool f32, const void *in, void *out, const float *w9c, cons
                                      st);
   return depthwise_launch_t<__nv_bfloat16>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, w9c, scale, shift, n, H, W,
                                            C, stride, dil, act, st);
+}
+
+
+// Tile geometry for the TMA depthwise kernel (shared by the plan, which builds the tensor map, and the launcher).
+int depthwise_tma_geometry(bool f32, int n, int H, int W, int C, int stride, int dil, DwTileGeom *g) {
+  const int es = f32 ? 4 : 2;
+  const int cb = C * es <= 128 ? C : 128 / es;
+  if (C % cb != 0 || cb % 8 != 0) return LWP_EINVAL;
+  const int cv = cb / 8, pts = 256 / cv;
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  long long best = -1;
+  for (int tw = 4; tw <= pts * 4; tw <<= 1) {
+    if (pts % (tw / 4)) continue;
+    const int th = pts / (tw / 4);
+    const int iw = (tw - 1) * stride + 2 * dil + 1, ih = (th - 1) * stride + 2 * dil + 1;
+    if (iw > 256 || ih > 256) continue;
+    if ((long long)iw * ih * cb * es > 100 * 1024) continue;
+    // cost ~ bytes moved: padded input boxes + padded outputs
+    long long tiles = (long long)ceil_div(Wo, tw) * ceil_div(Ho, th);
+    long long cost = tiles * ((long long)iw * ih + (long long)tw * th);
+    if (best < 0 || cost < best) { best = cost; g->tw = tw; g->th = th; g->iw = iw; g->ih = ih; }
+  }
+  if (best < 0) return LWP_EINVAL;
+  g->cb = cb; g->cv = cv; g->Ho = Ho; g->Wo = Wo;
+  g->tiles_x = ceil_div(Wo, g->tw); g->tiles_y = ceil_div(Ho, g->th); g->cblocks = C / cb;
+  g->num_tiles = n * g->tiles_x * g->tiles_y * g->cblocks;
+  g->stage_bytes = (uint32_t)(g->iw * g->ih * cb * es);
+  return LWP_OK;
+}
+
+int depthwise_tma_init() {
+  static bool done = false;
+  if (done) return LWP_OK;
+#define LWP_DW_ATTR(T, S, D) \
+  LWP_CUDA_CHECK(cudaFuncSetAttribute(depthwise3x3_tma_kernel<T, S, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024))
+  LWP_DW_ATTR(float, 1, 1); LWP_DW_ATTR(float, 2, 1); LWP_DW_ATTR(float, 1, 2);
+  LWP_DW_ATTR(__nv_bfloat16, 1, 1); LWP_DW_ATTR(__nv_bfloat16, 2, 1); LWP_DW_ATTR(__nv_bfloat16, 1, 2);
+#undef LWP_DW_ATTR
+  done = true;
+  return LWP_OK;
+}
+
+template <typename T>
+static int depthwise_tma_launch_t(const CUtensorMap &tm, T *out, const float *w9c, const float *scale,
+                                  const float *shift, const DwTileParams &p, int stride, int dil, cudaStream_t st) {
+  const size_t smem = 128 + 128 + 2 * (size_t)p.stage_bytes;
+  int per_sm = (int)((200 * 1024) / smem);
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int grid = num_sms() * per_sm;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  if (stride == 1 && dil == 1) depthwise3x3_tma_kernel<T, 1, 1><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p);
+  else if (stride == 2 && dil == 1) depthwise3x3_tma_kernel<T, 2, 1><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p);
+  else if (stride == 1 && dil == 2) depthwise3x3_tma_kernel<T, 1, 2><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p);
+  else { set_error("depthwise: unsupported stride %d / dilation %d", stride, dil); return LWP_EINVAL; }
+  LWP_LAUNCH_CHECK();
+  return LWP_OK;
+}
+
+int depthwise_tma_launch(bool f32, const CUtensorMap &tm, void *out, const float *w9c, const float *scale,
+                         const float *shift, int n, int H, int W, int C, int stride, int dil, int act,
+                         const DwTileGeom &g, cudaStream_t st) {
+  DwTileParams p;
+  p.n = n; p.H = H; p.W = W; p.C = C; p.Ho = g.Ho; p.Wo = g.Wo; p.tw = g.tw; p.th = g.th; p.iw = g.iw; p.ih = g.ih;
+  p.cb = g.cb; p.cv = g.cv; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y; p.cblocks = g.cblocks;
+  p.num_tiles = g.num_tiles; p.act = act; p.stage_bytes = g.stage_bytes;
+  if (f32) return depthwise_tma_launch_t<float>(tm, (float *)out, w9c, scale, shift, p, stride, dil, st);
+  return depthwise_tma_launch_t<__nv_bfloat16>(tm, (__nv_bfloat16 *)out, w9c, scale, shift, p, stride, dil, st);
 }
 
 int nhwc_to_nchw_launch(bool in_f32, const void *in, int ld, int c0, int c, float *out, int n, int HW,

@@ -38,7 +38,9 @@ struct Op {
   const float *w = nullptr, *scale = nullptr, *shift = nullptr;
   int n = 0, H = 0, W = 0, C = 0, stride = 1, dil = 1, act = 0;
   int ld = 0, c0 = 0, in_f32 = 0;
-  // gemm
+  DwTileGeom dwg;
+  bool dw_tma = false;
+  // gemm (tmA is also the input map of the TMA depthwise kernel)
   CUtensorMap tmA, tmB;
   GemmParams gp;
   int grid = 0;
@@ -112,6 +114,21 @@ extern "C" int lwp_plan_add_depthwise(lwp_plan *p, const void *in, void *out, co
   op.kind = OP_DW;
   op.in = in; op.out = out; op.w = w; op.scale = scale; op.shift = shift;
   op.n = n; op.H = H; op.W = W; op.C = C; op.stride = stride; op.dil = dilation; op.act = act;
+  const bool f32 = p->dtype == LWP_DTYPE_TF32;
+  const int es = f32 ? 4 : 2;
+  if (depthwise_tma_geometry(f32, n, H, W, C, stride, dilation, &op.dwg) == LWP_OK && ((uintptr_t)in % 16) == 0 &&
+      depthwise_tma_init() == LWP_OK) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)C * es * W, (cuuint64_t)C * es * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)op.dwg.cb, (cuuint32_t)op.dwg.iw, (cuuint32_t)op.dwg.ih, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = get_encode_fn()(&op.tmA, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                                 const_cast<void *>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(depthwise) failed: %d", (int)r); return LWP_ECUDA; }
+    op.dw_tma = true;
+  }
   p->ops.push_back(op);
   return LWP_OK;
 }
@@ -236,8 +253,12 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int la
         rc = stem_launch(f32, x, op.w, op.scale, op.shift, op.out, op.n, op.H, op.W, st);
         break;
       case OP_DW:
-        rc = depthwise_launch(f32, op.in, op.out, op.w, op.scale, op.shift, op.n, op.H, op.W, op.C, op.stride, op.dil,
-                              op.act, st);
+        if (op.dw_tma)
+          rc = depthwise_tma_launch(f32, op.tmA, op.out, op.w, op.scale, op.shift, op.n, op.H, op.W, op.C, op.stride,
+                                    op.dil, op.act, op.dwg, st);
+        else
+          rc = depthwise_launch(f32, op.in, op.out, op.w, op.scale, op.shift, op.n, op.H, op.W, op.C, op.stride,
+                                op.dil, op.act, st);
         break;
       case OP_GEMM:
         rc = conv_gemm_launch(f32, op.tmA, op.tmB, op.gp, op.grid, st);

@@ -15,6 +15,7 @@
 
 #include <float.h>
 #include <limits.h>
+#include <string.h>
 
 namespace lwp {
 
@@ -55,50 +56,81 @@ __device__ __forceinline__ int cubic_axis(int d, double scale, float c[4]) {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-__global__ void __launch_bounds__(256)
-upsample_cubic_kernel(const float *__restrict__ src, int h, int w, int c, int src_ld, float *__restrict__ dst,
-                      int H, int W, double scale_x, double scale_y, long long total) {
-  const int rowlen = W * c;
+// Where an up-sampled map comes from when it is not materialised: the stride-8 source + the resize geometry.
+struct UpSrc {
+  const float *src;   // [n][h][w] pixels, pixel stride ld floats; the resized channels start at the pointer
+  int h, w, ld;
+  int c_layout;       // channel count of the cv2.resize call being reproduced (decides the SIMD-tail columns)
+  int H, W;           // up-sampled size
+  double scale_x, scale_y;  // 1 / inv_scale
+};
+
+// horizontal 4-tap sum of HResizeCubic for one source row pointer (already offset to the channel)
+__device__ __forceinline__ float cubic_hsum(const float *p, int i0, int i1, int i2, int i3, const float (&cx)[4],
+                                            bool border) {
+  float p0 = __fmul_rn(__ldg(p + i0), cx[0]);
+  float p1 = __fmul_rn(__ldg(p + i1), cx[1]);
+  float p2 = __fmul_rn(__ldg(p + i2), cx[2]);
+  float p3 = __fmul_rn(__ldg(p + i3), cx[3]);
+  float v = border ? __fadd_rn(0.f, p0) : p0;  // border columns start from v = 0 and add the products in turn
+  v = __fadd_rn(v, p1);
+  v = __fadd_rn(v, p2);
+  return __fadd_rn(v, p3);
+}
+
+// vertical combination: VResizeCubicVec_32f body order, or the scalar-tail order for the last (W*C)%4 floats of a row
+__device__ __forceinline__ float cubic_vsum(const float (&T)[4], const float (&cy)[4], bool simd_body) {
+  float o;
+  if (simd_body) {
+    o = __fadd_rn(__fmul_rn(T[2], cy[2]), __fmul_rn(T[3], cy[3]));
+    o = __fadd_rn(__fmul_rn(T[1], cy[1]), o);
+    o = __fadd_rn(__fmul_rn(T[0], cy[0]), o);
+  } else {
+    o = __fadd_rn(__fmul_rn(T[0], cy[0]), __fmul_rn(T[1], cy[1]));
+    o = __fadd_rn(o, __fmul_rn(T[2], cy[2]));
+    o = __fadd_rn(o, __fmul_rn(T[3], cy[3]));
+  }
+  return o;
+}
+
+// NCH (1 or 2) channels of up-sampled pixel (e, d) of image img, computed from the source with OpenCV's bits.
+template <int NCH>
+__device__ __forceinline__ void upsampled_at(const UpSrc &u, int img, int e, int d, const int (&ch)[NCH],
+                                             float (&out)[NCH]) {
+  float cx[4], cy[4];
+  const int sx = cubic_axis(d, u.scale_x, cx);
+  const int sy = cubic_axis(e, u.scale_y, cy);
+  const bool border = (sx < 1) || (sx + 2 >= u.w);
+  const int i0 = clampi(sx - 1, 0, u.w - 1) * u.ld, i1 = clampi(sx, 0, u.w - 1) * u.ld;
+  const int i2 = clampi(sx + 1, 0, u.w - 1) * u.ld, i3 = clampi(sx + 2, 0, u.w - 1) * u.ld;
+  const int rowlen = u.W * u.c_layout;
   const int body = rowlen - (rowlen & 3);
+  float T[NCH][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = clampi(sy - 1 + r, 0, u.h - 1);
+    const float *p = u.src + ((size_t)img * u.h + row) * (size_t)u.w * u.ld;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) T[c][r] = cubic_hsum(p + ch[c], i0, i1, i2, i3, cx, border);
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) out[c] = cubic_vsum(T[c], cy, d * u.c_layout + ch[c] < body);
+}
+
+__global__ void __launch_bounds__(256)
+upsample_cubic_kernel(const UpSrc u, float *__restrict__ dst, long long total) {
+  const int rowlen = u.W * u.c_layout;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int q = (int)(idx % rowlen);
-    long long t = idx / rowlen;
-    int e = (int)(t % H);
-    int img = (int)(t / H);
-    int d = q / c, ch = q - d * c;
-    float cx[4], cy[4];
-    int sx = cubic_axis(d, scale_x, cx);
-    int sy = cubic_axis(e, scale_y, cy);
-    bool border = (sx < 1) || (sx + 2 >= w);
-    int i0 = clampi(sx - 1, 0, w - 1) * src_ld, i1 = clampi(sx, 0, w - 1) * src_ld;
-    int i2 = clampi(sx + 1, 0, w - 1) * src_ld, i3 = clampi(sx + 2, 0, w - 1) * src_ld;
-    float T[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int row = clampi(sy - 1 + r, 0, h - 1);
-      const float *p = src + ((size_t)img * h + row) * (size_t)w * src_ld + ch;
-      float p0 = __fmul_rn(__ldg(p + i0), cx[0]);
-      float p1 = __fmul_rn(__ldg(p + i1), cx[1]);
-      float p2 = __fmul_rn(__ldg(p + i2), cx[2]);
-      float p3 = __fmul_rn(__ldg(p + i3), cx[3]);
-      // HResizeCubic: border columns start from v = 0 and add the four products in turn
-      float v = border ? __fadd_rn(0.f, p0) : p0;
-      v = __fadd_rn(v, p1);
-      v = __fadd_rn(v, p2);
-      T[r] = __fadd_rn(v, p3);
-    }
-    float o;
-    if (q < body) {  // VResizeCubicVec_32f body: S0*b0 + (S1*b1 + (S2*b2 + S3*b3))
-      o = __fadd_rn(__fmul_rn(T[2], cy[2]), __fmul_rn(T[3], cy[3]));
-      o = __fadd_rn(__fmul_rn(T[1], cy[1]), o);
-      o = __fadd_rn(__fmul_rn(T[0], cy[0]), o);
-    } else {         // scalar tail: left to right
-      o = __fadd_rn(__fmul_rn(T[0], cy[0]), __fmul_rn(T[1], cy[1]));
-      o = __fadd_rn(o, __fmul_rn(T[2], cy[2]));
-      o = __fadd_rn(o, __fmul_rn(T[3], cy[3]));
-    }
-    dst[idx] = o;
+    const int q = (int)(idx % rowlen);
+    const long long t = idx / rowlen;
+    const int e = (int)(t % u.H);
+    const int img = (int)(t / u.H);
+    const int d = q / u.c_layout;
+    const int ch[1] = {q - d * u.c_layout};
+    float o[1];
+    upsampled_at<1>(u, img, e, d, ch, o);
+    dst[idx] = o[0];
   }
 }
 
@@ -133,6 +165,115 @@ peak_candidates_kernel(const float *__restrict__ hm, int H, int W, int ld, int n
       int slot = atomicAdd(&cand_count[img * n_ch + ch], 1);
       if (slot < cap) {
         unsigned long long key = ((unsigned long long)(((unsigned)x << 16) | (unsigned)y) << 32) | __float_as_uint(v);
+        cand[((size_t)img * n_ch + ch) * cap + slot] = key;
+      }
+    }
+  }
+}
+
+// Fused variant: the up-sampled heat-map is never written to memory.  A block rebuilds a 32x32 tile
+// (+1 halo) of the up-sampled map for 6 channels in shared memory straight from the stride-8 source --
+// separable cubic with exactly the operation order of upsample_cubic_kernel, so the values are
+// bit-identical to the materialised map -- and runs the same threshold + strict 4-neighbour test on it.
+constexpr int kPkTile = 32, kPkPad = kPkTile + 2, kPkSrcMax = 16, kPkCG = 6;
+
+__global__ void __launch_bounds__(256)
+peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__restrict__ cand,
+                             int *__restrict__ cand_count, int cap, int *__restrict__ overflow) {
+  __shared__ float s_cx[kPkPad][4], s_cy[kPkPad][4];
+  __shared__ int s_sx[kPkPad], s_sy[kPkPad];
+  __shared__ int s_win[4];  // sx_lo, ncols, sy_lo, nrows
+  extern __shared__ float pk_smem[];
+  float *s_src = pk_smem;                                         // [nrows][ncols][CG]
+  float *s_T = s_src + kPkSrcMax * kPkSrcMax * kPkCG;             // [nrows][kPkPad][CG]
+  float *s_V = s_T + kPkSrcMax * kPkPad * kPkCG;                  // [kPkPad][kPkPad][CG]
+  const int tid = threadIdx.x;
+  const int tiles_x = (u.W + kPkTile - 1) / kPkTile;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int cg0 = blockIdx.y * kPkCG, img = blockIdx.z;
+  const int ox0 = tx * kPkTile, oy0 = ty * kPkTile;
+  constexpr int kInvalid = -(1 << 30);
+  if (tid < kPkPad) {
+    const int d = ox0 - 1 + tid;
+    int sx = kInvalid;
+    if (d >= 0 && d < u.W) sx = cubic_axis(d, u.scale_x, s_cx[tid]);
+    s_sx[tid] = sx;
+  } else if (tid >= 64 && tid < 64 + kPkPad) {
+    const int i = tid - 64, e = oy0 - 1 + i;
+    int sy = kInvalid;
+    if (e >= 0 && e < u.H) sy = cubic_axis(e, u.scale_y, s_cy[i]);
+    s_sy[i] = sy;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int jf = ox0 == 0 ? 1 : 0, jl = min(kPkPad - 1, u.W - ox0);
+    const int if_ = oy0 == 0 ? 1 : 0, il = min(kPkPad - 1, u.H - oy0);
+    s_win[0] = s_sx[jf] - 1; s_win[1] = s_sx[jl] + 2 - s_win[0] + 1;
+    s_win[2] = s_sy[if_] - 1; s_win[3] = s_sy[il] + 2 - s_win[2] + 1;
+  }
+  __syncthreads();
+  const int sx_lo = s_win[0], ncols = s_win[1], sy_lo = s_win[2], nrows = s_win[3];
+  if (ncols > kPkSrcMax || nrows > kPkSrcMax) {  // host guarantees ratio >= 3; never silently wrong
+    if (tid == 0) overflow[img] = 1;
+    return;
+  }
+  // 1. source window (replicate border by clamping the coordinates)
+  for (int idx = tid; idx < nrows * ncols * kPkCG; idx += blockDim.x) {
+    const int c = idx % kPkCG, rx = (idx / kPkCG) % ncols, ry = idx / (kPkCG * ncols);
+    float v = 0.f;
+    if (cg0 + c < n_ch)
+      v = __ldg(u.src + (((size_t)img * u.h + clampi(sy_lo + ry, 0, u.h - 1)) * u.w + clampi(sx_lo + rx, 0, u.w - 1)) *
+                            (size_t)u.ld + cg0 + c);
+    s_src[idx] = v;
+  }
+  __syncthreads();
+  // 2. horizontal pass on every source row of the window
+  for (int idx = tid; idx < nrows * kPkPad * kPkCG; idx += blockDim.x) {
+    const int c = idx % kPkCG, j = (idx / kPkCG) % kPkPad, ry = idx / (kPkCG * kPkPad);
+    const int sx = s_sx[j];
+    float v = 0.f;
+    if (sx != kInvalid) {
+      const float *p = s_src + ((size_t)ry * ncols + (sx - 1 - sx_lo)) * kPkCG + c;
+      const bool border = (sx < 1) || (sx + 2 >= u.w);
+      float p0 = __fmul_rn(p[0], s_cx[j][0]);
+      float p1 = __fmul_rn(p[kPkCG], s_cx[j][1]);
+      float p2 = __fmul_rn(p[2 * kPkCG], s_cx[j][2]);
+      float p3 = __fmul_rn(p[3 * kPkCG], s_cx[j][3]);
+      v = border ? __fadd_rn(0.f, p0) : p0;
+      v = __fadd_rn(v, p1);
+      v = __fadd_rn(v, p2);
+      v = __fadd_rn(v, p3);
+    }
+    s_T[idx] = v;
+  }
+  __syncthreads();
+  // 3. vertical pass + threshold; positions outside the image count as 0 like the reference's zero border
+  const int rowlen = u.W * u.c_layout, body = rowlen - (rowlen & 3);
+  for (int idx = tid; idx < kPkPad * kPkPad * kPkCG; idx += blockDim.x) {
+    const int c = idx % kPkCG, j = (idx / kPkCG) % kPkPad, i = idx / (kPkCG * kPkPad);
+    const int sx = s_sx[j], sy = s_sy[i];
+    float v = 0.f;
+    if (sx != kInvalid && sy != kInvalid) {
+      const float *t = s_T + ((size_t)(sy - 1 - sy_lo) * kPkPad + j) * kPkCG + c;
+      float T[4] = {t[0], t[kPkPad * kPkCG], t[2 * kPkPad * kPkCG], t[3 * kPkPad * kPkCG]};
+      float cyv[4] = {s_cy[i][0], s_cy[i][1], s_cy[i][2], s_cy[i][3]};
+      v = thr01(cubic_vsum(T, cyv, (ox0 - 1 + j) * u.c_layout + cg0 + c < body));
+    }
+    s_V[idx] = v;
+  }
+  __syncthreads();
+  // 4. strict 4-neighbour maxima of the tile interior
+  for (int idx = tid; idx < kPkTile * kPkTile * kPkCG; idx += blockDim.x) {
+    const int c = idx % kPkCG, jx = (idx / kPkCG) % kPkTile, iy = idx / (kPkCG * kPkTile);
+    const int d = ox0 + jx, e = oy0 + iy, ch = cg0 + c;
+    if (d >= u.W || e >= u.H || ch >= n_ch) continue;
+    const float *vp = s_V + ((size_t)(iy + 1) * kPkPad + (jx + 1)) * kPkCG + c;
+    const float v = vp[0];
+    if (!(v > 0.f)) continue;
+    if (v > vp[-kPkCG] && v > vp[kPkCG] && v > vp[-kPkPad * kPkCG] && v > vp[kPkPad * kPkCG]) {
+      int slot = atomicAdd(&cand_count[img * n_ch + ch], 1);
+      if (slot < cap) {
+        unsigned long long key = ((unsigned long long)(((unsigned)d << 16) | (unsigned)e) << 32) | __float_as_uint(v);
         cand[((size_t)img * n_ch + ch) * cap + slot] = key;
       }
     }
@@ -266,10 +407,11 @@ struct ConnBefore {  // ratio descending; ties keep (i, j) generation order (sta
 // PAF line integral: a warp scores 3 candidate pairs at a time, 10 lanes per pair, lane k takes
 // sample k of linspace2d; the sum is then re-done in k order so the float64 result is the
 // reference's.  grid = (blocks per limb, 19 limbs, images).
+template <bool kFused>
 __global__ void __launch_bounds__(256)
 paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ counts, int cap_kpts,
-                 const float *__restrict__ pafs, int H, int W, int ld, int demo, double min_paf_score,
-                 Conn *__restrict__ conn, int *__restrict__ conn_count, int cap_conn) {
+                 const float *__restrict__ pafs, int H, int W, int ld, const UpSrc up, int demo,
+                 double min_paf_score, Conn *__restrict__ conn, int *__restrict__ conn_count, int cap_conn) {
   const int limb = blockIdx.y, img = blockIdx.z;
   const int ka = c_kpt_ids[limb][0], kb = c_kpt_ids[limb][1];
   const int nA = counts[img * LWP_NUM_KPT_TYPES + ka], nB = counts[img * LWP_NUM_KPT_TYPES + kb];
@@ -277,7 +419,7 @@ paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ 
   const lwp_keypoint *A = kpts + ((size_t)img * LWP_NUM_KPT_TYPES + ka) * cap_kpts;
   const lwp_keypoint *B = kpts + ((size_t)img * LWP_NUM_KPT_TYPES + kb) * cap_kpts;
   const int cx = c_paf_ids[limb][0], cy = c_paf_ids[limb][1];
-  const float *paf = pafs + (size_t)img * H * W * ld;
+  const float *paf = kFused ? nullptr : pafs + (size_t)img * H * W * ld;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int g = lane / 10, k = lane - g * 10;
   const int total = nA * nB;
@@ -303,8 +445,15 @@ paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ 
         double fy = __dadd_rn(__dmul_rn(__dmul_rn(1.0 / 9, (double)vy), (double)k), (double)a.y);
         int ix = demo ? __double2int_rz(fx) : __double2int_rn(fx);
         int iy = demo ? __double2int_rz(fy) : __double2int_rn(fy);
-        const float *pp = paf + ((size_t)iy * W + ix) * ld;
-        v = __dadd_rn(__dmul_rn(ux, (double)__ldg(pp + cx)), __dmul_rn(uy, (double)__ldg(pp + cy)));
+        float pv[2];
+        if constexpr (kFused) {  // the up-sampled PAF pixel is computed on the fly, bit-identical to the materialised map
+          const int ch[2] = {cx, cy};
+          upsampled_at<2>(up, img, iy, ix, ch, pv);
+        } else {
+          const float *pp = paf + ((size_t)iy * W + ix) * ld;
+          pv[0] = __ldg(pp + cx); pv[1] = __ldg(pp + cy);
+        }
+        v = __dadd_rn(__dmul_rn(ux, (double)pv[0]), __dmul_rn(uy, (double)pv[1]));
         pass = v > min_paf_score;
       }
     }
@@ -538,9 +687,10 @@ extern "C" int lwp_upsample_cubic(const float *src, int n, int h, int w, int c, 
   LWP_REQUIRE(inv_scale_x > 0 && inv_scale_y > 0, "lwp_upsample_cubic: bad scale");
   long long total = (long long)n * H * W * c;
   LWP_REQUIRE((long long)W * c < INT_MAX, "lwp_upsample_cubic: row too long");
-  double sx = 1. / inv_scale_x, sy = 1. / inv_scale_y;
-  upsample_cubic_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, h, w, c, src_ld, dst, H, W, sx,
-                                                                                sy, total);
+  UpSrc u;
+  u.src = src; u.h = h; u.w = w; u.ld = src_ld; u.c_layout = c; u.H = H; u.W = W;
+  u.scale_x = 1. / inv_scale_x; u.scale_y = 1. / inv_scale_y;
+  upsample_cubic_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(u, dst, total);
   LWP_LAUNCH_CHECK();
   return LWP_OK;
 }
@@ -550,9 +700,9 @@ extern "C" size_t lwp_extract_workspace_bytes(int n, int n_ch, int cap_candidate
   return align_up(slots * sizeof(int), 256) + slots * (size_t)cap_candidates * sizeof(unsigned long long);
 }
 
-extern "C" int lwp_extract_keypoints(const float *hm, int n, int H, int W, int ld, int n_ch, lwp_keypoint *kpts,
-                                     int32_t *counts, int32_t *kpt_start, int cap_kpts, int cap_candidates,
-                                     void *workspace, size_t workspace_bytes, int32_t *overflow, void *stream) {
+static int extract_common(bool fused, const float *hm, const UpSrc *up, int n, int H, int W, int ld, int n_ch,
+                          lwp_keypoint *kpts, int32_t *counts, int32_t *kpt_start, int cap_kpts, int cap_candidates,
+                          void *workspace, size_t workspace_bytes, int32_t *overflow, void *stream) {
   LWP_REQUIRE(hm && kpts && counts && kpt_start && workspace && overflow, "lwp_extract_keypoints: null pointer");
   LWP_REQUIRE(n > 0 && H > 0 && W > 0 && H < 65536 && W < 65536 && n_ch > 0 && n_ch <= 64 && ld >= n_ch,
               "lwp_extract_keypoints: bad shape");
@@ -567,21 +717,59 @@ extern "C" int lwp_extract_keypoints(const float *hm, int n, int H, int W, int l
   unsigned long long *cand = (unsigned long long *)((char *)workspace + align_up(slots * sizeof(int), 256));
   LWP_CUDA_CHECK(cudaMemsetAsync(cand_count, 0, slots * sizeof(int), st));
   LWP_CUDA_CHECK(cudaMemsetAsync(overflow, 0, (size_t)n * sizeof(int), st));
-  long long total = (long long)n * H * W * n_ch;
-  peak_candidates_kernel<<<grid_for(total, 256), 256, 0, st>>>(hm, H, W, ld, n_ch, cand, cand_count, cap_candidates,
-                                                               total);
-  LWP_LAUNCH_CHECK();
   static bool attr_set = false;
   if (!attr_set) {
     LWP_CUDA_CHECK(cudaFuncSetAttribute(peak_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LWP_CUDA_CHECK(cudaFuncSetAttribute(peak_candidates_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        64 * 1024));
     attr_set = true;
   }
+  if (fused) {
+    const size_t pk_smem = (size_t)(kPkSrcMax * kPkSrcMax + kPkSrcMax * kPkPad + kPkPad * kPkPad) * kPkCG * sizeof(float);
+    dim3 grid(ceil_div(W, kPkTile) * ceil_div(H, kPkTile), ceil_div(n_ch, kPkCG), n);
+    peak_candidates_fused_kernel<<<grid, 256, pk_smem, st>>>(*up, n_ch, cand, cand_count, cap_candidates, overflow);
+  } else {
+    long long total = (long long)n * H * W * n_ch;
+    peak_candidates_kernel<<<grid_for(total, 256), 256, 0, st>>>(hm, H, W, ld, n_ch, cand, cand_count, cap_candidates,
+                                                                 total);
+  }
+  LWP_LAUNCH_CHECK();
   peak_nms_kernel<<<(unsigned)slots, 256, smem, st>>>(cand, cand_count, cap_candidates, n_ch, kpts, counts, cap_kpts,
                                                       overflow);
   LWP_LAUNCH_CHECK();
   keypoint_ids_kernel<<<n, 128, 0, st>>>(kpts, counts, kpt_start, n_ch, cap_kpts);
   LWP_LAUNCH_CHECK();
   return LWP_OK;
+}
+
+extern "C" int lwp_extract_keypoints(const float *hm, int n, int H, int W, int ld, int n_ch, lwp_keypoint *kpts,
+                                     int32_t *counts, int32_t *kpt_start, int cap_kpts, int cap_candidates,
+                                     void *workspace, size_t workspace_bytes, int32_t *overflow, void *stream) {
+  return extract_common(false, hm, nullptr, n, H, W, ld, n_ch, kpts, counts, kpt_start, cap_kpts, cap_candidates,
+                        workspace, workspace_bytes, overflow, stream);
+}
+
+static int make_upsrc(const float *src, int h, int w, int ld, int c_layout, int H, int W, double inv_scale_x,
+                      double inv_scale_y, UpSrc *u) {
+  LWP_REQUIRE(src && h > 0 && w > 0 && ld >= c_layout && c_layout > 0 && H > 0 && W > 0, "fused source: bad shape");
+  LWP_REQUIRE(inv_scale_x >= 3.0 && inv_scale_y >= 3.0,
+              "fused post-processing needs an up-sampling factor >= 3 (got %g, %g); use the materialising path",
+              inv_scale_x, inv_scale_y);
+  u->src = src; u->h = h; u->w = w; u->ld = ld; u->c_layout = c_layout; u->H = H; u->W = W;
+  u->scale_x = 1. / inv_scale_x; u->scale_y = 1. / inv_scale_y;
+  return LWP_OK;
+}
+
+extern "C" int lwp_extract_keypoints_fused(const float *src, int n, int h, int w, int ld, int n_ch, int c_layout, int H,
+                                           int W, double inv_scale_x, double inv_scale_y, lwp_keypoint *kpts,
+                                           int32_t *counts, int32_t *kpt_start, int cap_kpts, int cap_candidates,
+                                           void *workspace, size_t workspace_bytes, int32_t *overflow, void *stream) {
+  UpSrc u;
+  int rc = make_upsrc(src, h, w, ld, c_layout, H, W, inv_scale_x, inv_scale_y, &u);
+  if (rc != LWP_OK) return rc;
+  LWP_REQUIRE(n_ch <= c_layout, "lwp_extract_keypoints_fused: n_ch > c_layout");
+  return extract_common(true, src, &u, n, H, W, ld, n_ch, kpts, counts, kpt_start, cap_kpts, cap_candidates, workspace,
+                        workspace_bytes, overflow, stream);
 }
 
 namespace {
@@ -612,11 +800,10 @@ extern "C" size_t lwp_group_workspace_bytes(int n, int cap_kpts, int cap_connect
   return carve_group_ws(nullptr, n, cap_kpts, cap_connections, cap_poses).bytes;
 }
 
-extern "C" int lwp_group_keypoints(const lwp_keypoint *kpts, const int32_t *counts, const int32_t *kpt_start,
-                                   int cap_kpts, const float *pafs, int n, int H, int W, int paf_ld, int demo,
-                                   double min_paf_score, double *pose_entries, int32_t *n_poses, int cap_poses,
-                                   int cap_connections, void *workspace, size_t workspace_bytes, int32_t *overflow,
-                                   void *stream) {
+static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *counts, const int32_t *kpt_start,
+                        int cap_kpts, const float *pafs, const UpSrc *up, int n, int H, int W, int paf_ld, int demo,
+                        double min_paf_score, double *pose_entries, int32_t *n_poses, int cap_poses,
+                        int cap_connections, void *workspace, size_t workspace_bytes, int32_t *overflow, void *stream) {
   LWP_REQUIRE(kpts && counts && kpt_start && pafs && pose_entries && n_poses && workspace && overflow,
               "lwp_group_keypoints: null pointer");
   LWP_REQUIRE(n > 0 && H > 0 && W > 0 && paf_ld >= 38 && cap_kpts > 0 && cap_poses > 0 && cap_connections > 0,
@@ -630,8 +817,16 @@ extern "C" int lwp_group_keypoints(const lwp_keypoint *kpts, const int32_t *coun
   LWP_CUDA_CHECK(cudaMemsetAsync(w.conn_count, 0, (size_t)n * LWP_NUM_LIMBS * sizeof(int), st));
   int bx = 1184 / (LWP_NUM_LIMBS * n);
   bx = bx < 2 ? 2 : (bx > 32 ? 32 : bx);
-  paf_score_kernel<<<dim3(bx, LWP_NUM_LIMBS, n), 256, 0, st>>>(kpts, counts, cap_kpts, pafs, H, W, paf_ld, demo,
-                                                               min_paf_score, w.conn, w.conn_count, cap_connections);
+  UpSrc u0;
+  memset(&u0, 0, sizeof(u0));
+  if (fused)
+    paf_score_kernel<true><<<dim3(bx, LWP_NUM_LIMBS, n), 256, 0, st>>>(kpts, counts, cap_kpts, nullptr, H, W, paf_ld, *up,
+                                                                       demo, min_paf_score, w.conn, w.conn_count,
+                                                                       cap_connections);
+  else
+    paf_score_kernel<false><<<dim3(bx, LWP_NUM_LIMBS, n), 256, 0, st>>>(kpts, counts, cap_kpts, pafs, H, W, paf_ld, u0,
+                                                                        demo, min_paf_score, w.conn, w.conn_count,
+                                                                        cap_connections);
   LWP_LAUNCH_CHECK();
   static bool attr_set = false;
   if (!attr_set) {
@@ -645,4 +840,25 @@ extern "C" int lwp_group_keypoints(const lwp_keypoint *kpts, const int32_t *coun
                                          pose_entries, n_poses, cap_poses, overflow);
   LWP_LAUNCH_CHECK();
   return LWP_OK;
+}
+
+extern "C" int lwp_group_keypoints(const lwp_keypoint *kpts, const int32_t *counts, const int32_t *kpt_start,
+                                   int cap_kpts, const float *pafs, int n, int H, int W, int paf_ld, int demo,
+                                   double min_paf_score, double *pose_entries, int32_t *n_poses, int cap_poses,
+                                   int cap_connections, void *workspace, size_t workspace_bytes, int32_t *overflow,
+                                   void *stream) {
+  return group_common(false, kpts, counts, kpt_start, cap_kpts, pafs, nullptr, n, H, W, paf_ld, demo, min_paf_score,
+                      pose_entries, n_poses, cap_poses, cap_connections, workspace, workspace_bytes, overflow, stream);
+}
+
+extern "C" int lwp_group_keypoints_fused(const lwp_keypoint *kpts, const int32_t *counts, const int32_t *kpt_start,
+                                         int cap_kpts, const float *src, int n, int h, int w, int ld, int H, int W,
+                                         double inv_scale_x, double inv_scale_y, int demo, double min_paf_score,
+                                         double *pose_entries, int32_t *n_poses, int cap_poses, int cap_connections,
+                                         void *workspace, size_t workspace_bytes, int32_t *overflow, void *stream) {
+  UpSrc u;
+  int rc = make_upsrc(src, h, w, ld, 38, H, W, inv_scale_x, inv_scale_y, &u);
+  if (rc != LWP_OK) return rc;
+  return group_common(true, kpts, counts, kpt_start, cap_kpts, src, &u, n, H, W, ld, demo, min_paf_score, pose_entries,
+                      n_poses, cap_poses, cap_connections, workspace, workspace_bytes, overflow, stream);
 }

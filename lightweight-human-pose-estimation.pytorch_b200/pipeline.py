@@ -44,13 +44,16 @@ class PoseResult:
 class PosePipeline:
     def __init__(self, net, batch, height, width, precision="bf16", upsample_ratio=4, demo=True,
                  min_paf_score=0.05, cap_kpts=128, cap_candidates=2048, cap_poses=256, cap_connections=2048,
-                 heads_hook=None):
+                 heads_hook=None, fused=True):
         _lib.require_cuda()
         self.net, self.precision = net, precision
         self.n, self.H, self.W = batch, height, width
         self.ratio, self.demo, self.min_paf_score = upsample_ratio, demo, min_paf_score
         self.caps = (cap_kpts, cap_candidates, cap_poses, cap_connections)
         self.heads_hook = heads_hook
+        # fused: peaks / PAF samples are computed straight from the stride-8 heads (no up-sampled maps in HBM);
+        # needs an up-sampling factor >= 3, otherwise the maps are materialised like the reference does
+        self.fused = bool(fused) and upsample_ratio >= 3
         eng = net.engine()
         dev = eng.device
         self.device = dev
@@ -62,8 +65,9 @@ class PosePipeline:
         self.L = L
         with torch.cuda.device(dev):
             self.x_dev = torch.empty((batch, 3, height, width), dtype=torch.float32, device=dev)
-            self.heat_up = torch.empty((batch, self.Hu, self.Wu, 19), dtype=torch.float32, device=dev)
-            self.paf_up = torch.empty((batch, self.Hu, self.Wu, 38), dtype=torch.float32, device=dev)
+            if not self.fused:
+                self.heat_up = torch.empty((batch, self.Hu, self.Wu, 19), dtype=torch.float32, device=dev)
+                self.paf_up = torch.empty((batch, self.Hu, self.Wu, 38), dtype=torch.float32, device=dev)
             self.kb = postproc.KeypointBatch(batch, postproc.NUM_KPT_TYPES, cap_kpts, dev)
             self.pose_entries = torch.empty((batch, cap_poses, postproc.POSE_ENTRY), dtype=torch.float64, device=dev)
             self.n_poses = torch.empty((batch,), dtype=torch.int32, device=dev)
@@ -92,7 +96,7 @@ class PosePipeline:
     # number of kernels of this library one step launches (memsets / copies not counted)
     @property
     def launches_per_step(self):
-        return self.plan.num_compute_ops + 2 + 3 + 3
+        return self.plan.num_compute_ops + (0 if self.fused else 2) + 3 + 3
 
     def enqueue(self, x_dev):
         """Enqueue one pass of the hot path on the current stream; x_dev: float32 cuda [n,3,H,W]."""
@@ -101,9 +105,16 @@ class PosePipeline:
         if self.heads_hook is not None:
             self.heads_hook(heads)
         r = self.ratio
+        ck, cc, cp, cn = self.caps
+        if self.fused:
+            postproc.extract_keypoints_fused(heads, r, cap_kpts=ck, cap_candidates=cc, workspace=self.ws_extract,
+                                             out=self.kb)
+            postproc.group_keypoints_fused(self.kb, heads, r, demo=self.demo, min_paf_score=self.min_paf_score,
+                                           cap_poses=cp, cap_connections=cn, workspace=self.ws_group,
+                                           out=(self.pose_entries, self.n_poses))
+            return
         postproc.upsample_cubic(heads, channels=19, fx=r, fy=r, out=self.heat_up, channel_offset=0)
         postproc.upsample_cubic(heads, channels=38, fx=r, fy=r, out=self.paf_up, channel_offset=19)
-        ck, cc, cp, cn = self.caps
         postproc.extract_keypoints_batched(self.heat_up, cap_kpts=ck, cap_candidates=cc, workspace=self.ws_extract,
                                            out=self.kb)
         postproc.group_keypoints_batched(self.kb, self.paf_up, demo=self.demo, min_paf_score=self.min_paf_score,

@@ -122,6 +122,57 @@ def group_keypoints_batched(kb, pafs, demo=False, min_paf_score=0.05, cap_poses=
     return pose_entries, n_poses
 
 
+def extract_keypoints_fused(maps, ratio, n_ch=NUM_KPT_TYPES, c_layout=19, channel_offset=0, cap_kpts=128,
+                            cap_candidates=2048, workspace=None, out=None):
+    """Peaks of the (never materialised) `ratio` x cubic up-sampling of `maps`: float32 cuda [n, h, w, ld], heat-map
+    channels [channel_offset, channel_offset + c_layout).  Same result as upsample_cubic + extract_keypoints_batched."""
+    L = _lib.load()
+    assert maps.is_cuda and maps.dtype == torch.float32 and maps.dim() == 4 and maps.is_contiguous()
+    n, h, w, ld = maps.shape
+    H, W = int(np.rint(h * float(ratio))), int(np.rint(w * float(ratio)))
+    kb = out if out is not None else KeypointBatch(n, n_ch, cap_kpts, maps.device)
+    assert kb.n == n and kb.n_ch == n_ch and kb.cap_kpts == cap_kpts
+    ws_bytes = L.lwp_extract_workspace_bytes(n, n_ch, cap_candidates)
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=maps.device)
+    _lib.check(L.lwp_extract_keypoints_fused(_ptr(maps) + 4 * channel_offset, n, h, w, ld, n_ch, c_layout, H, W,
+                                             float(ratio), float(ratio), _ptr(kb.kpts), _ptr(kb.counts),
+                                             _ptr(kb.kpt_start), cap_kpts, cap_candidates, _ptr(workspace),
+                                             workspace.numel(), _ptr(kb.overflow), _lib.current_stream()),
+               "lwp_extract_keypoints_fused")
+    kb._ws = workspace
+    kb.up_size = (H, W)
+    return kb
+
+
+def group_keypoints_fused(kb, maps, ratio, channel_offset=19, demo=False, min_paf_score=0.05, cap_poses=128,
+                          cap_connections=2048, workspace=None, out=None):
+    """PAF grouping with every PAF sample computed on the fly from `maps` (float32 cuda [n, h, w, ld], the 38 PAF
+    channels start at channel_offset).  Same result as upsample_cubic + group_keypoints_batched."""
+    L = _lib.load()
+    assert kb.n_ch == NUM_KPT_TYPES
+    assert maps.is_cuda and maps.dtype == torch.float32 and maps.dim() == 4 and maps.is_contiguous()
+    n, h, w, ld = maps.shape
+    assert n == kb.n and channel_offset + 38 <= ld
+    H, W = int(np.rint(h * float(ratio))), int(np.rint(w * float(ratio)))
+    if out is None:
+        pose_entries = torch.empty((n, cap_poses, POSE_ENTRY), dtype=torch.float64, device=maps.device)
+        n_poses = torch.empty((n,), dtype=torch.int32, device=maps.device)
+    else:
+        pose_entries, n_poses = out
+    ws_bytes = L.lwp_group_workspace_bytes(n, kb.cap_kpts, cap_connections, cap_poses)
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=maps.device)
+    _lib.check(L.lwp_group_keypoints_fused(_ptr(kb.kpts), _ptr(kb.counts), _ptr(kb.kpt_start), kb.cap_kpts,
+                                           _ptr(maps) + 4 * channel_offset, n, h, w, ld, H, W, float(ratio),
+                                           float(ratio), int(bool(demo)), float(min_paf_score), _ptr(pose_entries),
+                                           _ptr(n_poses), cap_poses, cap_connections, _ptr(workspace),
+                                           workspace.numel(), _ptr(kb.overflow), _lib.current_stream()),
+               "lwp_group_keypoints_fused")
+    kb._gws = workspace
+    return pose_entries, n_poses
+
+
 def raise_on_overflow(overflow_h):
     bad = np.nonzero(np.asarray(overflow_h))[0]
     if bad.size:

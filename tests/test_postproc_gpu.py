@@ -132,3 +132,63 @@ def test_dropin_functions_match_golden(torch_cuda):
     empty = [[] for _ in range(18)]
     poses, allk = group_keypoints(empty, pafs, demo=True)
     assert poses.shape == (0,) and allk.shape == (0,)
+
+
+def _fused_postproc(torch, hm, paf, demo, ratio=4, cap_kpts=256, cap_cand=4096, cap_poses=2048, cap_conn=8192):
+    from lwpose_b200 import postproc
+    n, _, h, w = hm.shape
+    heads = torch.zeros((n, h, w, 64), dtype=torch.float32, device="cuda")
+    heads[..., :19] = torch.from_numpy(np.ascontiguousarray(hm.transpose(0, 2, 3, 1))).cuda()
+    heads[..., 19:57] = torch.from_numpy(np.ascontiguousarray(paf.transpose(0, 2, 3, 1))).cuda()
+    kb = postproc.extract_keypoints_fused(heads, ratio, cap_kpts=cap_kpts, cap_candidates=cap_cand)
+    poses_d, n_d = postproc.group_keypoints_fused(kb, heads, ratio, demo=demo, cap_poses=cap_poses,
+                                                  cap_connections=cap_conn)
+    kpts_h, counts_h, start_h, ovf = kb.to_host()
+    postproc.raise_on_overflow(ovf)
+    return kpts_h, counts_h, start_h, poses_d.cpu().numpy(), n_d.cpu().numpy()
+
+
+@pytest.mark.parametrize("case", gc.postproc_cases(), ids=lambda c: c[0])
+@pytest.mark.parametrize("demo", [True, False])
+def test_fused_postproc_bit_exact_vs_reference_golden(torch_cuda, case, demo):
+    """No up-sampled map in memory: peaks from smem-rebuilt tiles, PAF samples computed on the fly --
+    still the reference's exact key-points and pose entries."""
+    from lwpose_b200 import postproc
+    g = gc.load("postproc_golden.npz")
+    hm, paf = gc.postproc_maps(case)
+    kpts_h, counts_h, start_h, poses_h, n_h = _fused_postproc(torch_cuda, hm[None], paf[None], demo)
+    by_type = postproc.keypoint_lists(kpts_h, counts_h, start_h, 0)
+    tag = "pp_%s_%s" % (case[0], "demo" if demo else "val")
+    assert np.array_equal(gc.pack_keypoints(by_type), g[tag + "_kpts"])
+    poses = np.asarray(postproc.pose_entries_array(poses_h, n_h, 0), np.float64).reshape(-1, 20)
+    assert poses.shape == g[tag + "_poses"].shape
+    assert np.array_equal(poses.view(np.int64), g[tag + "_poses"].view(np.int64))
+
+
+@pytest.mark.parametrize("shape,ratio", [((3, 13, 21), 4), ((2, 46, 82), 4), ((2, 9, 40), 8), ((1, 33, 7), 3)])
+def test_fused_equals_materialised_on_noise(torch_cuda, shape, ratio):
+    """Random maps with odd sizes / other ratios: fused and materialising paths give identical tables."""
+    torch = torch_cuda
+    from lwpose_b200 import postproc
+    n, h, w = shape
+    rng = np.random.default_rng(h * 100 + w)
+    hm = (rng.standard_normal((n, 19, h, w)) * 0.12).astype(np.float32)
+    paf = (rng.standard_normal((n, 38, h, w)) * 0.3).astype(np.float32)
+    a = _fused_postproc(torch, hm, paf, False, ratio=ratio, cap_kpts=1024, cap_cand=8192)
+    hm_d = torch.from_numpy(np.ascontiguousarray(hm.transpose(0, 2, 3, 1))).cuda()
+    paf_d = torch.from_numpy(np.ascontiguousarray(paf.transpose(0, 2, 3, 1))).cuda()
+    heat = postproc.upsample_cubic(hm_d, fx=ratio, fy=ratio)
+    pafs = postproc.upsample_cubic(paf_d, fx=ratio, fy=ratio)
+    kb = postproc.extract_keypoints_batched(heat, cap_kpts=1024, cap_candidates=8192)
+    poses_d, n_d = postproc.group_keypoints_batched(kb, pafs, demo=False, cap_poses=2048, cap_connections=8192)
+    kpts_h, counts_h, start_h, ovf = kb.to_host()
+    postproc.raise_on_overflow(ovf)
+    assert np.array_equal(a[1], counts_h) and np.array_equal(a[2], start_h)
+    for b in range(n):
+        assert np.array_equal(gc.pack_keypoints(postproc.keypoint_lists(a[0], a[1], a[2], b)),
+                              gc.pack_keypoints(postproc.keypoint_lists(kpts_h, counts_h, start_h, b)))
+    assert np.array_equal(a[4], n_d.cpu().numpy())
+    ph = poses_d.cpu().numpy()
+    for b in range(n):
+        k = int(a[4][b])
+        assert np.array_equal(a[3][b, :k].view(np.int64), ph[b, :k].view(np.int64))
