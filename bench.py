@@ -36,6 +36,7 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the workload timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per pipeline chunk (0 = whole batch)")
     ap.add_argument("--unfused-postproc", action="store_true", help="materialise the up-sampled maps like the reference")
     return ap.parse_args()
 
@@ -194,6 +195,7 @@ def workload_config(args, world):
                         "(demo=True)" % (REFINE, args.batch, HEIGHT, WIDTH, args.max_persons),
             "frames_per_gpu_per_step": args.batch, "global_batch": args.batch * world,
             "parallelism": "dp%d (frames sharded, no collective on the compute path)" % world,
+            "chunk": args.chunk,
             "l2": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (args.batch * 3 * HEIGHT * WIDTH * 4 / 1e6)}
 
 
@@ -220,7 +222,8 @@ def main():
     inject_h, persons = person_maps(args.batch, rank, args.max_persons)
     inject = torch.from_numpy(inject_h).to(dev)
     pipe = PosePipeline(net, args.batch, HEIGHT, WIDTH, precision=args.precision, demo=True,
-                        heads_hook=lambda heads: heads.add_(inject), fused=not args.unfused_postproc)
+                        heads_hook=lambda heads, lo: heads.add_(inject[lo:lo + heads.shape[0]]),
+                        fused=not args.unfused_postproc, chunk=args.chunk or None)
     x_host = synth.synthetic_net_input(args.batch, HEIGHT, WIDTH, seed=1 + rank).pin_memory()
     x_dev = x_host.to(dev)
 
@@ -247,25 +250,31 @@ def main():
         raise RuntimeError("GEMM pipeline wait timed out (error flag %d)" % pipe.error_flag())
     value = world * args.batch / (ms / 1000.0)
 
-    # ---- end to end through the public API: pinned host frames in, host pose tables out ----------
+    # ---- end to end through the public API: pinned host frames in, host pose tables out --------------
+    # streaming use of PosePipeline (submit / collect, 2 batches in flight): every step's H2D copy and
+    # result read-back are inside the timed region; the copy of step i+1 overlaps the kernels of step i
     for _ in range(2):
         pipe(x_host)
     barrier()
-    t_e2e = []
-    for _ in range(args.steps):
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(pipe.stream):
-            s0.record()
-        res = pipe(x_host)
-        with torch.cuda.stream(pipe.stream):
-            s1.record()
-        s1.synchronize()
-        t_e2e.append(s0.elapsed_time(s1))
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    pipe.submit(x_host)
+    for _ in range(args.steps - 1):
+        pipe.submit(x_host)
+        res = pipe.collect()
+    res = pipe.collect()
+    s1.record()
+    s1.synchronize()
     barrier()
     res.check()
-    e2e_ms = parallel.max_over_ranks(sum(t_e2e) / len(t_e2e), device=dev)
+    e2e_ms = parallel.max_over_ranks(s0.elapsed_time(s1) / args.steps, device=dev)
     e2e_value = world * args.batch / (e2e_ms / 1000.0)
     total_poses = res.total_poses()
+    # latency of one synchronous call (H2D -> kernels -> D2H, nothing overlapped)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        pipe(x_host)
+    sync_ms = (time.perf_counter() - t0) / 3 * 1000.0
 
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -273,7 +282,8 @@ def main():
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": pipe.h2d_bytes,
-                "d2h_bytes_per_step": pipe.d2h_bytes},
+                "d2h_bytes_per_step": pipe.d2h_bytes, "mode": "PosePipeline.submit/collect, 2 batches in flight",
+                "sync_call_ms": sync_ms},
         "gpu_launches": pipe.launches_per_step * args.steps,
         "clocks": clocks,
         "poses_per_step_rank0": total_poses, "persons_injected_rank0": int(sum(persons)),
@@ -292,29 +302,35 @@ def main():
 
 def roofline_pass(pipe, x_dev, args):
     """Per-kernel device time (CUDA events on the launching stream, op by op, after the timed region) ->
-    achieved TFLOP/s of the tcgen05 GEMM kernel and GB/s of the depthwise kernel vs the measured peaks."""
+    achieved TFLOP/s of the tcgen05 GEMM kernel and GB/s of the depthwise kernel vs the measured peaks.
+    Times are summed over the chunks of one step."""
     import torch
-    plan = pipe.plan
     pk = peaks()
     reps = max(3, min(args.steps, 10))
-    nops = plan.num_compute_ops
+    plan0 = pipe.chunks[0].plan
+    nops = plan0.num_compute_ops
     times = [0.0] * nops
-    for i in range(nops):
-        plan.run(x_dev, i, i + 1)  # warm
-    torch.cuda.synchronize()
-    for _ in range(reps):
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(nops + 1)]
-        evs[0].record()
+    for c in pipe.chunks:
+        plan, xc = c.plan, x_dev[c.lo:c.lo + c.n]
         for i in range(nops):
-            plan.run(x_dev, i, i + 1)
-            evs[i + 1].record()
+            plan.run(xc, i, i + 1)  # warm
         torch.cuda.synchronize()
-        for i in range(nops):
-            times[i] += evs[i].elapsed_time(evs[i + 1]) / reps
+        for _ in range(reps):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(nops + 1)]
+            evs[0].record()
+            for i in range(nops):
+                plan.run(xc, i, i + 1)
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            for i in range(nops):
+                times[i] += evs[i].elapsed_time(evs[i + 1]) / reps
     agg = {}
-    for meta, t in zip(plan.op_meta[:nops], times):
-        a = agg.setdefault(meta["kind"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
-        a["ms"] += t; a["flops"] += meta["flops"]; a["bytes"] += meta["bytes"]; a["launches"] += 1
+    for i, t in enumerate(times):
+        kind = plan0.op_meta[i]["kind"]
+        a = agg.setdefault(kind, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+        a["ms"] += t
+        for c in pipe.chunks:
+            a["flops"] += c.plan.op_meta[i]["flops"]; a["bytes"] += c.plan.op_meta[i]["bytes"]; a["launches"] += 1
     gemm_ms = sum(agg[k]["ms"] for k in agg if k.startswith("gemm"))
     gemm_flops = sum(agg[k]["flops"] for k in agg if k.startswith("gemm"))
     gemm_launches = sum(agg[k]["launches"] for k in agg if k.startswith("gemm"))
@@ -329,50 +345,30 @@ def roofline_pass(pipe, x_dev, args):
     if "depthwise" in agg:
         d = agg["depthwise"]
         gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-        res["roofline_depthwise"] = {"kernel": "depthwise3x3_kernel (%d launches)" % d["launches"], "bound": "hbm",
+        res["roofline_depthwise"] = {"kernel": "depthwise3x3_tma_kernel (%d launches)" % d["launches"], "bound": "hbm",
                                      "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                                      "traffic": None, "ms_per_step": d["ms"]}
     res["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in agg.items()}
     res["kernel_ms_per_step"].update(postproc_stage_ms(pipe, x_dev, reps))
-    res["layer_ms"] = {n: round(t, 4) for n, t in zip(plan.op_names[:nops], times)}
+    res["layer_ms"] = {n: round(t, 4) for n, t in zip(plan0.op_names[:nops], times)}
     return res
 
 
 def postproc_stage_ms(pipe, x_dev, reps):
     """Device time of the post-processing stages of one step (events on the launching stream)."""
     import torch
-    from lwpose_b200 import postproc
-    pipe.run_device(x_dev)  # leaves net output + injected persons in the head buffer
-    heads = pipe.heads
-    ck, cc, cp, cn = pipe.caps
-    if pipe.fused:
-        stages = {
-            "extract_fused": lambda: postproc.extract_keypoints_fused(heads, pipe.ratio, cap_kpts=ck, cap_candidates=cc,
-                                                                      workspace=pipe.ws_extract, out=pipe.kb),
-            "group_fused": lambda: postproc.group_keypoints_fused(pipe.kb, heads, pipe.ratio, demo=pipe.demo,
-                                                                  cap_poses=cp, cap_connections=cn,
-                                                                  workspace=pipe.ws_group,
-                                                                  out=(pipe.pose_entries, pipe.n_poses)),
-        }
-    else:
-        stages = {
-            "upsample": lambda: (postproc.upsample_cubic(heads, channels=19, fx=4, fy=4, out=pipe.heat_up),
-                                 postproc.upsample_cubic(heads, channels=38, fx=4, fy=4, out=pipe.paf_up,
-                                                         channel_offset=19)),
-            "extract": lambda: postproc.extract_keypoints_batched(pipe.heat_up, cap_kpts=ck, cap_candidates=cc,
-                                                                  workspace=pipe.ws_extract, out=pipe.kb),
-            "group": lambda: postproc.group_keypoints_batched(pipe.kb, pipe.paf_up, demo=pipe.demo, cap_poses=cp,
-                                                              cap_connections=cn, workspace=pipe.ws_group,
-                                                              out=(pipe.pose_entries, pipe.n_poses)),
-        }
+    pipe.run_device(x_dev)  # leaves net output + injected persons in the head buffers
+    names = ["extract_fused", "group_fused"] if pipe.fused else ["upsample", "extract", "group"]
     out = {}
-    for name, fn in stages.items():
-        fn()
+    for name in names:
+        for c in pipe.chunks:
+            c.enqueue_postproc(c.heads, stage=name)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(reps):
-            fn()
+            for c in pipe.chunks:
+                c.enqueue_postproc(c.heads, stage=name)
         b.record()
         torch.cuda.synchronize()
         out[name] = round(a.elapsed_time(b) / reps, 4)

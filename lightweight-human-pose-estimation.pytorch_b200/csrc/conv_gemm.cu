@@ -25,6 +25,7 @@ namespace lwp {
 struct SmemLayout {
   uint32_t stage_bytes;
   uint32_t stages_off;   // 0 (after 1024-alignment)
+  uint32_t staging_off;  // output staging of the TMA-store epilogue (1024-aligned: stages are multiples of 1024)
   uint32_t scale_off, shift_off, bars_off, total;
 };
 
@@ -32,10 +33,11 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int num_stages, i
   SmemLayout L;
   L.stage_bytes = kATileBytes + (uint32_t)block_n * kKBlockBytes;
   L.stages_off = 0;
-  L.scale_off = L.stage_bytes * (uint32_t)num_stages;
+  L.staging_off = L.stage_bytes * (uint32_t)num_stages;
+  L.scale_off = L.staging_off + kStagingBytes;
   L.shift_off = L.scale_off + (uint32_t)cout_pad * 4;
   L.bars_off = (L.shift_off + (uint32_t)cout_pad * 4 + 15u) & ~15u;
-  L.total = L.bars_off + (2 * kMaxStages + 4) * 8 + 16;
+  L.total = L.bars_off + (2 * kMaxStages + 2 * kMaxAccStages) * 8 + 16;
   return L;
 }
 
@@ -68,7 +70,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams &p, int t) {
 template <bool kTf32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const SmemLayout L = smem_layout(p.block_n, p.num_stages, p.cout_pad);
@@ -77,8 +79,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L.bars_off);
   uint64_t *empty_bar = full_bar + kMaxStages;
   uint64_t *tfull_bar = empty_bar + kMaxStages;
-  uint64_t *tempty_bar = tfull_bar + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+  uint64_t *tempty_bar = tfull_bar + kMaxAccStages;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + kMaxAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
@@ -87,11 +89,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    if (p.tma_store) ptx::prefetch_tmap(&tmC);
     for (int s = 0; s < p.num_stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < p.acc_stages; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
       ptx::mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
     }
@@ -153,8 +156,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (!ok) break;
         ptx::umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
@@ -162,7 +164,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int ty = row / p.tile_w, tx = row - ty * p.tile_w;
-    int acc = 0;
+    int acc = 0, sbuf_idx = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase)) { atomicExch(p.err_flag, 4); break; }
@@ -172,20 +174,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool valid = y < p.H && x < p.W;
       const size_t pix = ((size_t)tc.img * p.H + y) * (size_t)p.W + x;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
-      for (int c = 0; c < p.block_n; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(t_row + (uint32_t)c, r);
-        ptx::tmem_ld_wait();
-        if (valid) {
+      if (p.tma_store) {
+        // ---- staged epilogue: 128 output bytes per row per chunk -> swizzled smem -> one TMA tensor store per warp
+        constexpr int kChunkCols = kTf32 ? 32 : 64;
+        uint8_t *stage_base = smem + L.staging_off + (size_t)q * 2 * kStageOutBytes;
+        const int r0 = q * 32;
+        const int by0 = r0 / p.tile_w, bx0 = r0 - by0 * p.tile_w;
+        for (int c = 0; c < p.block_n; c += kChunkCols) {
+          const int cg0 = tc.n0 + c;
+          if (cg0 >= p.n_store) break;  // warp-uniform
+          uint8_t *sbuf = stage_base + (size_t)sbuf_idx * kStageOutBytes;
+          if (lane == 0) ptx::bulk_wait_read<1>();  // the store issued two chunks ago has finished reading this buffer
+          __syncwarp();
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            const int cg = tc.n0 + c + g8 * 8;
-            if (cg + 8 <= p.n_store) {
+          for (int half = 0; half < kChunkCols / 32; ++half) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(t_row + (uint32_t)(c + half * 32), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const int cg = cg0 + half * 32 + g8 * 8;
               float v[8];
+              {
+                const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + cg), sc1 = *reinterpret_cast<const float4 *>(s_scale + cg + 4);
+                const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + cg), sh1 = *reinterpret_cast<const float4 *>(s_shift + cg + 4);
+                const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                v[j] = apply_act(fmaf(__uint_as_float(r[g8 * 8 + j]), s_scale[cg + j], s_shift[cg + j]), p.act);
-              if (p.residual != nullptr) {
+                for (int j = 0; j < 8; ++j)
+                  v[j] = apply_act(fmaf(__uint_as_float(r[g8 * 8 + j]), scv[j], shv[j]), p.act);
+              }
+              if (p.residual != nullptr && valid && cg + 8 <= p.n_store) {
                 if constexpr (kTf32) {
                   const float4 *rp = reinterpret_cast<const float4 *>(
                       reinterpret_cast<const float *>(p.residual) + pix * p.res_ld + cg);
@@ -203,23 +222,81 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   }
                 }
               }
-              if (p.out != nullptr) {
-                if constexpr (kTf32) {
-                  float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + pix * p.out_ld + cg);
+              // 16-byte pieces of this row's 128-byte line, XOR-swizzled like SWIZZLE_128B expects
+              if constexpr (kTf32) {
+                const int j0 = (half * 32 + g8 * 8) / 4;  // two 16-byte pieces
+                *reinterpret_cast<float4 *>(sbuf + lane * 128 + (((j0) ^ (lane & 7)) << 4)) =
+                    make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(sbuf + lane * 128 + (((j0 + 1) ^ (lane & 7)) << 4)) =
+                    make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+                const int j0 = (half * 32 + g8 * 8) / 8;
+                uint4 pk;
+                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                *reinterpret_cast<uint4 *>(sbuf + lane * 128 + ((j0 ^ (lane & 7)) << 4)) = pk;
+              }
+            }
+          }
+          ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_4d(&tmC, sbuf, cg0, tc.x0 + bx0, tc.y0 + by0, tc.img);
+            ptx::bulk_commit();
+          }
+          sbuf_idx ^= 1;
+        }
+      } else {
+        for (int c = 0; c < p.block_n; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_row + (uint32_t)c, r);
+          ptx::tmem_ld_wait();
+          if (valid) {
+  #pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const int cg = tc.n0 + c + g8 * 8;
+              if (cg + 8 <= p.n_store) {
+                float v[8];
+  #pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  v[j] = apply_act(fmaf(__uint_as_float(r[g8 * 8 + j]), s_scale[cg + j], s_shift[cg + j]), p.act);
+                if (p.residual != nullptr) {
+                  if constexpr (kTf32) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(
+                        reinterpret_cast<const float *>(p.residual) + pix * p.res_ld + cg);
+                    float4 a = __ldg(rp), b = __ldg(rp + 1);
+                    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+                    v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+                  } else {
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(
+                        reinterpret_cast<const __nv_bfloat16 *>(p.residual) + pix * p.res_ld + cg));
+                    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+  #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      float2 f = __bfloat1622float2(h[j]);
+                      v[2 * j] += f.x; v[2 * j + 1] += f.y;
+                    }
+                  }
+                }
+                if (p.out != nullptr) {
+                  if constexpr (kTf32) {
+                    float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + pix * p.out_ld + cg);
+                    op[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    op[1] = make_float4(v[4], v[5], v[6], v[7]);
+                  } else {
+                    uint4 pk;
+                    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+  #pragma unroll
+                    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_ld + cg) = pk;
+                  }
+                }
+                if (p.out_f32 != nullptr) {
+                  float4 *op = reinterpret_cast<float4 *>(p.out_f32 + pix * p.out_f32_ld + cg);
                   op[0] = make_float4(v[0], v[1], v[2], v[3]);
                   op[1] = make_float4(v[4], v[5], v[6], v[7]);
-                } else {
-                  uint4 pk;
-                  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                  *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_ld + cg) = pk;
                 }
-              }
-              if (p.out_f32 != nullptr) {
-                float4 *op = reinterpret_cast<float4 *>(p.out_f32 + pix * p.out_f32_ld + cg);
-                op[0] = make_float4(v[0], v[1], v[2], v[3]);
-                op[1] = make_float4(v[4], v[5], v[6], v[7]);
               }
             }
           }
@@ -228,9 +305,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);  // accumulator stage drained
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
+    if (p.tma_store && lane == 0) ptx::bulk_wait<0>();  // all tensor stores of this warp have landed
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -246,13 +323,13 @@ int conv_gemm_init() {
   return LWP_OK;
 }
 
-int conv_gemm_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int grid,
-                     cudaStream_t st) {
+int conv_gemm_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+                     const GemmParams &p, int grid, cudaStream_t st) {
   size_t smem = conv_gemm_smem_bytes(p);
   if (tf32)
-    conv_gemm_kernel<true><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+    conv_gemm_kernel<true><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmC, p);
   else
-    conv_gemm_kernel<false><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+    conv_gemm_kernel<false><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmC, p);
   LWP_LAUNCH_CHECK();
   return LWP_OK;
 }

@@ -10,6 +10,7 @@ constexpr int kBlockM = 128;        // pixels per tile == UMMA M == TMEM lanes
 constexpr int kKBlockBytes = 128;   // one SWIZZLE_128B row of K per pipeline stage
 constexpr int kATileBytes = kBlockM * kKBlockBytes;
 constexpr int kMaxStages = 8;
+constexpr int kMaxAccStages = 8;    // TMEM accumulator stages: 512 columns / block_n
 constexpr int kMaxCout = 1024;
 
 struct GemmParams {
@@ -26,7 +27,8 @@ struct GemmParams {
   uint32_t idesc;          // UMMA instruction descriptor (M = 128, N = block_n)
   int act;                 // LWP_ACT_*
   int num_stages;
-  uint32_t tmem_cols;      // power of two >= 2 * block_n
+  uint32_t tmem_cols;      // power of two >= acc_stages * block_n
+  int acc_stages;          // TMEM accumulator ring depth (2..8)
   const float *scale, *shift;
   const void *residual;    // plan dtype, pixel stride res_ld, or nullptr
   int res_ld;
@@ -35,11 +37,18 @@ struct GemmParams {
   float *out_f32;          // optional float32 copy, pixel stride out_f32_ld
   int out_f32_ld;
   int *err_flag;           // set non-zero if a pipeline wait timed out
+  // epilogue through shared memory + TMA store (plain single-output layers): each epilogue warp stages its
+  // 32 pixel rows x 128 bytes of output and one lane issues a 4-D tensor store of that box
+  int tma_store;           // 0: direct register -> global stores
+  int store_bw, store_bh;  // pixel box of one warp's 32 rows (store_bw * store_bh == 32)
 };
 
+constexpr int kStageOutBytes = 32 * 128;          // one warp, one 128-byte column chunk
+constexpr int kStagingBytes = 4 * 2 * kStageOutBytes;  // 4 epilogue warps x double buffer
+
 size_t conv_gemm_smem_bytes(const GemmParams &p);
-int conv_gemm_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int grid,
-                     cudaStream_t st);
+int conv_gemm_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+                     const GemmParams &p, int grid, cudaStream_t st);
 int conv_gemm_init();
 
 }  // namespace lwp

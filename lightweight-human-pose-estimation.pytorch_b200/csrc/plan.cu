@@ -8,6 +8,8 @@
 #include "tcgen05.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 namespace lwp {
@@ -41,7 +43,7 @@ struct Op {
   DwTileGeom dwg;
   bool dw_tma = false;
   // gemm (tmA is also the input map of the TMA depthwise kernel)
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   GemmParams gp;
   int grid = 0;
 };
@@ -170,7 +172,11 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   g.taps = taps; g.dil = dilation; g.cin = Cin; g.kb_elems = kb_elems;
   g.kblocks_per_tap = (Cin + kb_elems - 1) / kb_elems;
   g.cout_pad = cout_pad;
-  g.block_n = cout_pad % 128 == 0 ? 128 : 64;
+  g.block_n = cout_pad % 256 == 0 ? 256 : cout_pad % 128 == 0 ? 128 : 64;
+  if (const char *bn = getenv("LWP_BLOCK_N")) {  // tuning knob: wider N tiles halve the A re-reads of wide layers
+    int v = atoi(bn);
+    if ((v == 64 || v == 128 || v == 256) && cout_pad % v == 0) g.block_n = v;
+  }
   g.n_tiles = cout_pad / g.block_n;
   // columns actually written: whole 8-groups that fit the narrowest destination row
   int n_store = cout_pad;
@@ -188,12 +194,16 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   g.out = out; g.out_ld = out_ld; g.out_f32 = out_f32; g.out_f32_ld = out_f32_ld;
   g.err_flag = p->err_flag;
   const int stage_bytes = kATileBytes + g.block_n * kKBlockBytes;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (200 * 1024 - kStagingBytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   g.num_stages = stages;
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * g.block_n)) cols <<= 1;
-  g.tmem_cols = cols;
+  g.acc_stages = 512 / g.block_n;  // the CTA owns the SM (smem > half), so it can take all 512 TMEM columns
+  if (g.acc_stages > kMaxAccStages) g.acc_stages = kMaxAccStages;
+  if (const char *as = getenv("LWP_ACC_STAGES")) {
+    int v = atoi(as);
+    if (v >= 2 && v <= g.acc_stages) g.acc_stages = v;
+  }
+  g.tmem_cols = 512;
 
   // geometry: 1x1 -> whole batch flattened to one row of pixels; 3x3 -> best rectangular tile
   if (taps == 1) {
@@ -235,6 +245,22 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return LWP_ECUDA; }
   }
+  // epilogue through smem + TMA tensor store for plain single-output layers whose stored width is whole 128-byte chunks
+  memset(&op.tmC, 0, sizeof(op.tmC));
+  g.tma_store = 0; g.store_bw = 32; g.store_bh = 1;
+  const int chunk_cols = kKBlockBytes / es;
+  if (out != nullptr && out_f32 == nullptr && g.n_store % chunk_cols == 0 && getenv("LWP_NO_TMA_STORE") == nullptr) {
+    g.store_bw = g.tile_w < 32 ? g.tile_w : 32;
+    g.store_bh = 32 / g.store_bw;
+    cuuint64_t dims[4] = {(cuuint64_t)g.n_store, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.NIMG};
+    cuuint64_t strides[3] = {(cuuint64_t)out_ld * es, (cuuint64_t)out_ld * es * g.W, (cuuint64_t)out_ld * es * g.W * g.H};
+    cuuint32_t box[4] = {(cuuint32_t)chunk_cols, (cuuint32_t)g.store_bw, (cuuint32_t)g.store_bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&op.tmC, dt, 4, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(C) failed: %d", (int)r); return LWP_ECUDA; }
+    g.tma_store = 1;
+  }
   p->ops.push_back(op);
   return LWP_OK;
 }
@@ -261,7 +287,7 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int la
                                 op.dil, op.act, st);
         break;
       case OP_GEMM:
-        rc = conv_gemm_launch(f32, op.tmA, op.tmB, op.gp, op.grid, st);
+        rc = conv_gemm_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st);
         break;
       case OP_NCHW:
         rc = nhwc_to_nchw_launch(op.in_f32 != 0, op.in, op.ld, op.c0, op.C, (float *)op.out, op.n, op.H * op.W, st);

@@ -72,6 +72,21 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const void *tmap, ui
       : "memory");
 }
 
+// smem -> global tensor store (OOB coordinates are clipped by the hardware)
+__device__ __forceinline__ void tma_store_4d(const void *tmap, const void *smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // at most N groups may still be READING their smem source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- TMEM ---------------------------------------------------------------------------------------
 // Executed by one full warp.  ncols: power of two in [32, 512].
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_result, uint32_t ncols) {

@@ -348,8 +348,10 @@ class NetEngine:
                 self._packed[precision] = _Packed(self.net, _PREC[precision][1])
         return self._packed[precision]
 
-    def plan(self, precision, n, H, W):
-        key = (precision, n, H, W)
+    def plan(self, precision, n, H, W, slot=0):
+        """Launch plan (with its own activation buffers) for one shape; `slot` distinguishes independent
+        instances of the same shape that run concurrently on different streams."""
+        key = (precision, n, H, W, slot)
         if key not in self._plans:
             net = self.net
             with torch.cuda.device(self.device):

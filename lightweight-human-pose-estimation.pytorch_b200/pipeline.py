@@ -7,8 +7,10 @@ batch, without the heat-maps / PAFs ever leaving the GPU.
     res = pipe(frames_pinned)          # float32 [64,3,368,656] pinned host tensor -> PoseResult (host)
     poses, all_keypoints = res.frame(0)   # exactly what group_keypoints returns for that frame
 
-All buffers (activations, up-sampled maps, key-point / pose tables, workspaces, pinned staging) are
-allocated once in the constructor; a call only enqueues kernels and copies on one stream.
+Streaming use: `pipe.submit(frames)` / `pipe.collect()` keep `depth` batches in flight, so the pinned
+host->device copy of batch i+1 (copy stream) overlaps the kernels of batch i (compute stream).  All
+buffers (activations, key-point / pose tables, workspaces, pinned staging, input double buffer) are
+allocated once in the constructor; a call only enqueues kernels and copies.
 """
 import numpy as np
 import torch
@@ -41,116 +43,194 @@ class PoseResult:
         return int(self.n_poses.sum())
 
 
+class _Chunk:
+    """Plan + device result tables of one slice [lo, lo + n) of the batch."""
+
+    def __init__(self, pipe, slot, lo, n):
+        self.pipe, self.lo, self.n = pipe, lo, n
+        dev = pipe.device
+        eng = pipe.net.engine()
+        self.plan = eng.plan(pipe.precision, n, pipe.H, pipe.W, slot=slot)
+        ck, cc, cp, cn = pipe.caps
+        L = pipe.L
+        if not pipe.fused:
+            self.heat_up = torch.empty((n, pipe.Hu, pipe.Wu, 19), dtype=torch.float32, device=dev)
+            self.paf_up = torch.empty((n, pipe.Hu, pipe.Wu, 38), dtype=torch.float32, device=dev)
+        self.kb = postproc.KeypointBatch(n, postproc.NUM_KPT_TYPES, ck, dev)
+        self.pose_entries = torch.empty((n, cp, postproc.POSE_ENTRY), dtype=torch.float64, device=dev)
+        self.n_poses = torch.empty((n,), dtype=torch.int32, device=dev)
+        self.ws_extract = torch.empty((L.lwp_extract_workspace_bytes(n, 18, cc),), dtype=torch.uint8, device=dev)
+        self.ws_group = torch.empty((L.lwp_group_workspace_bytes(n, ck, cn, cp),), dtype=torch.uint8, device=dev)
+
+    @property
+    def heads(self):
+        return self.plan.heads_f32[-1].view(self.n, self.pipe.h, self.pipe.w, HEAD_LD)
+
+    def enqueue(self, x_dev):
+        """One pass of the hot path for this chunk on the current stream."""
+        pipe = self.pipe
+        self.plan.run_compute(x_dev)
+        heads = self.heads
+        if pipe.heads_hook is not None:
+            pipe.heads_hook(heads, self.lo)
+        self.enqueue_postproc(heads)
+
+    def enqueue_postproc(self, heads, stage=None):
+        pipe = self.pipe
+        r = pipe.ratio
+        ck, cc, cp, cn = pipe.caps
+        if pipe.fused:
+            if stage in (None, "extract_fused"):
+                postproc.extract_keypoints_fused(heads, r, cap_kpts=ck, cap_candidates=cc, workspace=self.ws_extract,
+                                                 out=self.kb)
+            if stage in (None, "group_fused"):
+                postproc.group_keypoints_fused(self.kb, heads, r, demo=pipe.demo, min_paf_score=pipe.min_paf_score,
+                                               cap_poses=cp, cap_connections=cn, workspace=self.ws_group,
+                                               out=(self.pose_entries, self.n_poses))
+            return
+        if stage in (None, "upsample"):
+            postproc.upsample_cubic(heads, channels=19, fx=r, fy=r, out=self.heat_up, channel_offset=0)
+            postproc.upsample_cubic(heads, channels=38, fx=r, fy=r, out=self.paf_up, channel_offset=19)
+        if stage in (None, "extract"):
+            postproc.extract_keypoints_batched(self.heat_up, cap_kpts=ck, cap_candidates=cc,
+                                               workspace=self.ws_extract, out=self.kb)
+        if stage in (None, "group"):
+            postproc.group_keypoints_batched(self.kb, self.paf_up, demo=pipe.demo, min_paf_score=pipe.min_paf_score,
+                                             cap_poses=cp, cap_connections=cn, workspace=self.ws_group,
+                                             out=(self.pose_entries, self.n_poses))
+
+
+class _Slot:
+    """One in-flight batch: device input buffer, pinned host result tables, events."""
+
+    def __init__(self, pipe):
+        b, (ck, _, cp, _) = pipe.n, pipe.caps
+        self.x_dev = torch.empty((b, 3, pipe.H, pipe.W), dtype=torch.float32, device=pipe.device)
+        pin = dict(pin_memory=True)
+        self.h_pose_entries = torch.empty((b, cp, postproc.POSE_ENTRY), dtype=torch.float64, **pin)
+        self.h_n_poses = torch.empty((b,), dtype=torch.int32, **pin)
+        self.h_kpts = torch.empty((b, 18, ck, 4), dtype=torch.int32, **pin)
+        self.h_counts = torch.empty((b, 18), dtype=torch.int32, **pin)
+        self.h_kpt_start = torch.empty((b, 19), dtype=torch.int32, **pin)
+        self.h_overflow = torch.empty((b,), dtype=torch.int32, **pin)
+        self.copied = torch.cuda.Event()   # H2D of this slot's input finished
+        self.done = torch.cuda.Event()     # compute + D2H of this slot finished
+        self.busy = False
+
+    def tables(self):
+        return (self.h_pose_entries, self.h_n_poses, self.h_kpts, self.h_counts, self.h_kpt_start, self.h_overflow)
+
+    def result(self):
+        return PoseResult(*[t.numpy() for t in self.tables()])
+
+
 class PosePipeline:
+    """`depth` batches can be in flight: submit() enqueues the host->device copy of a batch on a copy stream
+    and its kernels + result read-back on the compute stream; collect() returns the oldest batch's
+    PoseResult.  With depth >= 2 the copy of batch i+1 overlaps the kernels of batch i.  pipe(frames) is
+    submit + collect."""
+
     def __init__(self, net, batch, height, width, precision="bf16", upsample_ratio=4, demo=True,
                  min_paf_score=0.05, cap_kpts=128, cap_candidates=2048, cap_poses=256, cap_connections=2048,
-                 heads_hook=None, fused=True):
+                 heads_hook=None, fused=True, chunk=None, depth=2):
         _lib.require_cuda()
         self.net, self.precision = net, precision
         self.n, self.H, self.W = batch, height, width
         self.ratio, self.demo, self.min_paf_score = upsample_ratio, demo, min_paf_score
         self.caps = (cap_kpts, cap_candidates, cap_poses, cap_connections)
+        # optional callable(heads [n_chunk, h, w, 64] float32, first_frame_index) run between network and post-processing
         self.heads_hook = heads_hook
         # fused: peaks / PAF samples are computed straight from the stride-8 heads (no up-sampled maps in HBM);
         # needs an up-sampling factor >= 3, otherwise the maps are materialised like the reference does
         self.fused = bool(fused) and upsample_ratio >= 3
-        eng = net.engine()
-        dev = eng.device
-        self.device = dev
-        self.plan = eng.plan(precision, batch, height, width)
-        h, w = height // 8, width // 8
-        self.h, self.w = h, w
-        self.Hu, self.Wu = h * upsample_ratio, w * upsample_ratio
-        L = _lib.load()
-        self.L = L
-        with torch.cuda.device(dev):
-            self.x_dev = torch.empty((batch, 3, height, width), dtype=torch.float32, device=dev)
-            if not self.fused:
-                self.heat_up = torch.empty((batch, self.Hu, self.Wu, 19), dtype=torch.float32, device=dev)
-                self.paf_up = torch.empty((batch, self.Hu, self.Wu, 38), dtype=torch.float32, device=dev)
-            self.kb = postproc.KeypointBatch(batch, postproc.NUM_KPT_TYPES, cap_kpts, dev)
-            self.pose_entries = torch.empty((batch, cap_poses, postproc.POSE_ENTRY), dtype=torch.float64, device=dev)
-            self.n_poses = torch.empty((batch,), dtype=torch.int32, device=dev)
-            self.ws_extract = torch.empty((L.lwp_extract_workspace_bytes(batch, 18, cap_candidates),),
-                                          dtype=torch.uint8, device=dev)
-            self.ws_group = torch.empty((L.lwp_group_workspace_bytes(batch, cap_kpts, cap_connections, cap_poses),),
-                                        dtype=torch.uint8, device=dev)
-            self.stream = torch.cuda.Stream(device=dev)
-        # pinned staging for results
-        pin = dict(pin_memory=True)
-        self.h_pose_entries = torch.empty((batch, cap_poses, postproc.POSE_ENTRY), dtype=torch.float64, **pin)
-        self.h_n_poses = torch.empty((batch,), dtype=torch.int32, **pin)
-        self.h_kpts = torch.empty((batch, 18, cap_kpts, 4), dtype=torch.int32, **pin)
-        self.h_counts = torch.empty((batch, 18), dtype=torch.int32, **pin)
-        self.h_kpt_start = torch.empty((batch, 19), dtype=torch.int32, **pin)
-        self.h_overflow = torch.empty((batch,), dtype=torch.int32, **pin)
-        self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.h_pose_entries, self.h_n_poses, self.h_kpts,
-                                                                    self.h_counts, self.h_kpt_start, self.h_overflow))
-        self.h2d_bytes = self.x_dev.numel() * 4
+        self.device = net.engine().device
+        self.h, self.w = height // 8, width // 8
+        self.Hu, self.Wu = self.h * upsample_ratio, self.w * upsample_ratio
+        self.L = _lib.load()
+        chunk = batch if chunk is None else max(1, min(int(chunk), batch))
+        with torch.cuda.device(self.device):
+            self.chunks = []
+            lo = 0
+            while lo < batch:
+                n = min(chunk, batch - lo)
+                self.chunks.append(_Chunk(self, len(self.chunks), lo, n))
+                lo += n
+            self.slots = [_Slot(self) for _ in range(max(1, int(depth)))]
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+            self.stream = torch.cuda.Stream(device=self.device)
+        self._next, self._pending = 0, []
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0].tables())
+        self.h2d_bytes = batch * 3 * height * width * 4
 
     @property
     def heads(self):
-        """float32 [n, h, w, 64]: last stage's 19 heat-map + 38 PAF channels (+7 zero) at stride 8."""
-        return self.plan.heads_f32[-1].view(self.n, self.h, self.w, HEAD_LD)
+        """float32 [n, h, w, 64]: last stage's 19 heat-map + 38 PAF channels (+7 zero) at stride 8 (a copy)."""
+        return torch.cat([c.heads for c in self.chunks], 0)
+
+    @property
+    def n_poses(self):
+        return torch.cat([c.n_poses for c in self.chunks], 0)
+
+    @property
+    def pose_entries(self):
+        return torch.cat([c.pose_entries for c in self.chunks], 0)
 
     # number of kernels of this library one step launches (memsets / copies not counted)
     @property
     def launches_per_step(self):
-        return self.plan.num_compute_ops + (0 if self.fused else 2) + 3 + 3
-
-    def enqueue(self, x_dev):
-        """Enqueue one pass of the hot path on the current stream; x_dev: float32 cuda [n,3,H,W]."""
-        self.plan.run_compute(x_dev)
-        heads = self.heads
-        if self.heads_hook is not None:
-            self.heads_hook(heads)
-        r = self.ratio
-        ck, cc, cp, cn = self.caps
-        if self.fused:
-            postproc.extract_keypoints_fused(heads, r, cap_kpts=ck, cap_candidates=cc, workspace=self.ws_extract,
-                                             out=self.kb)
-            postproc.group_keypoints_fused(self.kb, heads, r, demo=self.demo, min_paf_score=self.min_paf_score,
-                                           cap_poses=cp, cap_connections=cn, workspace=self.ws_group,
-                                           out=(self.pose_entries, self.n_poses))
-            return
-        postproc.upsample_cubic(heads, channels=19, fx=r, fy=r, out=self.heat_up, channel_offset=0)
-        postproc.upsample_cubic(heads, channels=38, fx=r, fy=r, out=self.paf_up, channel_offset=19)
-        postproc.extract_keypoints_batched(self.heat_up, cap_kpts=ck, cap_candidates=cc, workspace=self.ws_extract,
-                                           out=self.kb)
-        postproc.group_keypoints_batched(self.kb, self.paf_up, demo=self.demo, min_paf_score=self.min_paf_score,
-                                         cap_poses=cp, cap_connections=cn, workspace=self.ws_group,
-                                         out=(self.pose_entries, self.n_poses))
+        return sum(c.plan.num_compute_ops + (0 if self.fused else 2) + 3 + 3 for c in self.chunks)
 
     def run_device(self, x_dev):
-        """Hot path on a device-resident batch (no host traffic); results stay in self.pose_entries etc."""
+        """Hot path on a device-resident batch (no host traffic) on the current stream; results stay on the
+        device (self.pose_entries / self.n_poses / chunk.kb)."""
         with torch.cuda.device(self.device):
-            self.enqueue(x_dev)
+            for c in self.chunks:
+                c.enqueue(x_dev[c.lo:c.lo + c.n])
 
-    def _enqueue_d2h(self):
-        self.h_pose_entries.copy_(self.pose_entries, non_blocking=True)
-        self.h_n_poses.copy_(self.n_poses, non_blocking=True)
-        self.h_kpts.copy_(self.kb.kpts, non_blocking=True)
-        self.h_counts.copy_(self.kb.counts, non_blocking=True)
-        self.h_kpt_start.copy_(self.kb.kpt_start, non_blocking=True)
-        self.h_overflow.copy_(self.kb.overflow, non_blocking=True)
-
-    def host_result(self):
-        return PoseResult(self.h_pose_entries.numpy(), self.h_n_poses.numpy(), self.h_kpts.numpy(),
-                          self.h_counts.numpy(), self.h_kpt_start.numpy(), self.h_overflow.numpy())
-
-    def __call__(self, frames):
-        """End to end: frames float32 [n,3,H,W] on the host (pinned for an asynchronous copy) or on the
-        device -> PoseResult on the host.  Synchronises before returning."""
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+    def submit(self, frames):
+        """Enqueue one batch: frames float32 [n,3,H,W], pinned host memory (asynchronous copy) or device."""
+        if len(self._pending) == len(self.slots):
+            raise RuntimeError("pipeline full: collect() a result first (depth=%d)" % len(self.slots))
+        slot = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        with torch.cuda.device(self.device):
             if frames.is_cuda:
                 x = frames
+                slot.copied.record(torch.cuda.current_stream())
             else:
-                self.x_dev.copy_(frames, non_blocking=True)
-                x = self.x_dev
-            self.enqueue(x)
-            self._enqueue_d2h()
-        self.stream.synchronize()
-        return self.host_result()
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(slot.done)   # the kernels that read this buffer last are finished
+                    slot.x_dev.copy_(frames, non_blocking=True)
+                    slot.copied.record(self.copy_stream)
+                x = slot.x_dev
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(slot.copied)
+                for c in self.chunks:
+                    sl = slice(c.lo, c.lo + c.n)
+                    c.enqueue(x[sl])
+                    slot.h_pose_entries[sl].copy_(c.pose_entries, non_blocking=True)
+                    slot.h_n_poses[sl].copy_(c.n_poses, non_blocking=True)
+                    slot.h_kpts[sl].copy_(c.kb.kpts, non_blocking=True)
+                    slot.h_counts[sl].copy_(c.kb.counts, non_blocking=True)
+                    slot.h_kpt_start[sl].copy_(c.kb.kpt_start, non_blocking=True)
+                    slot.h_overflow[sl].copy_(c.kb.overflow, non_blocking=True)
+                slot.done.record(self.stream)
+        self._pending.append(slot)
+
+    def collect(self):
+        """PoseResult of the oldest submitted batch (blocks until its read-back has finished)."""
+        if not self._pending:
+            raise RuntimeError("nothing submitted")
+        slot = self._pending.pop(0)
+        slot.done.synchronize()
+        return slot.result()
+
+    def __call__(self, frames):
+        """End to end, synchronous: frames -> PoseResult on the host."""
+        while self._pending:
+            self.collect()
+        self.submit(frames)
+        return self.collect()
 
     def error_flag(self):
-        return self.plan.error_flag()
+        return max(c.plan.error_flag() for c in self.chunks)

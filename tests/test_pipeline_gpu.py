@@ -44,7 +44,8 @@ def test_pipeline_end_to_end(env, precision):
     inj[..., :19] = hm.transpose(0, 2, 3, 1)
     inj[..., 19:57] = paf.transpose(0, 2, 3, 1)
     inj_d = torch.from_numpy(inj).cuda()
-    pipe = PosePipeline(net, B, H, W, precision=precision, demo=True, heads_hook=lambda t: t.add_(inj_d))
+    pipe = PosePipeline(net, B, H, W, precision=precision, demo=True, chunk=3,
+                        heads_hook=lambda t, lo: t.add_(inj_d[lo:lo + t.shape[0]]))
     x = synth.synthetic_net_input(B, H, W, seed=2)
     res = pipe(x.pin_memory()).check()
     assert pipe.error_flag() == 0
