@@ -198,24 +198,27 @@ struct DwTileParams {
   uint32_t stage_bytes;
 };
 
-template <typename T> struct SmemVec8;
+template <typename T> struct SmemVec8;  // 8 channels from shared memory as four packed fp32 pairs
 template <> struct SmemVec8<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const uint8_t *p, float (&v)[8]) {
+  static __device__ __forceinline__ void load(const uint8_t *p, float2 (&v)[4]) {
     uint4 raw = *reinterpret_cast<const uint4 *>(p);
     const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 f = __bfloat1622float2(h[j]);
-      v[2 * j] = f.x; v[2 * j + 1] = f.y;
-    }
+    for (int j = 0; j < 4; ++j) v[j] = __bfloat1622float2(h[j]);
   }
 };
 template <> struct SmemVec8<float> {
-  static __device__ __forceinline__ void load(const uint8_t *p, float (&v)[8]) {
+  static __device__ __forceinline__ void load(const uint8_t *p, float2 (&v)[4]) {
     float4 a = reinterpret_cast<const float4 *>(p)[0], b = reinterpret_cast<const float4 *>(p)[1];
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+    v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
   }
 };
+__device__ __forceinline__ void ldg_pairs(const float *p, float2 (&v)[4]) {
+  float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+  v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+  v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+}
 
 template <typename T, int S, int D>
 __global__ void __launch_bounds__(256)
@@ -268,21 +271,21 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict
     const int yo = tyy * p.th + ty, xo0 = tx * p.tw + xg * TWT;
     const uint8_t *sbuf = bufs + (size_t)buf * p.stage_bytes;
     const int pix_bytes = p.cb * (int)sizeof(T);
-    float acc[TWT][8];
+    float2 acc[TWT][4];  // packed fp32 pairs: one FFMA2 does two channels
 #pragma unroll
     for (int a = 0; a < TWT; ++a)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc[a][j] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      float wk[3][8];
+      float2 wk[3][4];
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) Vec8<float>::load(w9c + (size_t)(ky * 3 + kx) * p.C + c0, wk[kx]);
+      for (int kx = 0; kx < 3; ++kx) ldg_pairs(w9c + (size_t)(ky * 3 + kx) * p.C + c0, wk[kx]);
       const uint8_t *rowp = sbuf + ((size_t)(ty * S + ky * D) * p.iw + (size_t)xg * TWT * S) * pix_bytes +
                             cv * 8 * (int)sizeof(T);
 #pragma unroll
       for (int ci = 0; ci < NCOL; ++ci) {
-        float v[8];
+        float2 v[4];
         SmemVec8<T>::load(rowp + (size_t)ci * pix_bytes, v);
 #pragma unroll
         for (int a = 0; a < TWT; ++a) {
@@ -290,23 +293,27 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict
           for (int kx = 0; kx < 3; ++kx) {
             if (a * S + kx * D == ci) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[a][j] = fmaf(v[j], wk[kx][j], acc[a][j]);
+              for (int j = 0; j < 4; ++j) acc[a][j] = __ffma2_rn(v[j], wk[kx][j], acc[a][j]);
             }
           }
         }
       }
     }
     if (yo < p.Ho) {
-      float sc[8], sh[8];
-      Vec8<float>::load(scale + c0, sc);
-      Vec8<float>::load(shift + c0, sh);
+      float2 sc[4], sh[4];
+      ldg_pairs(scale + c0, sc);
+      ldg_pairs(shift + c0, sh);
 #pragma unroll
       for (int a = 0; a < TWT; ++a) {
         const int xo = xo0 + a;
         if (xo < p.Wo) {
           float o[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = act_apply(fmaf(acc[a][j], sc[j], sh[j]), p.act);
+          for (int j = 0; j < 4; ++j) {
+            const float2 r = __ffma2_rn(acc[a][j], sc[j], sh[j]);
+            o[2 * j] = act_apply(r.x, p.act);
+            o[2 * j + 1] = act_apply(r.y, p.act);
+          }
           Vec8<T>::store(out + (((size_t)img * p.Ho + yo) * p.Wo + xo) * p.C + c0, o);
         }
       }

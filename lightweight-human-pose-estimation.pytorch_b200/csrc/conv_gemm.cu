@@ -180,6 +180,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint8_t *stage_base = smem + L.staging_off + (size_t)q * 2 * kStageOutBytes;
         const int r0 = q * 32;
         const int by0 = r0 / p.tile_w, bx0 = r0 - by0 * p.tile_w;
+        const int act = p.act;
+        const bool fast_relu = act == LWP_ACT_RELU && p.residual == nullptr;
         for (int c = 0; c < p.block_n; c += kChunkCols) {
           const int cg0 = tc.n0 + c;
           if (cg0 >= p.n_store) break;  // warp-uniform
@@ -194,15 +196,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
               const int cg = cg0 + half * 32 + g8 * 8;
-              float v[8];
-              {
-                const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + cg), sc1 = *reinterpret_cast<const float4 *>(s_scale + cg + 4);
-                const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + cg), sh1 = *reinterpret_cast<const float4 *>(s_shift + cg + 4);
-                const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-                const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+              // y = acc * scale + shift as packed fp32 FMAs (FFMA2), two channels per instruction
+              const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + cg), sc1 = *reinterpret_cast<const float4 *>(s_scale + cg + 4);
+              const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + cg), sh1 = *reinterpret_cast<const float4 *>(s_shift + cg + 4);
+              float2 a2[4];
+              a2[0] = __ffma2_rn(make_float2(__uint_as_float(r[g8 * 8 + 0]), __uint_as_float(r[g8 * 8 + 1])), make_float2(sc0.x, sc0.y), make_float2(sh0.x, sh0.y));
+              a2[1] = __ffma2_rn(make_float2(__uint_as_float(r[g8 * 8 + 2]), __uint_as_float(r[g8 * 8 + 3])), make_float2(sc0.z, sc0.w), make_float2(sh0.z, sh0.w));
+              a2[2] = __ffma2_rn(make_float2(__uint_as_float(r[g8 * 8 + 4]), __uint_as_float(r[g8 * 8 + 5])), make_float2(sc1.x, sc1.y), make_float2(sh1.x, sh1.y));
+              a2[3] = __ffma2_rn(make_float2(__uint_as_float(r[g8 * 8 + 6]), __uint_as_float(r[g8 * 8 + 7])), make_float2(sc1.z, sc1.w), make_float2(sh1.z, sh1.w));
+              if constexpr (!kTf32) {
+                if (fast_relu) {  // bf16, ReLU, no residual: round first, then one packed max per two channels
+                  const int j0 = (half * 32 + g8 * 8) / 8;
+                  uint4 pk;
+                  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+                  const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  v[j] = apply_act(fmaf(__uint_as_float(r[g8 * 8 + j]), scv[j], shv[j]), p.act);
+                  for (int j = 0; j < 4; ++j) h[j] = __hmax2(__float22bfloat162_rn(a2[j]), zero2);
+                  *reinterpret_cast<uint4 *>(sbuf + lane * 128 + ((j0 ^ (lane & 7)) << 4)) = pk;
+                  continue;
+                }
+              }
+              float v[8] = {a2[0].x, a2[0].y, a2[1].x, a2[1].y, a2[2].x, a2[2].y, a2[3].x, a2[3].y};
+              if (act == LWP_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+              } else if (act == LWP_ACT_ELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
               }
               if (p.residual != nullptr && valid && cg + 8 <= p.n_store) {
                 if constexpr (kTf32) {

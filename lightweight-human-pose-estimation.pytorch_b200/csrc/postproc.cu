@@ -171,44 +171,51 @@ peak_candidates_kernel(const float *__restrict__ hm, int H, int W, int ld, int n
   }
 }
 
-// Fused variant: the up-sampled heat-map is never written to memory.  A block rebuilds a 32x32 tile
-// (+1 halo) of the up-sampled map for 6 channels in shared memory straight from the stride-8 source --
-// separable cubic with exactly the operation order of upsample_cubic_kernel, so the values are
-// bit-identical to the materialised map -- and runs the same threshold + strict 4-neighbour test on it.
-constexpr int kPkTile = 32, kPkPad = kPkTile + 2, kPkSrcMax = 16, kPkCG = 6;
+// Fused variant: the up-sampled heat-map is never written to memory.  A block rebuilds a tile of
+// 30 columns x 32 rows (+1 halo) of the up-sampled map for all scanned channels straight from the
+// stride-8 source -- separable cubic with exactly the operation order of upsample_cubic_kernel, so the
+// values are bit-identical to the materialised map.  Lanes own up-sampled columns (each lane keeps its
+// column's cubic weights in registers), warps own channels: the horizontal pass goes source -> smem,
+// the vertical pass streams down the rows keeping three consecutive rows in registers, so the up/down
+// neighbours are registers and the left/right neighbours are warp shuffles.
+constexpr int kPkCols = 30, kPkRows = 32, kPkSrcMax = 16, kPkWarps = 6, kPkMaxCh = 24;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPkWarps * 32)
 peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__restrict__ cand,
                              int *__restrict__ cand_count, int cap, int *__restrict__ overflow) {
-  __shared__ float s_cx[kPkPad][4], s_cy[kPkPad][4];
-  __shared__ int s_sx[kPkPad], s_sy[kPkPad];
+  __shared__ float s_cy[kPkRows + 2][4];
+  __shared__ int s_sy[kPkRows + 2];
   __shared__ int s_win[4];  // sx_lo, ncols, sy_lo, nrows
   extern __shared__ float pk_smem[];
-  float *s_src = pk_smem;                                         // [nrows][ncols][CG]
-  float *s_T = s_src + kPkSrcMax * kPkSrcMax * kPkCG;             // [nrows][kPkPad][CG]
-  float *s_V = s_T + kPkSrcMax * kPkPad * kPkCG;                  // [kPkPad][kPkPad][CG]
-  const int tid = threadIdx.x;
-  const int tiles_x = (u.W + kPkTile - 1) / kPkTile;
+  float *s_src = pk_smem;                                   // [nrows][n_ch][kPkSrcMax]
+  float *s_T = s_src + kPkSrcMax * n_ch * kPkSrcMax;        // [nrows][n_ch][32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = (u.W + kPkCols - 1) / kPkCols;
   const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-  const int cg0 = blockIdx.y * kPkCG, img = blockIdx.z;
-  const int ox0 = tx * kPkTile, oy0 = ty * kPkTile;
+  const int img = blockIdx.y;
+  const int ox0 = tx * kPkCols, oy0 = ty * kPkRows;
   constexpr int kInvalid = -(1 << 30);
-  if (tid < kPkPad) {
-    const int d = ox0 - 1 + tid;
-    int sx = kInvalid;
-    if (d >= 0 && d < u.W) sx = cubic_axis(d, u.scale_x, s_cx[tid]);
-    s_sx[tid] = sx;
-  } else if (tid >= 64 && tid < 64 + kPkPad) {
-    const int i = tid - 64, e = oy0 - 1 + i;
+  // this lane's up-sampled column (lanes 0 and 31 are halo only)
+  const int d = ox0 - 1 + lane;
+  const bool col_ok = d >= 0 && d < u.W;
+  float cx[4] = {0.f, 0.f, 0.f, 0.f};
+  const int sx = col_ok ? cubic_axis(d, u.scale_x, cx) : kInvalid;
+  if (tid < kPkRows + 2) {
+    const int e = oy0 - 1 + tid;
     int sy = kInvalid;
-    if (e >= 0 && e < u.H) sy = cubic_axis(e, u.scale_y, s_cy[i]);
-    s_sy[i] = sy;
+    if (e >= 0 && e < u.H) sy = cubic_axis(e, u.scale_y, s_cy[tid]);
+    s_sy[tid] = sy;
+  }
+  // source window: sx is monotone in d, so the first / last valid lane give the range
+  {
+    const unsigned okm = __ballot_sync(0xffffffffu, col_ok);
+    const int lo = __shfl_sync(0xffffffffu, sx, __ffs(okm) - 1) - 1;
+    const int hi = __shfl_sync(0xffffffffu, sx, 31 - __clz(okm)) + 2;
+    if (tid == 0) { s_win[0] = lo; s_win[1] = hi - lo + 1; }
   }
   __syncthreads();
   if (tid == 0) {
-    const int jf = ox0 == 0 ? 1 : 0, jl = min(kPkPad - 1, u.W - ox0);
-    const int if_ = oy0 == 0 ? 1 : 0, il = min(kPkPad - 1, u.H - oy0);
-    s_win[0] = s_sx[jf] - 1; s_win[1] = s_sx[jl] + 2 - s_win[0] + 1;
+    const int if_ = oy0 == 0 ? 1 : 0, il = min(kPkRows + 1, u.H - oy0);
     s_win[2] = s_sy[if_] - 1; s_win[3] = s_sy[il] + 2 - s_win[2] + 1;
   }
   __syncthreads();
@@ -217,65 +224,61 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
     if (tid == 0) overflow[img] = 1;
     return;
   }
-  // 1. source window (replicate border by clamping the coordinates)
-  for (int idx = tid; idx < nrows * ncols * kPkCG; idx += blockDim.x) {
-    const int c = idx % kPkCG, rx = (idx / kPkCG) % ncols, ry = idx / (kPkCG * ncols);
-    float v = 0.f;
-    if (cg0 + c < n_ch)
-      v = __ldg(u.src + (((size_t)img * u.h + clampi(sy_lo + ry, 0, u.h - 1)) * u.w + clampi(sx_lo + rx, 0, u.w - 1)) *
-                            (size_t)u.ld + cg0 + c);
-    s_src[idx] = v;
+  // 1. source window -> smem [ry][c][rx]; replicate border by clamping the coordinates
+  for (int idx = tid; idx < nrows * ncols * n_ch; idx += blockDim.x) {
+    const int c = idx % n_ch, rx = (idx / n_ch) % ncols, ry = idx / (n_ch * ncols);
+    s_src[((size_t)ry * n_ch + c) * kPkSrcMax + rx] =
+        __ldg(u.src + (((size_t)img * u.h + clampi(sy_lo + ry, 0, u.h - 1)) * u.w + clampi(sx_lo + rx, 0, u.w - 1)) *
+                          (size_t)u.ld + c);
   }
   __syncthreads();
-  // 2. horizontal pass on every source row of the window
-  for (int idx = tid; idx < nrows * kPkPad * kPkCG; idx += blockDim.x) {
-    const int c = idx % kPkCG, j = (idx / kPkCG) % kPkPad, ry = idx / (kPkCG * kPkPad);
-    const int sx = s_sx[j];
-    float v = 0.f;
-    if (sx != kInvalid) {
-      const float *p = s_src + ((size_t)ry * ncols + (sx - 1 - sx_lo)) * kPkCG + c;
-      const bool border = (sx < 1) || (sx + 2 >= u.w);
-      float p0 = __fmul_rn(p[0], s_cx[j][0]);
-      float p1 = __fmul_rn(p[kPkCG], s_cx[j][1]);
-      float p2 = __fmul_rn(p[2 * kPkCG], s_cx[j][2]);
-      float p3 = __fmul_rn(p[3 * kPkCG], s_cx[j][3]);
-      v = border ? __fadd_rn(0.f, p0) : p0;
-      v = __fadd_rn(v, p1);
-      v = __fadd_rn(v, p2);
-      v = __fadd_rn(v, p3);
-    }
-    s_T[idx] = v;
-  }
-  __syncthreads();
-  // 3. vertical pass + threshold; positions outside the image count as 0 like the reference's zero border
-  const int rowlen = u.W * u.c_layout, body = rowlen - (rowlen & 3);
-  for (int idx = tid; idx < kPkPad * kPkPad * kPkCG; idx += blockDim.x) {
-    const int c = idx % kPkCG, j = (idx / kPkCG) % kPkPad, i = idx / (kPkCG * kPkPad);
-    const int sx = s_sx[j], sy = s_sy[i];
-    float v = 0.f;
-    if (sx != kInvalid && sy != kInvalid) {
-      const float *t = s_T + ((size_t)(sy - 1 - sy_lo) * kPkPad + j) * kPkCG + c;
-      float T[4] = {t[0], t[kPkPad * kPkCG], t[2 * kPkPad * kPkCG], t[3 * kPkPad * kPkCG]};
-      float cyv[4] = {s_cy[i][0], s_cy[i][1], s_cy[i][2], s_cy[i][3]};
-      v = thr01(cubic_vsum(T, cyv, (ox0 - 1 + j) * u.c_layout + cg0 + c < body));
-    }
-    s_V[idx] = v;
-  }
-  __syncthreads();
-  // 4. strict 4-neighbour maxima of the tile interior
-  for (int idx = tid; idx < kPkTile * kPkTile * kPkCG; idx += blockDim.x) {
-    const int c = idx % kPkCG, jx = (idx / kPkCG) % kPkTile, iy = idx / (kPkCG * kPkTile);
-    const int d = ox0 + jx, e = oy0 + iy, ch = cg0 + c;
-    if (d >= u.W || e >= u.H || ch >= n_ch) continue;
-    const float *vp = s_V + ((size_t)(iy + 1) * kPkPad + (jx + 1)) * kPkCG + c;
-    const float v = vp[0];
-    if (!(v > 0.f)) continue;
-    if (v > vp[-kPkCG] && v > vp[kPkCG] && v > vp[-kPkPad * kPkCG] && v > vp[kPkPad * kPkCG]) {
-      int slot = atomicAdd(&cand_count[img * n_ch + ch], 1);
-      if (slot < cap) {
-        unsigned long long key = ((unsigned long long)(((unsigned)d << 16) | (unsigned)e) << 32) | __float_as_uint(v);
-        cand[((size_t)img * n_ch + ch) * cap + slot] = key;
+  // 2. horizontal pass: T[ry][c][lane]
+  const bool border = (sx < 1) || (sx + 2 >= u.w);
+  const int rx0 = col_ok ? sx - 1 - sx_lo : 0;
+  for (int c = warp; c < n_ch; c += kPkWarps) {
+    for (int ry = 0; ry < nrows; ++ry) {
+      const float *p = s_src + ((size_t)ry * n_ch + c) * kPkSrcMax + rx0;
+      float v = 0.f;
+      if (col_ok) {
+        float p0 = __fmul_rn(p[0], cx[0]), p1 = __fmul_rn(p[1], cx[1]);
+        float p2 = __fmul_rn(p[2], cx[2]), p3 = __fmul_rn(p[3], cx[3]);
+        v = border ? __fadd_rn(0.f, p0) : p0;
+        v = __fadd_rn(v, p1);
+        v = __fadd_rn(v, p2);
+        v = __fadd_rn(v, p3);
       }
+      s_T[((size_t)ry * n_ch + c) * 32 + lane] = v;
+    }
+  }
+  __syncwarp();  // a warp only reads back the T rows of its own channels
+  // 3. vertical pass streamed down the rows + strict 4-neighbour test on the row in the middle
+  const int rowlen = u.W * u.c_layout, body = rowlen - (rowlen & 3);
+  for (int c = warp; c < n_ch; c += kPkWarps) {
+    const bool simd_body = d * u.c_layout + c < body;
+    float v0 = 0.f, v1 = 0.f;  // rows i-2, i-1
+    for (int i = 0; i < kPkRows + 2; ++i) {
+      const int sy = s_sy[i];
+      float v2 = 0.f;
+      if (sy != kInvalid && col_ok) {
+        const float *t = s_T + ((size_t)(sy - 1 - sy_lo) * n_ch + c) * 32 + lane;
+        const float T[4] = {t[0], t[n_ch * 32], t[2 * n_ch * 32], t[3 * n_ch * 32]};
+        const float cyv[4] = {s_cy[i][0], s_cy[i][1], s_cy[i][2], s_cy[i][3]};
+        v2 = thr01(cubic_vsum(T, cyv, simd_body));
+      }
+      const float vl = __shfl_up_sync(0xffffffffu, v1, 1), vr = __shfl_down_sync(0xffffffffu, v1, 1);
+      // centre = row i-1 (tile rows are i-1 in [1, kPkRows]), interior lanes only
+      if (i >= 2 && lane >= 1 && lane <= kPkCols && col_ok && v1 > 0.f && v1 > vl && v1 > vr && v1 > v0 && v1 > v2) {
+        const int e = oy0 - 1 + (i - 1);
+        if (e < u.H) {
+          int slot = atomicAdd(&cand_count[img * n_ch + c], 1);
+          if (slot < cap) {
+            unsigned long long key =
+                ((unsigned long long)(((unsigned)d << 16) | (unsigned)e) << 32) | __float_as_uint(v1);
+            cand[((size_t)img * n_ch + c) * cap + slot] = key;
+          }
+        }
+      }
+      v0 = v1; v1 = v2;
     }
   }
 }
@@ -553,6 +556,7 @@ limb_match_kernel(const Conn *__restrict__ conn, const int *__restrict__ conn_co
 
 // One warp per image walks the 19 limbs in table order and builds the pose entries exactly like the
 // reference's sequential code; lanes parallelise the "for every pose" scans.
+template <bool kSmem>
 __global__ void __launch_bounds__(32)
 pose_assemble_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ counts,
                      const int *__restrict__ kpt_start, int cap_kpts, const Match *__restrict__ match,
@@ -560,7 +564,10 @@ pose_assemble_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restric
                      double *__restrict__ pose_entries, int *__restrict__ n_poses, int cap_poses,
                      int *__restrict__ overflow) {
   const int img = blockIdx.x, lane = threadIdx.x;
-  double *poses = scratch + (size_t)img * cap_poses * LWP_POSE_ENTRY;
+  extern __shared__ __align__(16) unsigned char pa_smem[];
+  // working set in shared memory (latency ~30 cycles instead of an L2 round trip per dependent step)
+  double *poses = kSmem ? reinterpret_cast<double *>(pa_smem) : scratch + (size_t)img * cap_poses * LWP_POSE_ENTRY;
+  Match *s_match = reinterpret_cast<Match *>(pa_smem + (kSmem ? (size_t)cap_poses * LWP_POSE_ENTRY * sizeof(double) : 0));
 #define POSE(jj) (poses + (size_t)(jj) * LWP_POSE_ENTRY)
   int np = 0;
   bool ovf = false;
@@ -599,7 +606,13 @@ pose_assemble_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restric
     }
     const int m = match_count[img * LWP_NUM_LIMBS + limb];
     if (m == 0) continue;
-    const Match *M = match + ((size_t)img * LWP_NUM_LIMBS + limb) * cap_kpts;
+    const Match *Mg = match + ((size_t)img * LWP_NUM_LIMBS + limb) * cap_kpts;
+    const Match *M = Mg;
+    if (kSmem) {  // stage this limb's accepted connections with one coalesced read
+      for (int c = lane; c < m; c += 32) s_match[c] = Mg[c];
+      __syncwarp();
+      M = s_match;
+    }
     if (limb == 0) {  // :159-165 replaces the list
       np = 0;
       for (int c = 0; c < m; ++c) {
@@ -721,13 +734,15 @@ static int extract_common(bool fused, const float *hm, const UpSrc *up, int n, i
   if (!attr_set) {
     LWP_CUDA_CHECK(cudaFuncSetAttribute(peak_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     LWP_CUDA_CHECK(cudaFuncSetAttribute(peak_candidates_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        64 * 1024));
+                                        100 * 1024));
     attr_set = true;
   }
   if (fused) {
-    const size_t pk_smem = (size_t)(kPkSrcMax * kPkSrcMax + kPkSrcMax * kPkPad + kPkPad * kPkPad) * kPkCG * sizeof(float);
-    dim3 grid(ceil_div(W, kPkTile) * ceil_div(H, kPkTile), ceil_div(n_ch, kPkCG), n);
-    peak_candidates_fused_kernel<<<grid, 256, pk_smem, st>>>(*up, n_ch, cand, cand_count, cap_candidates, overflow);
+    LWP_REQUIRE(n_ch <= kPkMaxCh, "lwp_extract_keypoints_fused: at most %d channels", kPkMaxCh);
+    const size_t pk_smem = (size_t)(kPkSrcMax * n_ch * kPkSrcMax + kPkSrcMax * n_ch * 32) * sizeof(float);
+    dim3 grid(ceil_div(W, kPkCols) * ceil_div(H, kPkRows), n);
+    peak_candidates_fused_kernel<<<grid, kPkWarps * 32, pk_smem, st>>>(*up, n_ch, cand, cand_count, cap_candidates,
+                                                                      overflow);
   } else {
     long long total = (long long)n * H * W * n_ch;
     peak_candidates_kernel<<<grid_for(total, 256), 256, 0, st>>>(hm, H, W, ld, n_ch, cand, cand_count, cap_candidates,
@@ -815,8 +830,8 @@ static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *cou
   cudaStream_t st = (cudaStream_t)stream;
   GroupWs w = carve_group_ws(workspace, n, cap_kpts, cap_connections, cap_poses);
   LWP_CUDA_CHECK(cudaMemsetAsync(w.conn_count, 0, (size_t)n * LWP_NUM_LIMBS * sizeof(int), st));
-  int bx = 1184 / (LWP_NUM_LIMBS * n);
-  bx = bx < 2 ? 2 : (bx > 32 ? 32 : bx);
+  int bx = 2368 / (LWP_NUM_LIMBS * n);  // frames differ a lot in pair count: spread each limb over several blocks
+  bx = bx < 8 ? 8 : (bx > 32 ? 32 : bx);
   UpSrc u0;
   memset(&u0, 0, sizeof(u0));
   if (fused)
@@ -836,8 +851,20 @@ static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *cou
   limb_match_kernel<<<dim3(LWP_NUM_LIMBS, n), 256, smem, st>>>(w.conn, w.conn_count, cap_connections, kpts, counts,
                                                               kpt_start, cap_kpts, w.match, w.match_count, overflow);
   LWP_LAUNCH_CHECK();
-  pose_assemble_kernel<<<n, 32, 0, st>>>(kpts, counts, kpt_start, cap_kpts, w.match, w.match_count, w.poses,
-                                         pose_entries, n_poses, cap_poses, overflow);
+  const size_t pa_smem = (size_t)cap_poses * LWP_POSE_ENTRY * sizeof(double) + (size_t)cap_kpts * sizeof(Match);
+  if (pa_smem <= 160 * 1024) {
+    static bool pa_attr = false;
+    if (!pa_attr) {
+      LWP_CUDA_CHECK(cudaFuncSetAttribute(pose_assemble_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          160 * 1024));
+      pa_attr = true;
+    }
+    pose_assemble_kernel<true><<<n, 32, pa_smem, st>>>(kpts, counts, kpt_start, cap_kpts, w.match, w.match_count,
+                                                       w.poses, pose_entries, n_poses, cap_poses, overflow);
+  } else {
+    pose_assemble_kernel<false><<<n, 32, (size_t)cap_kpts * sizeof(Match), st>>>(
+        kpts, counts, kpt_start, cap_kpts, w.match, w.match_count, w.poses, pose_entries, n_poses, cap_poses, overflow);
+  }
   LWP_LAUNCH_CHECK();
   return LWP_OK;
 }
