@@ -175,6 +175,17 @@ int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, const void *w
                            float *out_f32, int out_f32_ld, int n, int H, int W, int Cin, int Cout, int taps,
                            int dilation, int act);
 
+/*
+ * Fused depthwise-separable block (modules/conv.py:13-32 conv_dw / conv_dw_no_bn): depthwise 3x3 stride 1
+ * (pad == dilation, 1 or 2) + scale/shift + dw_act, whose result is written straight into the shared-memory A
+ * operand of the following 1x1 convolution's tcgen05 GEMM (+ scale/shift + act (+ residual)).  The depthwise
+ * output never goes to global memory.  in: NHWC [n][H][W][Cin] (dense), dw_w: [9][Cin] float32,
+ * w: [Cout_pad][Cin] plan dtype; Cin a multiple of the 128-byte K block, Cout_pad (multiple of 64) must divide 512.
+ */
+int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w, const float *dw_scale, const float *dw_shift,
+                      int dw_act, int dilation, const void *w, const float *scale, const float *shift, int act,
+                      const void *residual, int res_ld, void *out, int out_ld, int n, int H, int W, int Cin, int Cout);
+
 /* NHWC (plan dtype or float32) -> NCHW float32, for the tensors `forward` returns at the module boundary. */
 int lwp_plan_add_nhwc_to_nchw(lwp_plan *p, const void *in, int in_ld, int in_is_f32, int c0, int c, float *out, int n,
                               int H, int W);

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "conv_gemm.cuh"
 #include "tcgen05.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace lwp {
 
@@ -175,98 +176,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const size_t pix = ((size_t)tc.img * p.H + y) * (size_t)p.W + x;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
       if (p.tma_store) {
-        // ---- staged epilogue: 128 output bytes per row per chunk -> swizzled smem -> one TMA tensor store per warp
-        constexpr int kChunkCols = kTf32 ? 32 : 64;
-        uint8_t *stage_base = smem + L.staging_off + (size_t)q * 2 * kStageOutBytes;
-        const int r0 = q * 32;
-        const int by0 = r0 / p.tile_w, bx0 = r0 - by0 * p.tile_w;
-        const int act = p.act;
-        const bool fast_relu = act == LWP_ACT_RELU && p.residual == nullptr;
-        for (int c = 0; c < p.block_n; c += kChunkCols) {
-          const int cg0 = tc.n0 + c;
-          if (cg0 >= p.n_store) break;  // warp-uniform
-          uint8_t *sbuf = stage_base + (size_t)sbuf_idx * kStageOutBytes;
-          if (lane == 0) ptx::bulk_wait_read<1>();  // the store issued two chunks ago has finished reading this buffer
-          __syncwarp();
-#pragma unroll
-          for (int half = 0; half < kChunkCols / 32; ++half) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(t_row + (uint32_t)(c + half * 32), r);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const int cg = cg0 + half * 32 + g8 * 8;
-              // y = acc * scale + shift as packed fp32 FMAs (FFMA2), two channels per instruction
-              const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + cg), sc1 = *reinterpret_cast<const float4 *>(s_scale + cg + 4);
-              const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + cg), sh1 = *reinterpret_cast<const float4 *>(s_shift + cg + 4);
-              float2 a2[4];
-              a2[0] = __ffma2_rn(make_float2(__uint_as_float(r[g8 * 8 + 0]), __uint_as_float(r[g8 * 8 + 1])), make_float2(sc0.x, sc0.y), make_float2(sh0.x, sh0.y));
-              a2[1] = __ffma2_rn(make_float2(__uint_as_float(r[g8 * 8 + 2]), __uint_as_float(r[g8 * 8 + 3])), make_float2(sc0.z, sc0.w), make_float2(sh0.z, sh0.w));
-              a2[2] = __ffma2_rn(make_float2(__uint_as_float(r[g8 * 8 + 4]), __uint_as_float(r[g8 * 8 + 5])), make_float2(sc1.x, sc1.y), make_float2(sh1.x, sh1.y));
-              a2[3] = __ffma2_rn(make_float2(__uint_as_float(r[g8 * 8 + 6]), __uint_as_float(r[g8 * 8 + 7])), make_float2(sc1.z, sc1.w), make_float2(sh1.z, sh1.w));
-              if constexpr (!kTf32) {
-                if (fast_relu) {  // bf16, ReLU, no residual: round first, then one packed max per two channels
-                  const int j0 = (half * 32 + g8 * 8) / 8;
-                  uint4 pk;
-                  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-                  const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) h[j] = __hmax2(__float22bfloat162_rn(a2[j]), zero2);
-                  *reinterpret_cast<uint4 *>(sbuf + lane * 128 + ((j0 ^ (lane & 7)) << 4)) = pk;
-                  continue;
-                }
-              }
-              float v[8] = {a2[0].x, a2[0].y, a2[1].x, a2[1].y, a2[2].x, a2[2].y, a2[3].x, a2[3].y};
-              if (act == LWP_ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-              } else if (act == LWP_ACT_ELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
-              }
-              if (p.residual != nullptr && valid && cg + 8 <= p.n_store) {
-                if constexpr (kTf32) {
-                  const float4 *rp = reinterpret_cast<const float4 *>(
-                      reinterpret_cast<const float *>(p.residual) + pix * p.res_ld + cg);
-                  float4 a = __ldg(rp), b = __ldg(rp + 1);
-                  v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-                  v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-                } else {
-                  const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(
-                      reinterpret_cast<const __nv_bfloat16 *>(p.residual) + pix * p.res_ld + cg));
-                  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    float2 f = __bfloat1622float2(h[j]);
-                    v[2 * j] += f.x; v[2 * j + 1] += f.y;
-                  }
-                }
-              }
-              // 16-byte pieces of this row's 128-byte line, XOR-swizzled like SWIZZLE_128B expects
-              if constexpr (kTf32) {
-                const int j0 = (half * 32 + g8 * 8) / 4;  // two 16-byte pieces
-                *reinterpret_cast<float4 *>(sbuf + lane * 128 + (((j0) ^ (lane & 7)) << 4)) =
-                    make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4 *>(sbuf + lane * 128 + (((j0 + 1) ^ (lane & 7)) << 4)) =
-                    make_float4(v[4], v[5], v[6], v[7]);
-              } else {
-                const int j0 = (half * 32 + g8 * 8) / 8;
-                uint4 pk;
-                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                *reinterpret_cast<uint4 *>(sbuf + lane * 128 + ((j0 ^ (lane & 7)) << 4)) = pk;
-              }
-            }
-          }
-          ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
-          __syncwarp();
-          if (lane == 0) {
-            ptx::tma_store_4d(&tmC, sbuf, cg0, tc.x0 + bx0, tc.y0 + by0, tc.img);
-            ptx::bulk_commit();
-          }
-          sbuf_idx ^= 1;
-        }
+        staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)q * 2 * kStageOutBytes, 2, sbuf_idx, t_row, tc.n0,
+                                    p.block_n, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld, valid, pix, lane,
+                                    tc.x0 + (q * 32) % p.tile_w, tc.y0 + (q * 32) / p.tile_w, tc.img);
       } else {
         for (int c = 0; c < p.block_n; c += 32) {
           uint32_t r[32];

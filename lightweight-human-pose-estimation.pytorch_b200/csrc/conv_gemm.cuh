@@ -3,6 +3,8 @@
 #include <cuda.h>
 #include <stdint.h>
 
+#include "gemm_epilogue.cuh"
+
 namespace lwp {
 
 constexpr int kGemmThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
@@ -43,7 +45,6 @@ struct GemmParams {
   int store_bw, store_bh;  // pixel box of one warp's 32 rows (store_bw * store_bh == 32)
 };
 
-constexpr int kStageOutBytes = 32 * 128;          // one warp, one 128-byte column chunk
 constexpr int kStagingBytes = 4 * 2 * kStageOutBytes;  // 4 epilogue warps x double buffer
 
 size_t conv_gemm_smem_bytes(const GemmParams &p);

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "conv_direct.cuh"
 #include "conv_gemm.cuh"
+#include "dwpw_gemm.cuh"
 #include "tcgen05.cuh"
 
 #include <cuda.h>
@@ -30,7 +31,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-enum OpKind { OP_STEM, OP_DW, OP_GEMM, OP_NCHW };
+enum OpKind { OP_STEM, OP_DW, OP_GEMM, OP_NCHW, OP_DWPW };
 
 struct Op {
   OpKind kind;
@@ -45,6 +46,7 @@ struct Op {
   // gemm (tmA is also the input map of the TMA depthwise kernel)
   CUtensorMap tmA, tmB, tmC;
   GemmParams gp;
+  DwpwParams fp;
   int grid = 0;
 };
 
@@ -265,6 +267,102 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   return LWP_OK;
 }
 
+extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w, const float *dw_scale,
+                                 const float *dw_shift, int dw_act, int dilation, const void *w, const float *scale,
+                                 const float *shift, int act, const void *residual, int res_ld, void *out, int out_ld,
+                                 int n, int H, int W, int Cin, int Cout) {
+  LWP_REQUIRE(p && in && dw_w && dw_scale && dw_shift && w && scale && shift && out, "lwp_plan_add_dwpw: null pointer");
+  LWP_REQUIRE(n > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "lwp_plan_add_dwpw: bad shape");
+  LWP_REQUIRE(dilation == 1 || dilation == 2, "lwp_plan_add_dwpw: dilation must be 1 or 2");
+  const bool tf32 = p->dtype == LWP_DTYPE_TF32;
+  const int es = tf32 ? 4 : 2;
+  const int kb_ch = kKBlockBytes / es;
+  const int cout_pad = (Cout + 63) / 64 * 64;
+  LWP_REQUIRE(Cin % kb_ch == 0, "lwp_plan_add_dwpw: Cin must be a multiple of %d", kb_ch);
+  LWP_REQUIRE(cout_pad <= 512 && (512 % cout_pad == 0), "lwp_plan_add_dwpw: Cout (padded %d) must divide 512", cout_pad);
+  LWP_REQUIRE(out_ld % 8 == 0 && out_ld >= Cout && ((uintptr_t)out % 16) == 0 && ((uintptr_t)in % 16) == 0 &&
+                  ((uintptr_t)w % 16) == 0,
+              "lwp_plan_add_dwpw: bad out_ld / alignment");
+  LWP_REQUIRE(!residual || (res_ld % 8 == 0 && (uintptr_t)residual % 16 == 0), "lwp_plan_add_dwpw: bad res_ld");
+  int rc = dwpw_init();
+  if (rc != LWP_OK) return rc;
+  Op op;
+  op.kind = OP_DWPW;
+  DwpwParams &f = op.fp;
+  f.H = H; f.W = W; f.NIMG = n; f.dil = dilation; f.cin = Cin; f.kb_ch = kb_ch; f.kblocks = Cin / kb_ch;
+  f.cout_pad = cout_pad;
+  const int chunk_cols = kKBlockBytes / es;
+  int n_store = cout_pad;
+  if (out_ld < n_store) n_store = out_ld / 8 * 8;
+  if (residual) { int lim = (Cout + 7) / 8 * 8; if (lim < n_store) n_store = lim; }
+  LWP_REQUIRE(n_store % chunk_cols == 0, "lwp_plan_add_dwpw: stored width %d is not whole 128-byte chunks", n_store);
+  f.n_store = n_store;
+  f.n_mma = cout_pad > 256 ? 2 : 1;
+  f.n_per_mma = cout_pad / f.n_mma;
+  f.idesc = make_umma_idesc(tf32, kBlockM, f.n_per_mma);
+  f.acc_stages = 512 / cout_pad;
+  if (f.acc_stages > 4) f.acc_stages = 4;
+  f.dw_act = dw_act; f.act = act;
+  f.dw_w9c = dw_w; f.dw_scale = dw_scale; f.dw_shift = dw_shift; f.scale = scale; f.shift = shift;
+  f.residual = residual; f.res_ld = res_ld; f.err_flag = p->err_flag;
+  // tile: rectangle of 128 pixels, width a multiple of 4 (a depthwise thread owns 4 consecutive columns)
+  long long best = -1;
+  for (int th = 1; th <= 32; th <<= 1) {
+    const int tw = 128 / th;
+    if (tw < 4) continue;
+    const int iw = tw + 2 * dilation, ih = th + 2 * dilation;
+    if (iw > 256 || ih > 256 || (long long)iw * ih * kKBlockBytes > 40 * 1024) continue;
+    long long cost = (long long)ceil_div(H, th) * ceil_div(W, tw) * ((long long)iw * ih + 128);
+    if (best < 0 || cost < best) { best = cost; f.tile_h = th; f.tile_w = tw; f.iw = iw; f.ih = ih; }
+  }
+  LWP_REQUIRE(best >= 0, "lwp_plan_add_dwpw: no tile shape fits");
+  f.tiles_x = ceil_div(W, f.tile_w); f.tiles_y = ceil_div(H, f.tile_h);
+  f.m_tiles = n * f.tiles_x * f.tiles_y;
+  f.in_stage_bytes = (uint32_t)(f.iw * f.ih * kKBlockBytes);
+  f.b_stage_bytes = (uint32_t)(cout_pad * kKBlockBytes);
+  // shared-memory budget: prefer deep B / A rings, then a second input stage, then double-buffered staging
+  f.b_stages = 2; f.a_stages = 2; f.in_stages = 1; f.staging_bufs = 1;
+  const size_t limit = 232448;
+  { DwpwParams t = f; t.in_stages = 2; if (dwpw_smem_bytes(t) <= limit) f = t; }
+  { DwpwParams t = f; t.staging_bufs = 2; if (dwpw_smem_bytes(t) <= limit) f = t; }
+  { DwpwParams t = f; t.a_stages = 3; if (dwpw_smem_bytes(t) <= limit) f = t; }
+  { DwpwParams t = f; t.b_stages = 3; if (dwpw_smem_bytes(t) <= limit) f = t; }
+  { DwpwParams t = f; t.in_stages = 3; if (dwpw_smem_bytes(t) <= limit) f = t; }
+  if (dwpw_smem_bytes(f) > limit) { set_error("lwp_plan_add_dwpw: shared memory budget exceeded"); return LWP_ECAP; }
+  op.grid = f.m_tiles < num_sms() ? f.m_tiles : num_sms();
+
+  EncodeTiledFn enc = get_encode_fn();
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * es, (cuuint64_t)Cin * es * W, (cuuint64_t)Cin * es * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)kb_ch, (cuuint32_t)f.iw, (cuuint32_t)f.ih, 1};
+    CUresult r = enc(&op.tmA, dt, 4, const_cast<void *>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(dwpw in) failed: %d", (int)r); return LWP_ECUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin * es};
+    cuuint32_t box[2] = {(cuuint32_t)kb_ch, (cuuint32_t)f.n_per_mma};
+    CUresult r = enc(&op.tmB, dt, 2, const_cast<void *>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(dwpw B) failed: %d", (int)r); return LWP_ECUDA; }
+  }
+  {
+    const int bw = f.tile_w < 32 ? f.tile_w : 32, bh = 32 / bw;
+    cuuint64_t dims[4] = {(cuuint64_t)n_store, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)out_ld * es, (cuuint64_t)out_ld * es * W, (cuuint64_t)out_ld * es * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)chunk_cols, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    CUresult r = enc(&op.tmC, dt, 4, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(dwpw C) failed: %d", (int)r); return LWP_ECUDA; }
+  }
+  p->ops.push_back(op);
+  return LWP_OK;
+}
+
 extern "C" int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int last, void *stream) {
   LWP_REQUIRE(p != nullptr, "lwp_plan_run: null plan");
   LWP_REQUIRE(first >= 0 && last <= (int)p->ops.size() && first <= last, "lwp_plan_run_range: bad range");
@@ -288,6 +386,9 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int la
         break;
       case OP_GEMM:
         rc = conv_gemm_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st);
+        break;
+      case OP_DWPW:
+        rc = dwpw_launch(f32, op.tmA, op.tmB, op.tmC, op.fp, op.grid, st);
         break;
       case OP_NCHW:
         rc = nhwc_to_nchw_launch(op.in_f32 != 0, op.in, op.ld, op.c0, op.C, (float *)op.out, op.n, op.H * op.W, st);

@@ -13,6 +13,8 @@ its forward (:114-123):
                                                    producers write straight into a 192-wide buffer
 PyTorch is used for device memory and one-off weight re-layout only.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -167,6 +169,7 @@ class Plan:
         handle = _lib._c_void_p()
         _lib.check(self.lib.lwp_plan_create(code, handle), "lwp_plan_create")
         self.handle = handle
+        self.fuse_dwpw = os.environ.get("LWP_NO_DWPW_FUSION") is None
         self.bufs = []
         self.op_names = []
         self.op_meta = []  # per op: kind, algorithmic flops and bytes (real channel counts, no padding)
@@ -216,21 +219,37 @@ class Plan:
         self.op_meta.append(dict(kind="depthwise", flops=2.0 * 9 * n * ho * wo * d.c,
                                  bytes=float((n * H * W * d.c + n * ho * wo * d.c) * es + 9 * d.c * 4)))
 
+    def _fusable(self, d, g):
+        """Depthwise (stride 1) + pointwise pair that the fused tcgen05 kernel can take."""
+        kb_ch = 64 if self.tdtype == torch.bfloat16 else 32
+        return (self.fuse_dwpw and d.stride == 1 and d.dilation in (1, 2) and g.taps == 1 and d.c == g.cin
+                and d.c % kb_ch == 0 and g.cout_pad <= 512 and 512 % g.cout_pad == 0)
+
+    def _dwpw(self, name, src, d, g, n, H, W, out, out_ld, residual=None, res_ld=0):
+        es = 2 if self.tdtype == torch.bfloat16 else 4
+        _lib.check(self.lib.lwp_plan_add_dwpw(
+            self.handle, src.data_ptr(), d.w.data_ptr(), d.scale.data_ptr(), d.shift.data_ptr(), d.act, d.dilation,
+            g.w.data_ptr(), g.scale.data_ptr(), g.shift.data_ptr(), g.act,
+            residual.data_ptr() if residual is not None else None, res_ld, out.data_ptr(), out_ld, n, H, W, d.c,
+            g.cout), "lwp_plan_add_dwpw(%s)" % name)
+        self.op_names.append(name)
+        px = n * H * W
+        nbytes = px * (d.c + g.cout) * es + d.c * g.cout * es + 9 * d.c * 4
+        if residual is not None:
+            nbytes += px * g.cout * es
+        self.op_meta.append(dict(kind="dwpw", flops=2.0 * px * d.c * (g.cout + 9), bytes=float(nbytes)))
+
     # -- the layer walk -----------------------------------------------------------------------
     def _build(self, P, n_stages_out, num_heatmaps, num_pafs):
         n, H, W = self.n, self.H, self.W
-        # backbone ping-pong buffers: sized for the largest activation either of them ever holds
-        sizes = [0, 0]
-        hh, ww, c, which = H // 2, W // 2, 32, 0
-        sizes[0] = n * hh * ww * 32
+        # backbone ping-pong buffers, both sized for the largest activation of the backbone
+        biggest = n * (H // 2) * (W // 2) * 32
+        hh, ww, c = H // 2, W // 2, 32
         for dw, pw in P.backbone:
             ho, wo = (hh - 1) // dw.stride + 1, (ww - 1) // dw.stride + 1
-            which ^= 1
-            sizes[which] = max(sizes[which], n * ho * wo * c)
-            which ^= 1
-            sizes[which] = max(sizes[which], n * ho * wo * pw.cout_pad)
+            biggest = max(biggest, n * ho * wo * c, n * ho * wo * pw.cout_pad)
             hh, ww, c = ho, wo, pw.cout
-        pp = [self._buf(sizes[0]), self._buf(sizes[1])]
+        pp = [self._buf(biggest), self._buf(biggest)]
 
         w_, s_, b_ = P.stem
         _lib.check(self.lib.lwp_plan_add_stem(self.handle, w_.data_ptr(), s_.data_ptr(), b_.data_ptr(),
@@ -242,8 +261,12 @@ class Plan:
         hh, ww, c, cur = H // 2, W // 2, 32, 0
         for i, (dw, pw) in enumerate(P.backbone):
             ho, wo = (hh - 1) // dw.stride + 1, (ww - 1) // dw.stride + 1
-            self._dw("model.%d.dw" % (i + 1), pp[cur], pp[cur ^ 1], dw, n, hh, ww)
-            self._gemm("model.%d.pw" % (i + 1), pp[cur ^ 1], c, pw, n, ho, wo, out=pp[cur], out_ld=pw.cout_pad)
+            if self._fusable(dw, pw):   # depthwise result goes straight into the GEMM's smem A operand
+                self._dwpw("model.%d.dwpw" % (i + 1), pp[cur], dw, pw, n, hh, ww, pp[cur ^ 1], pw.cout_pad)
+                cur ^= 1
+            else:
+                self._dw("model.%d.dw" % (i + 1), pp[cur], pp[cur ^ 1], dw, n, hh, ww)
+                self._gemm("model.%d.pw" % (i + 1), pp[cur ^ 1], c, pw, n, ho, wo, out=pp[cur], out_ld=pw.cout_pad)
             hh, ww, c = ho, wo, pw.cout
         assert (hh, ww) == (self.h, self.w) and c == 512
         feat = pp[cur]
@@ -261,11 +284,18 @@ class Plan:
         self._gemm("cpm.align", feat, 512, P.cpm_align, n, h, w, out=A, out_ld=nc)
         src = A
         for i, (dw, pw) in enumerate(P.cpm_trunk):
-            self._dw("cpm.trunk.%d.dw" % i, src, t0, dw, n, h, w)
             last = i == len(P.cpm_trunk) - 1
-            self._gemm("cpm.trunk.%d.pw" % i, t0, nc, pw, n, h, w, out=t1, out_ld=nc,
-                       residual=A if last else None, res_ld=nc)  # x + trunk(x) fused into the last epilogue
-            src = t1
+            res = A if last else None  # x + trunk(x) fused into the last epilogue
+            if self._fusable(dw, pw):
+                dst = t1 if src is t0 else t0
+                self._dwpw("cpm.trunk.%d.dwpw" % i, src, dw, pw, n, h, w, dst, nc, residual=res, res_ld=nc)
+            else:
+                mid = t1 if src is t0 else t0
+                dst = t0 if mid is t1 else t1
+                self._dw("cpm.trunk.%d.dw" % i, src, mid, dw, n, h, w)
+                self._gemm("cpm.trunk.%d.pw" % i, mid, nc, pw, n, h, w, out=dst, out_ld=nc, residual=res, res_ld=nc)
+            src = dst
+        t1, t0 = (src, t1 if src is t0 else t0)  # t1 := cpm trunk output, t0 := the free scratch buffer
         self._gemm("cpm.conv", t1, nc, P.cpm_conv, n, h, w, out=concat, out_ld=CONCAT_LD)
         # initial stage
         srcs = [(concat, CONCAT_LD), (t0, nc), (t1, nc)]

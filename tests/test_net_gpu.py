@@ -140,6 +140,56 @@ def test_depthwise_vs_torch(env, precision, shape):
 
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("shape", [
+    # (n, H, W, Cin, Cout, dil, dw_act, act, residual)
+    (1, 16, 8, 64, 128, 1, 1, 1, False),     # one exact tile, one K block (bf16)
+    (2, 23, 41, 128, 128, 1, 1, 1, False),   # ragged tiles
+    (1, 46, 82, 512, 512, 2, 1, 1, False),   # dilation 2, N = 512 as two MMAs, single accumulator stage
+    (1, 46, 82, 256, 512, 1, 1, 1, False),
+    (2, 13, 20, 128, 128, 1, 2, 2, True),    # Cpm trunk: ELU / ELU + residual
+    (1, 92, 164, 128, 128, 1, 1, 1, False),  # backbone model.3 grid
+    (3, 32, 57, 256, 256, 1, 1, 1, False),
+])
+def test_fused_dwpw_vs_torch(env, precision, shape):
+    """Fused depthwise 3x3 -> 1x1 GEMM (depthwise result only ever lives in the smem A operand)."""
+    torch, _lib, engine = env
+    n, H, W, Cin, Cout, dil, dw_act, act, use_res = shape
+    g = torch.Generator().manual_seed(hash(shape) % (2 ** 31))
+    tdtype = engine._PREC[precision][1]
+    x = torch.randn(n, Cin, H, W, generator=g)
+    wd = torch.randn(Cin, 1, 3, 3, generator=g) * 0.3
+    sd, bd = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g) * 0.1
+    wp = torch.randn(Cout, Cin, 1, 1, generator=g) * (1.0 / np.sqrt(Cin))
+    sp, bp = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g) * 0.1
+    res = torch.randn(n, Cout, H, W, generator=g) if use_res else None
+    actf = {0: lambda t: t, 1: torch.relu, 2: torch.nn.functional.elu}
+    xq = x.to(tdtype).float()
+    mid = torch.nn.functional.conv2d(xq, wd, None, 1, dil, dil, groups=Cin)
+    mid = actf[dw_act](mid * sd.view(1, -1, 1, 1) + bd.view(1, -1, 1, 1)).to(tdtype).float()  # stored in the plan dtype
+    ref = torch.nn.functional.conv2d(mid.double(), wp.to(tdtype).double()).float()
+    ref = actf[act](ref * sp.view(1, -1, 1, 1) + bp.view(1, -1, 1, 1))
+    if use_res:
+        ref = ref + res.to(tdtype).float()
+
+    gw = engine._GemmW(wp.cuda(), sp.cuda(), bp.cuda(), act, tdtype)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(tdtype).cuda()
+    w9c = wd.reshape(Cin, 9).t().contiguous().cuda()
+    sdd, bdd = sd.cuda(), bd.cuda()
+    out = torch.full((n, H, W, gw.cout_pad), 7.0, dtype=tdtype, device="cuda")
+    resd = res.permute(0, 2, 3, 1).contiguous().to(tdtype).cuda() if use_res else None
+    p = OnePlan(env, precision)
+    _lib.check(p.L.lwp_plan_add_dwpw(p.h, xd.data_ptr(), w9c.data_ptr(), sdd.data_ptr(), bdd.data_ptr(), dw_act, dil,
+                                     gw.w.data_ptr(), gw.scale.data_ptr(), gw.shift.data_ptr(), act,
+                                     resd.data_ptr() if use_res else None, Cout, out.data_ptr(), gw.cout_pad, n, H, W,
+                                     Cin, Cout), "add")
+    p.run()
+    got = out[..., :Cout].permute(0, 3, 1, 2).float().cpu()
+    p.close()
+    tol = 6e-3 if precision == "tf32" else 2.5e-2
+    assert _rel(got, ref) < tol * max(1.0, float(ref.abs().max())), _rel(got, ref)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
 def test_stem_vs_torch(env, precision):
     torch, _lib, engine = env
     g = torch.Generator().manual_seed(11)
