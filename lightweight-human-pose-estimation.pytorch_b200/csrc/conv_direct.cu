@@ -47,60 +47,85 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 
 // ------------------------------------------------------------------------------------------------
 // stem: NCHW fp32 [n][3][H][W] -> NHWC [n][H/2][W/2][32]; 3x3, stride 2, pad 1; BN folded; ReLU.
-// One thread = one output pixel x 16 output channels (two threads per pixel).
+// One thread = two horizontally adjacent output pixels x all 32 output channels: every weight pair read
+// from shared memory (LDS.128 = two pairs) feeds two packed FFMA2s, the 5 input columns the two pixels
+// share are loaded once.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 stem_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ scale,
             const float *__restrict__ shift, T *__restrict__ out, int n, int H, int W, int Ho, int Wo) {
-  __shared__ float s_w[27][32];  // [ci*9 + ky*3 + kx][co]
-  __shared__ float s_scale[32], s_shift[32];
+  __shared__ __align__(16) float s_w[27][32];  // [ci*9 + ky*3 + kx][co]
+  __shared__ __align__(16) float s_scale[32], s_shift[32];
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) {
     int co = i & 31, k = i >> 5;
     s_w[k][co] = w[co * 27 + k];
   }
   if (threadIdx.x < 32) { s_scale[threadIdx.x] = scale[threadIdx.x]; s_shift[threadIdx.x] = shift[threadIdx.x]; }
   __syncthreads();
-  const long long total = (long long)n * Ho * Wo * 2;
+  const int Wp = (Wo + 1) / 2;  // pixel pairs per output row
+  const long long total = (long long)n * Ho * Wp;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int half = (int)(idx & 1);
-    long long pix = idx >> 1;
-    const int xo = (int)(pix % Wo);
-    long long t = pix / Wo;
+    const int xp = (int)(idx % Wp);
+    long long t = idx / Wp;
     const int yo = (int)(t % Ho);
     const int img = (int)(t / Ho);
-    float acc[16];
+    const int xo = 2 * xp;                 // first of the two output pixels
+    const bool has2 = xo + 1 < Wo;
+    float2 acc[2][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[q][j] = make_float2(0.f, 0.f);
     const float *xb = x + (size_t)img * 3 * H * W;
+    const int xi0 = 2 * xo - 1;            // leftmost input column (pixel 0 taps xi0..xi0+2, pixel 1 taps xi0+2..xi0+4)
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int yi = 2 * yo - 1 + ky;
         if (yi < 0 || yi >= H) continue;
+        const float *row = xb + ((size_t)ci * H + yi) * W;
+        float v[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          const int xi = xi0 + c;
+          v[c] = (xi >= 0 && xi < W) ? __ldg(row + xi) : 0.f;
+        }
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int xi = 2 * xo - 1 + kx;
-          if (xi < 0 || xi >= W) continue;
-          const float v = __ldg(xb + ((size_t)ci * H + yi) * W + xi);
-          const float *wr = &s_w[ci * 9 + ky * 3 + kx][half * 16];
+          const float4 *wr = reinterpret_cast<const float4 *>(&s_w[ci * 9 + ky * 3 + kx][0]);
+          const float2 a = make_float2(v[kx], v[kx]), b = make_float2(v[kx + 2], v[kx + 2]);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+          for (int j = 0; j < 8; ++j) {
+            const float4 w4 = wr[j];
+            acc[0][2 * j] = __ffma2_rn(a, make_float2(w4.x, w4.y), acc[0][2 * j]);
+            acc[0][2 * j + 1] = __ffma2_rn(a, make_float2(w4.z, w4.w), acc[0][2 * j + 1]);
+            acc[1][2 * j] = __ffma2_rn(b, make_float2(w4.x, w4.y), acc[1][2 * j]);
+            acc[1][2 * j + 1] = __ffma2_rn(b, make_float2(w4.z, w4.w), acc[1][2 * j + 1]);
+          }
         }
       }
     }
-    T *op = out + (size_t)pix * 32 + half * 16;
-    float o[8];
+    const size_t pix = ((size_t)img * Ho + yo) * Wo + xo;
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
+    for (int q = 0; q < 2; ++q) {
+      if (q == 1 && !has2) break;
+      T *op = out + (pix + q) * 32;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = half * 16 + g * 8 + j;
-        o[j] = fmaxf(fmaf(acc[g * 8 + j], s_scale[c], s_shift[c]), 0.f);
+      for (int g = 0; g < 4; ++g) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = g * 8 + 2 * j;
+          const float2 r = __ffma2_rn(acc[q][g * 4 + j], make_float2(s_scale[c], s_scale[c + 1]),
+                                      make_float2(s_shift[c], s_shift[c + 1]));
+          o[2 * j] = fmaxf(r.x, 0.f);
+          o[2 * j + 1] = fmaxf(r.y, 0.f);
+        }
+        Vec8<T>::store(op + g * 8, o);
       }
-      Vec8<T>::store(op + g * 8, o);
     }
   }
 }
@@ -348,10 +373,10 @@ static int grid_for(long long total, int block, int per_sm) {
 int stem_launch(bool f32, const float *x, const float *w, const float *scale, const float *shift, void *out, int n,
                 int H, int W, cudaStream_t st) {
   const int Ho = H / 2, Wo = W / 2;
-  long long total = (long long)n * Ho * Wo * 2;
-  int grid = grid_for(total, 256, 8);
-  if (f32) stem_kernel<float><<<grid, 256, 0, st>>>(x, w, scale, shift, (float *)out, n, H, W, Ho, Wo);
-  else stem_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, w, scale, shift, (__nv_bfloat16 *)out, n, H, W, Ho, Wo);
+  long long total = (long long)n * Ho * ((Wo + 1) / 2);
+  int grid = grid_for(total, 128, 16);
+  if (f32) stem_kernel<float><<<grid, 128, 0, st>>>(x, w, scale, shift, (float *)out, n, H, W, Ho, Wo);
+  else stem_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(x, w, scale, shift, (__nv_bfloat16 *)out, n, H, W, Ho, Wo);
   LWP_LAUNCH_CHECK();
   return LWP_OK;
 }

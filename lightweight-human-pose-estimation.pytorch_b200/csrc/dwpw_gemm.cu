@@ -71,6 +71,77 @@ __device__ __forceinline__ void ldg4pairs(const float *p, float2 (&v)[4]) {
   v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
 }
 
+// Depthwise 3x3 of one thread's 8 channels x 4 consecutive output columns of one tile row, for one K block:
+// reads the smem halo tile through a register window, accumulates in packed fp32, applies the folded BN +
+// activation and writes the four 16-byte (bf16) / 32-byte (fp32) pieces into the swizzled A tile.
+// All addressing is 32-bit; the activation is a compile-time choice.
+template <bool kTf32, int D, int ACT>
+__device__ __forceinline__ void dw_block(const uint8_t *in0, int row_bytes, const float *w0, int cin, const float *sc0,
+                                         const float *sh0, uint8_t *abuf, int r0, int cv) {
+  constexpr int TWT = 4, NCOL = (TWT - 1) + 2 * D + 1;
+  float2 acc[TWT][4];
+#pragma unroll
+  for (int a = 0; a < TWT; ++a)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[a][j] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    float2 wk[3][4];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) ldg4pairs(w0 + (ky * 3 + kx) * cin, wk[kx]);
+    const uint8_t *rowp = in0 + ky * D * row_bytes;
+#pragma unroll
+    for (int ci = 0; ci < NCOL; ++ci) {
+      float2 v[4];
+      TileIn<kTf32>::load(rowp + ci * kKBlockBytes, v);
+#pragma unroll
+      for (int a = 0; a < TWT; ++a) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          if (a + kx * D == ci) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[a][j] = __ffma2_rn(v[j], wk[kx][j], acc[a][j]);
+          }
+        }
+      }
+    }
+  }
+  float2 sc[4], sh[4];
+  ldg4pairs(sc0, sc);
+  ldg4pairs(sh0, sh);
+#pragma unroll
+  for (int a = 0; a < TWT; ++a) {
+    const int r = r0 + a;  // row of the A tile == pixel of the tile
+    float2 y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      y[j] = __ffma2_rn(acc[a][j], sc[j], sh[j]);
+      if constexpr (ACT == LWP_ACT_ELU) {
+        y[j].x = y[j].x > 0.f ? y[j].x : __expf(y[j].x) - 1.f;
+        y[j].y = y[j].y > 0.f ? y[j].y : __expf(y[j].y) - 1.f;
+      } else if constexpr (ACT == LWP_ACT_RELU && kTf32) {
+        y[j].x = fmaxf(y[j].x, 0.f);
+        y[j].y = fmaxf(y[j].y, 0.f);
+      }
+    }
+    uint8_t *rowa = abuf + r * kKBlockBytes;
+    if constexpr (kTf32) {
+      *reinterpret_cast<float4 *>(rowa + (((2 * cv) ^ (r & 7)) << 4)) = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
+      *reinterpret_cast<float4 *>(rowa + (((2 * cv + 1) ^ (r & 7)) << 4)) = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
+    } else {
+      uint4 pk;
+      __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+      const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = __float22bfloat162_rn(y[j]);
+        if constexpr (ACT == LWP_ACT_RELU) h[j] = __hmax2(h[j], zero2);  // ReLU after rounding == rounding after ReLU
+      }
+      *reinterpret_cast<uint4 *>(rowa + ((cv ^ (r & 7)) << 4)) = pk;
+    }
+  }
+}
+
 template <bool kTf32, int D>
 __global__ void __launch_bounds__(kDwpwThreads, 1)
 dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmB,
@@ -194,7 +265,7 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     if (lane == 0) ptx::bulk_wait<0>();
   } else {
     // ===================== depthwise producers of the A operand (8 warps) =====================
-    constexpr int TWT = 4, NCOL = (TWT - 1) + 2 * D + 1;
+    constexpr int TWT = 4;
     constexpr int ES = kTf32 ? 4 : 2;
     const int dwtid = threadIdx.x - kDwWarp0 * 32;
     const int cvn = p.kb_ch / 8;                       // 8-channel vectors per pixel in a K block
@@ -203,6 +274,9 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     const int cv = dwtid % cvn, pt = dwtid / cvn;
     const int xgroups = p.tile_w / TWT;
     const int xg = pt % xgroups, ty = pt / xgroups;
+    const int row_bytes = p.iw * kKBlockBytes;
+    const int in_off0 = (ty * p.iw + xg * TWT) * kKBlockBytes + cv * 8 * ES;  // this thread's window origin in a stage
+    const int r0 = ty * p.tile_w + xg * TWT;
     int is = 0, as = 0;
     uint32_t iph = 0, aph = 0;
     bool ok = true;
@@ -212,59 +286,33 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
           ok = false; atomicExch(p.err_flag, 16); break;
         }
         if (active) {
-          const uint8_t *sbuf = smem + L.in_off + (size_t)is * p.in_stage_bytes;
-          uint8_t *abuf = smem + L.a_off + (size_t)as * kATileBytes;
+          const uint8_t *sbuf = smem + L.in_off + is * (int)p.in_stage_bytes;
+          uint8_t *abuf = smem + L.a_off + as * kATileBytes;
           const int c0 = kb * p.kb_ch + cv * 8;
-          float2 acc[TWT][4];
+          if (c0 < p.cin) {
+            const uint8_t *in0 = sbuf + in_off0;
+            if (p.dw_act == LWP_ACT_RELU)
+              dw_block<kTf32, D, LWP_ACT_RELU>(in0, row_bytes, p.dw_w9c + c0, p.cin, p.dw_scale + c0, p.dw_shift + c0, abuf,
+                                               r0, cv);
+            else if (p.dw_act == LWP_ACT_ELU)
+              dw_block<kTf32, D, LWP_ACT_ELU>(in0, row_bytes, p.dw_w9c + c0, p.cin, p.dw_scale + c0, p.dw_shift + c0, abuf,
+                                              r0, cv);
+            else
+              dw_block<kTf32, D, LWP_ACT_NONE>(in0, row_bytes, p.dw_w9c + c0, p.cin, p.dw_scale + c0, p.dw_shift + c0, abuf,
+                                               r0, cv);
+          } else {
+            // channels past Cin (a layer thinner than one K block): the GEMM weights there are zero-filled by TMA;
+            // write zeros so no NaN garbage can reach the tensor core
 #pragma unroll
-          for (int a = 0; a < TWT; ++a)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[a][j] = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            float2 wk[3][4];
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) ldg4pairs(p.dw_w9c + (size_t)(ky * 3 + kx) * p.cin + c0, wk[kx]);
-            const uint8_t *rowp = sbuf + ((size_t)(ty + ky * D) * p.iw + (size_t)xg * TWT) * kKBlockBytes + cv * 8 * ES;
-#pragma unroll
-            for (int ci = 0; ci < NCOL; ++ci) {
-              float2 v[4];
-              TileIn<kTf32>::load(rowp + (size_t)ci * kKBlockBytes, v);
-#pragma unroll
-              for (int a = 0; a < TWT; ++a) {
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                  if (a + kx * D == ci) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[a][j] = __ffma2_rn(v[j], wk[kx][j], acc[a][j]);
-                  }
-                }
+            for (int a = 0; a < 4; ++a) {
+              const int r = r0 + a;
+              uint8_t *rowa = abuf + r * kKBlockBytes;
+              if constexpr (kTf32) {
+                *reinterpret_cast<float4 *>(rowa + (((2 * cv) ^ (r & 7)) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4 *>(rowa + (((2 * cv + 1) ^ (r & 7)) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+              } else {
+                *reinterpret_cast<uint4 *>(rowa + ((cv ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
               }
-            }
-          }
-          float2 sc[4], sh[4];
-          ldg4pairs(p.dw_scale + c0, sc);
-          ldg4pairs(p.dw_shift + c0, sh);
-#pragma unroll
-          for (int a = 0; a < TWT; ++a) {
-            const int r = ty * p.tile_w + xg * TWT + a;   // row of the A tile == pixel of the tile
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 y2 = __ffma2_rn(acc[a][j], sc[j], sh[j]);
-              o[2 * j] = dw_act(y2.x, p.dw_act);
-              o[2 * j + 1] = dw_act(y2.y, p.dw_act);
-            }
-            uint8_t *rowa = abuf + (size_t)r * kKBlockBytes;
-            if constexpr (kTf32) {
-              *reinterpret_cast<float4 *>(rowa + (((2 * cv) ^ (r & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
-              *reinterpret_cast<float4 *>(rowa + (((2 * cv + 1) ^ (r & 7)) << 4)) = make_float4(o[4], o[5], o[6], o[7]);
-            } else {
-              uint4 pk;
-              __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
-              *reinterpret_cast<uint4 *>(rowa + ((cv ^ (r & 7)) << 4)) = pk;
             }
           }
         }

@@ -278,7 +278,7 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
   const int es = tf32 ? 4 : 2;
   const int kb_ch = kKBlockBytes / es;
   const int cout_pad = (Cout + 63) / 64 * 64;
-  LWP_REQUIRE(Cin % kb_ch == 0, "lwp_plan_add_dwpw: Cin must be a multiple of %d", kb_ch);
+  LWP_REQUIRE(Cin % 8 == 0 && (Cin % kb_ch == 0 || Cin < kb_ch), "lwp_plan_add_dwpw: Cin must be a multiple of %d (or a multiple of 8 below it)", kb_ch);
   LWP_REQUIRE(cout_pad <= 512 && (512 % cout_pad == 0), "lwp_plan_add_dwpw: Cout (padded %d) must divide 512", cout_pad);
   LWP_REQUIRE(out_ld % 8 == 0 && out_ld >= Cout && ((uintptr_t)out % 16) == 0 && ((uintptr_t)in % 16) == 0 &&
                   ((uintptr_t)w % 16) == 0,
@@ -289,7 +289,7 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
   Op op;
   op.kind = OP_DWPW;
   DwpwParams &f = op.fp;
-  f.H = H; f.W = W; f.NIMG = n; f.dil = dilation; f.cin = Cin; f.kb_ch = kb_ch; f.kblocks = Cin / kb_ch;
+  f.H = H; f.W = W; f.NIMG = n; f.dil = dilation; f.cin = Cin; f.kb_ch = kb_ch; f.kblocks = (Cin + kb_ch - 1) / kb_ch;
   f.cout_pad = cout_pad;
   const int chunk_cols = kKBlockBytes / es;
   int n_store = cout_pad;

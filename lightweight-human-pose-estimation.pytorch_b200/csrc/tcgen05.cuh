@@ -72,6 +72,14 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const void *tmap, ui
       : "memory");
 }
 
+// L2 prefetch of a 4-D box (no shared memory involved): hides DRAM latency behind the smem ring
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void *tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // smem -> global tensor store (OOB coordinates are clipped by the hardware)
 __device__ __forceinline__ void tma_store_4d(const void *tmap, const void *smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(

@@ -223,21 +223,27 @@ class Plan:
         """Depthwise (stride 1) + pointwise pair that the fused tcgen05 kernel can take."""
         kb_ch = 64 if self.tdtype == torch.bfloat16 else 32
         return (self.fuse_dwpw and d.stride == 1 and d.dilation in (1, 2) and g.taps == 1 and d.c == g.cin
-                and d.c % kb_ch == 0 and g.cout_pad <= 512 and 512 % g.cout_pad == 0)
+                and (d.c % kb_ch == 0 or d.c < kb_ch) and d.c % 8 == 0 and g.cout_pad <= 512
+                and 512 % g.cout_pad == 0)
 
     def _dwpw(self, name, src, d, g, n, H, W, out, out_ld, residual=None, res_ld=0):
+        """Record the fused block; returns False (nothing recorded) when its tiles do not fit in shared memory."""
         es = 2 if self.tdtype == torch.bfloat16 else 4
-        _lib.check(self.lib.lwp_plan_add_dwpw(
+        rc = self.lib.lwp_plan_add_dwpw(
             self.handle, src.data_ptr(), d.w.data_ptr(), d.scale.data_ptr(), d.shift.data_ptr(), d.act, d.dilation,
             g.w.data_ptr(), g.scale.data_ptr(), g.shift.data_ptr(), g.act,
             residual.data_ptr() if residual is not None else None, res_ld, out.data_ptr(), out_ld, n, H, W, d.c,
-            g.cout), "lwp_plan_add_dwpw(%s)" % name)
+            g.cout)
+        if rc == 3:  # LWP_ECAP: fall back to the two-kernel form of this block
+            return False
+        _lib.check(rc, "lwp_plan_add_dwpw(%s)" % name)
         self.op_names.append(name)
         px = n * H * W
         nbytes = px * (d.c + g.cout) * es + d.c * g.cout * es + 9 * d.c * 4
         if residual is not None:
             nbytes += px * g.cout * es
         self.op_meta.append(dict(kind="dwpw", flops=2.0 * px * d.c * (g.cout + 9), bytes=float(nbytes)))
+        return True
 
     # -- the layer walk -----------------------------------------------------------------------
     def _build(self, P, n_stages_out, num_heatmaps, num_pafs):
@@ -261,8 +267,9 @@ class Plan:
         hh, ww, c, cur = H // 2, W // 2, 32, 0
         for i, (dw, pw) in enumerate(P.backbone):
             ho, wo = (hh - 1) // dw.stride + 1, (ww - 1) // dw.stride + 1
-            if self._fusable(dw, pw):   # depthwise result goes straight into the GEMM's smem A operand
-                self._dwpw("model.%d.dwpw" % (i + 1), pp[cur], dw, pw, n, hh, ww, pp[cur ^ 1], pw.cout_pad)
+            # fused: the depthwise result goes straight into the GEMM's smem A operand
+            if self._fusable(dw, pw) and self._dwpw("model.%d.dwpw" % (i + 1), pp[cur], dw, pw, n, hh, ww, pp[cur ^ 1],
+                                                    pw.cout_pad):
                 cur ^= 1
             else:
                 self._dw("model.%d.dw" % (i + 1), pp[cur], pp[cur ^ 1], dw, n, hh, ww)
@@ -286,9 +293,10 @@ class Plan:
         for i, (dw, pw) in enumerate(P.cpm_trunk):
             last = i == len(P.cpm_trunk) - 1
             res = A if last else None  # x + trunk(x) fused into the last epilogue
-            if self._fusable(dw, pw):
-                dst = t1 if src is t0 else t0
-                self._dwpw("cpm.trunk.%d.dwpw" % i, src, dw, pw, n, h, w, dst, nc, residual=res, res_ld=nc)
+            dst = t1 if src is t0 else t0
+            if self._fusable(dw, pw) and self._dwpw("cpm.trunk.%d.dwpw" % i, src, dw, pw, n, h, w, dst, nc,
+                                                    residual=res, res_ld=nc):
+                pass
             else:
                 mid = t1 if src is t0 else t0
                 dst = t0 if mid is t1 else t1

@@ -144,11 +144,13 @@ def test_depthwise_vs_torch(env, precision, shape):
     # (n, H, W, Cin, Cout, dil, dw_act, act, residual)
     (1, 16, 8, 64, 128, 1, 1, 1, False),     # one exact tile, one K block (bf16)
     (2, 23, 41, 128, 128, 1, 1, 1, False),   # ragged tiles
-    (1, 46, 82, 512, 512, 2, 1, 1, False),   # dilation 2, N = 512 as two MMAs, single accumulator stage
+    (1, 46, 82, 512, 512, 1, 1, 1, False),   # N = 512 as two MMAs, single accumulator stage
+    (1, 46, 82, 256, 256, 2, 1, 1, False),   # dilation 2
     (1, 46, 82, 256, 512, 1, 1, 1, False),
     (2, 13, 20, 128, 128, 1, 2, 2, True),    # Cpm trunk: ELU / ELU + residual
     (1, 92, 164, 128, 128, 1, 1, 1, False),  # backbone model.3 grid
     (3, 32, 57, 256, 256, 1, 1, 1, False),
+    (1, 40, 56, 32, 64, 1, 1, 1, False),     # Cin below one bf16 K block (model.1): zero-filled channels
 ])
 def test_fused_dwpw_vs_torch(env, precision, shape):
     """Fused depthwise 3x3 -> 1x1 GEMM (depthwise result only ever lives in the smem A operand)."""
