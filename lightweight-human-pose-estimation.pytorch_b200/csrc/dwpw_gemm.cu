@@ -194,12 +194,13 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
           ptx::tma_load_4d(smem + L.in_off + (size_t)is * p.in_stage_bytes, &tmIn, &in_full[is], kb * p.kb_ch, x0 - D,
                            y0 - D, img);
           if (++is == p.in_stages) { is = 0; iph ^= 1u; }
-          if (!ptx::mbar_wait(&b_empty[bs], bph ^ 1u)) { ok = false; atomicExch(p.err_flag, 12); break; }
-          ptx::mbar_arrive_expect_tx(&b_full[bs], p.b_stage_bytes);
-          for (int h = 0; h < p.n_mma; ++h)
-            ptx::tma_load_2d(smem + L.b_off + (size_t)bs * p.b_stage_bytes + (size_t)h * p.n_per_mma * kKBlockBytes, &tmB,
-                             &b_full[bs], kb * p.kb_ch, h * p.n_per_mma);
-          if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+          for (int h = 0; h < p.n_mma && ok; ++h) {  // the weights ring works in halves of N (<= 256 rows each)
+            if (!ptx::mbar_wait(&b_empty[bs], bph ^ 1u)) { ok = false; atomicExch(p.err_flag, 12); break; }
+            ptx::mbar_arrive_expect_tx(&b_full[bs], p.b_stage_bytes);
+            ptx::tma_load_2d(smem + L.b_off + (size_t)bs * p.b_stage_bytes, &tmB, &b_full[bs], kb * p.kb_ch,
+                             h * p.n_per_mma);
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+          }
         }
       }
     }
@@ -214,23 +215,24 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.cout_pad);
         for (int kb = 0; kb < p.kblocks; ++kb) {
-          if (!ptx::mbar_wait(&a_full[as], aph) || !ptx::mbar_wait(&b_full[bs], bph)) {
-            ok = false; atomicExch(p.err_flag, 14); break;
-          }
-          ptx::tc_fence_after();
+          if (!ptx::mbar_wait(&a_full[as], aph)) { ok = false; atomicExch(p.err_flag, 14); break; }
           const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(smem + L.a_off + (size_t)as * kATileBytes));
-          const uint32_t sb = ptx::smem_u32(smem + L.b_off + (size_t)bs * p.b_stage_bytes);
           for (int h = 0; h < p.n_mma; ++h) {
-            const uint64_t db = ptx::umma_desc_k_sw128(sb + (uint32_t)(h * p.n_per_mma * kKBlockBytes));
+            if (!ptx::mbar_wait(&b_full[bs], bph)) { ok = false; atomicExch(p.err_flag, 14); break; }
+            ptx::tc_fence_after();
+            if (!(p.debug & 4)) {
+              const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem + L.b_off + (size_t)bs * p.b_stage_bytes));
 #pragma unroll
-            for (int k = 0; k < kKBlockBytes / 32; ++k)
-              ptx::umma<kTf32>(d_tmem + (uint32_t)(h * p.n_per_mma), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
-                               p.idesc, (uint32_t)((kb | k) != 0));
+              for (int k = 0; k < kKBlockBytes / 32; ++k)
+                ptx::umma<kTf32>(d_tmem + (uint32_t)(h * p.n_per_mma), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
+                                 p.idesc, (uint32_t)((kb | k) != 0));
+            }
+            ptx::umma_commit(&b_empty[bs]);
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
           }
+          if (!ok) break;
           ptx::umma_commit(&a_empty[as]);
-          ptx::umma_commit(&b_empty[bs]);
           if (++as == p.a_stages) { as = 0; aph ^= 1u; }
-          if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
         }
         if (!ok) break;
         ptx::umma_commit(&tfull[acc]);
@@ -254,6 +256,7 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
       const bool valid = y < p.H && x < p.W;
       const size_t pix = ((size_t)img * p.H + y) * (size_t)p.W + x;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.cout_pad);
+      if (!(p.debug & 2))
       staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)q * p.staging_bufs * kStageOutBytes, p.staging_bufs,
                                   sbuf_idx, t_row, 0, p.cout_pad, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld,
                                   valid, pix, lane, x0 + (q * 32) % p.tile_w, y0 + (q * 32) / p.tile_w, img);
@@ -285,7 +288,7 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         if (!ptx::mbar_wait(&in_full[is], iph) || !ptx::mbar_wait(&a_empty[as], aph ^ 1u)) {
           ok = false; atomicExch(p.err_flag, 16); break;
         }
-        if (active) {
+        if (active && !(p.debug & 1)) {
           const uint8_t *sbuf = smem + L.in_off + is * (int)p.in_stage_bytes;
           uint8_t *abuf = smem + L.a_off + as * kATileBytes;
           const int c0 = kb * p.kb_ch + cv * 8;

@@ -24,6 +24,7 @@ struct DwpwParams {
   const void *residual;
   int res_ld;
   int *err_flag;
+  int debug;                      // bit 0: skip depthwise math, bit 1: skip epilogue, bit 2: skip MMA (timing experiments only)
 };
 
 size_t dwpw_smem_bytes(const DwpwParams &p);

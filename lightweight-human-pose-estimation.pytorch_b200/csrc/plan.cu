@@ -305,6 +305,7 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
   f.dw_act = dw_act; f.act = act;
   f.dw_w9c = dw_w; f.dw_scale = dw_scale; f.dw_shift = dw_shift; f.scale = scale; f.shift = shift;
   f.residual = residual; f.res_ld = res_ld; f.err_flag = p->err_flag;
+  f.debug = getenv("LWP_DEBUG_DWPW") ? atoi(getenv("LWP_DEBUG_DWPW")) : 0;
   // tile: rectangle of 128 pixels, width a multiple of 4 (a depthwise thread owns 4 consecutive columns)
   long long best = -1;
   for (int th = 1; th <= 32; th <<= 1) {
@@ -319,15 +320,16 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
   f.tiles_x = ceil_div(W, f.tile_w); f.tiles_y = ceil_div(H, f.tile_h);
   f.m_tiles = n * f.tiles_x * f.tiles_y;
   f.in_stage_bytes = (uint32_t)(f.iw * f.ih * kKBlockBytes);
-  f.b_stage_bytes = (uint32_t)(cout_pad * kKBlockBytes);
+  f.b_stage_bytes = (uint32_t)(f.n_per_mma * kKBlockBytes);  // the weights ring works in halves of N when N > 256
   // shared-memory budget: prefer deep B / A rings, then a second input stage, then double-buffered staging
-  f.b_stages = 2; f.a_stages = 2; f.in_stages = 1; f.staging_bufs = 1;
+  f.b_stages = f.n_mma + 1; f.a_stages = 2; f.in_stages = 1; f.staging_bufs = 1;
   const size_t limit = 232448;
   { DwpwParams t = f; t.in_stages = 2; if (dwpw_smem_bytes(t) <= limit) f = t; }
   { DwpwParams t = f; t.staging_bufs = 2; if (dwpw_smem_bytes(t) <= limit) f = t; }
+  { DwpwParams t = f; t.b_stages = f.b_stages + 1; if (t.b_stages <= 4 && dwpw_smem_bytes(t) <= limit) f = t; }
   { DwpwParams t = f; t.a_stages = 3; if (dwpw_smem_bytes(t) <= limit) f = t; }
-  { DwpwParams t = f; t.b_stages = 3; if (dwpw_smem_bytes(t) <= limit) f = t; }
   { DwpwParams t = f; t.in_stages = 3; if (dwpw_smem_bytes(t) <= limit) f = t; }
+  { DwpwParams t = f; t.b_stages = f.b_stages + 1; if (t.b_stages <= 4 && dwpw_smem_bytes(t) <= limit) f = t; }
   if (dwpw_smem_bytes(f) > limit) { set_error("lwp_plan_add_dwpw: shared memory budget exceeded"); return LWP_ECAP; }
   op.grid = f.m_tiles < num_sms() ? f.m_tiles : num_sms();
 
