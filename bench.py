@@ -37,6 +37,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="frames per pipeline chunk (0 = whole batch)")
+    ap.add_argument("--no-overlap-postproc", action="store_true", help="post-processing on the network's stream")
     ap.add_argument("--unfused-postproc", action="store_true", help="materialise the up-sampled maps like the reference")
     return ap.parse_args()
 
@@ -223,7 +224,8 @@ def main():
     inject = torch.from_numpy(inject_h).to(dev)
     pipe = PosePipeline(net, args.batch, HEIGHT, WIDTH, precision=args.precision, demo=True,
                         heads_hook=lambda heads, lo: heads.add_(inject[lo:lo + heads.shape[0]]),
-                        fused=not args.unfused_postproc, chunk=args.chunk or None)
+                        fused=not args.unfused_postproc, chunk=args.chunk or None,
+                        overlap_postproc=not args.no_overlap_postproc)
     x_host = synth.synthetic_net_input(args.batch, HEIGHT, WIDTH, seed=1 + rank).pin_memory()
     x_dev = x_host.to(dev)
 
@@ -242,6 +244,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         pipe.run_device(x_dev)
+    pipe.join()   # post-processing runs on its own stream: the timed region ends when the last step's grouping ends
     e1.record()
     barrier()
     ms = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev) / args.steps

@@ -259,7 +259,7 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
       if (!(p.debug & 2))
       staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)q * p.staging_bufs * kStageOutBytes, p.staging_bufs,
                                   sbuf_idx, t_row, 0, p.cout_pad, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld,
-                                  valid, pix, lane, x0 + (q * 32) % p.tile_w, y0 + (q * 32) / p.tile_w, img);
+                                  valid, pix, lane, x0 + (q * 32) % p.tile_w, y0 + (q * 32) / p.tile_w, img, p.debug >> 3);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);

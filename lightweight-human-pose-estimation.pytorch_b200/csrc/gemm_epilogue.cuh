@@ -89,7 +89,7 @@ __device__ __forceinline__ void staged_epilogue_tile(const CUtensorMap *tmC, uin
                                                      uint32_t t_row, int n0, int block_n, int n_store,
                                                      const float *s_scale, const float *s_shift, int act,
                                                      const void *residual, int res_ld, bool valid, size_t pix, int lane,
-                                                     int store_x, int store_y, int img) {
+                                                     int store_x, int store_y, int img, int dbg = 0) {
   constexpr int kUnitsPerChunk = kTf32 ? 1 : 2;   // 128 output bytes = 32 fp32 / 64 bf16 columns
   const bool fast_relu = act == LWP_ACT_RELU && residual == nullptr;
   const bool res_ok = residual != nullptr && valid;
@@ -110,12 +110,13 @@ __device__ __forceinline__ void staged_epilogue_tile(const CUtensorMap *tmC, uin
       }
       __syncwarp();
     }
-    epilogue_unit<kTf32>(r, sbuf, lane, in_chunk * 32, n0 + u * 32, s_scale, s_shift, act, fast_relu, residual, res_ld,
-                         res_ok, pix);
+    if (!(dbg & 2))
+      epilogue_unit<kTf32>(r, sbuf, lane, in_chunk * 32, n0 + u * 32, s_scale, s_shift, act, fast_relu, residual, res_ld,
+                           res_ok, pix);
     if (in_chunk == kUnitsPerChunk - 1) {  // chunk complete -> one TMA tensor store of the warp's 32 x 128-byte box
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !(dbg & 1)) {
         ptx::tma_store_4d(tmC, sbuf, n0 + (u / kUnitsPerChunk) * (kUnitsPerChunk * 32), store_x, store_y, img);
         ptx::bulk_commit();
       }

@@ -61,19 +61,36 @@ class _Chunk:
         self.n_poses = torch.empty((n,), dtype=torch.int32, device=dev)
         self.ws_extract = torch.empty((L.lwp_extract_workspace_bytes(n, 18, cc),), dtype=torch.uint8, device=dev)
         self.ws_group = torch.empty((L.lwp_group_workspace_bytes(n, ck, cn, cp),), dtype=torch.uint8, device=dev)
+        # the post-processing runs on its own stream on a private copy of the heads, so the network of the next
+        # batch (which overwrites the plan's head buffer) can start while this batch is still being grouped
+        self.heads_pp = torch.empty((n, pipe.h, pipe.w, HEAD_LD), dtype=torch.float32, device=dev)
+        self.net_done = torch.cuda.Event()
+        self.pp_done = torch.cuda.Event()
 
     @property
     def heads(self):
         return self.plan.heads_f32[-1].view(self.n, self.pipe.h, self.pipe.w, HEAD_LD)
 
     def enqueue(self, x_dev):
-        """One pass of the hot path for this chunk on the current stream."""
+        """One pass of the hot path for this chunk: network on the current stream, post-processing on the
+        pipeline's post-processing stream (ordered after it by events)."""
         pipe = self.pipe
+        cur = torch.cuda.current_stream()
         self.plan.run_compute(x_dev)
         heads = self.heads
         if pipe.heads_hook is not None:
             pipe.heads_hook(heads, self.lo)
-        self.enqueue_postproc(heads)
+        if not pipe.overlap_postproc:
+            self.enqueue_postproc(heads)
+            self.pp_done.record(cur)
+            return
+        cur.wait_event(self.pp_done)          # the previous batch's post-processing has finished reading heads_pp
+        self.heads_pp.copy_(heads)
+        self.net_done.record(cur)
+        with torch.cuda.stream(pipe.pp_stream):
+            pipe.pp_stream.wait_event(self.net_done)
+            self.enqueue_postproc(self.heads_pp)
+            self.pp_done.record(pipe.pp_stream)
 
     def enqueue_postproc(self, heads, stage=None):
         pipe = self.pipe
@@ -114,6 +131,7 @@ class _Slot:
         self.h_kpt_start = torch.empty((b, 19), dtype=torch.int32, **pin)
         self.h_overflow = torch.empty((b,), dtype=torch.int32, **pin)
         self.copied = torch.cuda.Event()   # H2D of this slot's input finished
+        self.consumed = torch.cuda.Event() # the network has finished reading x_dev
         self.done = torch.cuda.Event()     # compute + D2H of this slot finished
         self.busy = False
 
@@ -132,7 +150,7 @@ class PosePipeline:
 
     def __init__(self, net, batch, height, width, precision="bf16", upsample_ratio=4, demo=True,
                  min_paf_score=0.05, cap_kpts=128, cap_candidates=2048, cap_poses=256, cap_connections=2048,
-                 heads_hook=None, fused=True, chunk=None, depth=2):
+                 heads_hook=None, fused=True, chunk=None, depth=2, overlap_postproc=True):
         _lib.require_cuda()
         self.net, self.precision = net, precision
         self.n, self.H, self.W = batch, height, width
@@ -143,6 +161,8 @@ class PosePipeline:
         # fused: peaks / PAF samples are computed straight from the stride-8 heads (no up-sampled maps in HBM);
         # needs an up-sampling factor >= 3, otherwise the maps are materialised like the reference does
         self.fused = bool(fused) and upsample_ratio >= 3
+        # post-processing of batch i on a second stream, overlapping the network of batch i+1
+        self.overlap_postproc = bool(overlap_postproc)
         self.device = net.engine().device
         self.h, self.w = height // 8, width // 8
         self.Hu, self.Wu = self.h * upsample_ratio, self.w * upsample_ratio
@@ -158,6 +178,7 @@ class PosePipeline:
             self.slots = [_Slot(self) for _ in range(max(1, int(depth)))]
             self.copy_stream = torch.cuda.Stream(device=self.device)
             self.stream = torch.cuda.Stream(device=self.device)
+            self.pp_stream = torch.cuda.Stream(device=self.device)
         self._next, self._pending = 0, []
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0].tables())
         self.h2d_bytes = batch * 3 * height * width * 4
@@ -166,6 +187,13 @@ class PosePipeline:
     def heads(self):
         """float32 [n, h, w, 64]: last stage's 19 heat-map + 38 PAF channels (+7 zero) at stride 8 (a copy)."""
         return torch.cat([c.heads for c in self.chunks], 0)
+
+    def join(self):
+        """Make the current stream wait for every enqueued post-processing (call before timing / reading results
+        produced by run_device)."""
+        cur = torch.cuda.current_stream()
+        for c in self.chunks:
+            cur.wait_event(c.pp_done)
 
     @property
     def n_poses(self):
@@ -181,8 +209,9 @@ class PosePipeline:
         return sum(c.plan.num_compute_ops + (0 if self.fused else 2) + 3 + 3 for c in self.chunks)
 
     def run_device(self, x_dev):
-        """Hot path on a device-resident batch (no host traffic) on the current stream; results stay on the
-        device (self.pose_entries / self.n_poses / chunk.kb)."""
+        """Hot path on a device-resident batch (no host traffic): network on the current stream, post-processing
+        on the post-processing stream (successive calls overlap); results stay on the device
+        (self.pose_entries / self.n_poses / chunk.kb).  Call join() (or synchronise the device) before reading."""
         with torch.cuda.device(self.device):
             for c in self.chunks:
                 c.enqueue(x_dev[c.lo:c.lo + c.n])
@@ -199,22 +228,27 @@ class PosePipeline:
                 slot.copied.record(torch.cuda.current_stream())
             else:
                 with torch.cuda.stream(self.copy_stream):
-                    self.copy_stream.wait_event(slot.done)   # the kernels that read this buffer last are finished
+                    self.copy_stream.wait_event(slot.consumed)   # the kernels that read this buffer last are finished
                     slot.x_dev.copy_(frames, non_blocking=True)
                     slot.copied.record(self.copy_stream)
                 x = slot.x_dev
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(slot.copied)
                 for c in self.chunks:
+                    c.enqueue(x[c.lo:c.lo + c.n])
+                slot.consumed.record(self.stream)       # the network has read this slot's input buffer
+            tail = self.pp_stream if self.overlap_postproc else self.stream
+            with torch.cuda.stream(tail):
+                for c in self.chunks:
                     sl = slice(c.lo, c.lo + c.n)
-                    c.enqueue(x[sl])
+                    tail.wait_event(c.pp_done)
                     slot.h_pose_entries[sl].copy_(c.pose_entries, non_blocking=True)
                     slot.h_n_poses[sl].copy_(c.n_poses, non_blocking=True)
                     slot.h_kpts[sl].copy_(c.kb.kpts, non_blocking=True)
                     slot.h_counts[sl].copy_(c.kb.counts, non_blocking=True)
                     slot.h_kpt_start[sl].copy_(c.kb.kpt_start, non_blocking=True)
                     slot.h_overflow[sl].copy_(c.kb.overflow, non_blocking=True)
-                slot.done.record(self.stream)
+                slot.done.record(tail)
         self._pending.append(slot)
 
     def collect(self):
