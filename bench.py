@@ -303,6 +303,20 @@ def main():
         print(json.dumps(out))
 
 
+def ncu_traffic(prefixes):
+    """Average dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernels from the committed
+    ncu --set full capture (profiles/r01d_dram_traffic_bytes.json); None when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "r01d_dram_traffic_bytes.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        data = json.load(f)
+    vals = [b for k, layers in data.items() if any(k.startswith(p) for p in prefixes) for b in layers.values()]
+    if not vals:
+        return None, None
+    return sum(vals) / len(vals), "profiles/r01d_ncu_full_layers.csv (mean over the %d captured launches)" % len(vals)
+
+
 def roofline_pass(pipe, x_dev, args):
     """Per-kernel device time (CUDA events on the launching stream, op by op, after the timed region) ->
     achieved TFLOP/s of the tcgen05 GEMM kernel and GB/s of the depthwise kernel vs the measured peaks.
@@ -334,23 +348,40 @@ def roofline_pass(pipe, x_dev, args):
         a["ms"] += t
         for c in pipe.chunks:
             a["flops"] += c.plan.op_meta[i]["flops"]; a["bytes"] += c.plan.op_meta[i]["bytes"]; a["launches"] += 1
-    gemm_ms = sum(agg[k]["ms"] for k in agg if k.startswith("gemm"))
-    gemm_flops = sum(agg[k]["flops"] for k in agg if k.startswith("gemm"))
-    gemm_launches = sum(agg[k]["launches"] for k in agg if k.startswith("gemm"))
+    tc_kinds = [k for k in agg if k.startswith("gemm") or k == "dwpw"]   # the two tcgen05 kernels
+    gemm_ms = sum(agg[k]["ms"] for k in tc_kinds)
+    gemm_flops = sum(agg[k]["flops"] for k in tc_kinds)
+    gemm_launches = sum(agg[k]["launches"] for k in tc_kinds)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak = pk["bf16"] if args.precision == "bf16" else pk["bf16"] / 2.0
-    res = {"roofline": {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all %d launches of a step)" % gemm_launches,
+    traffic, traffic_src = ncu_traffic(("conv_gemm_kernel", "dwpw_gemm_kernel"))
+    res = {"roofline": {"kernel": "tcgen05 implicit-GEMM kernels conv_gemm_kernel + dwpw_gemm_kernel (all %d launches of a "
+                                  "step; %.0f %% of the step)" % (gemm_launches, 100.0 * gemm_ms / max(sum(times), 1e-9)),
                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                        "frac": achieved / peak, "traffic": None,
+                        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": pk["source"] + (" bf16 sustained" if args.precision == "bf16"
                                                        else " bf16 sustained / 2 (tf32 nominal ratio)"),
-                        "ms_per_step": gemm_ms}}
+                        "algorithmic_flops_per_launch": gemm_flops / max(gemm_launches, 1),
+                        "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "ms_per_step": gemm_ms}}
+    if "gemm3x3" in agg:
+        d = agg["gemm3x3"]
+        tf = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        res["roofline_gemm3x3"] = {"kernel": "conv_gemm_kernel, dense 3x3 layers (%d launches)" % d["launches"],
+                                   "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                                   "ms_per_step": d["ms"]}
+    if "dwpw" in agg:
+        d = agg["dwpw"]
+        gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        res["roofline_dwpw_hbm"] = {"kernel": "dwpw_gemm_kernel as an HBM-bound fused block (%d launches)" % d["launches"],
+                                    "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                                    "frac": gbs / pk["hbm"], "ms_per_step": d["ms"]}
     if "depthwise" in agg:
         d = agg["depthwise"]
         gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        traffic_d, src_d = ncu_traffic(("depthwise3x3_tma_kernel",))
         res["roofline_depthwise"] = {"kernel": "depthwise3x3_tma_kernel (%d launches)" % d["launches"], "bound": "hbm",
                                      "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-                                     "traffic": None, "ms_per_step": d["ms"]}
+                                     "traffic": traffic_d, "traffic_source": src_d, "ms_per_step": d["ms"]}
     res["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in agg.items()}
     res["kernel_ms_per_step"].update(postproc_stage_ms(pipe, x_dev, reps))
     res["layer_ms"] = {n: round(t, 4) for n, t in zip(plan0.op_names[:nops], times)}
