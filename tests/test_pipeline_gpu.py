@@ -123,3 +123,90 @@ def test_val_infer_multiscale_matches_oracle(env):
             m = orc.resize_cubic(np.ascontiguousarray(m), dsize=(128, 96))
             avg += m / len(scales)
     assert np.abs(got_h - avg_h).max() < 3e-3 and np.abs(got_p - avg_p).max() < 3e-3
+
+
+def test_config1_infer_fast_720p_frame(env):
+    """BASELINE.json configs[0]: one 720x1280 BGR frame through infer_fast at height 256 -> net input
+    1x3x256x456 (pad [0,0,0,1]), then the drop-in extract/group calls (demo=True)."""
+    torch, net = env
+    from lwpose_b200 import demo
+    from oracle import net as onet
+    from lwpose_b200 import val
+    import cv2
+    net.precision = "tf32"
+    img = np.random.default_rng(0).integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+    heat, pafs, scale, pad = demo.infer_fast(net, img, 256, 8, 4, False)
+    assert heat.shape == (128, 228, 19) and pafs.shape == (128, 228, 38)
+    assert pad == [0, 0, 0, 1] and scale == 256 / 720
+    # same pre-processing as the reference, network through the CPU oracle
+    scaled = cv2.resize(img, (0, 0), fx=scale, fy=scale, interpolation=cv2.INTER_CUBIC)
+    padded, _ = val.pad_width(val.normalize(scaled, (128, 128, 128), 1 / 256), 8, (0, 0, 0), [256, max(scaled.shape[1], 256)])
+    x = torch.from_numpy(padded).permute(2, 0, 1).unsqueeze(0).float()
+    assert tuple(x.shape) == (1, 3, 256, 456)
+    ref = onet.forward(net.state_dict(), x)
+    from oracle import postproc as orc
+    ref_heat = orc.resize_cubic(np.ascontiguousarray(ref[-2][0].numpy().transpose(1, 2, 0)), fx=4, fy=4)
+    assert np.abs(heat - ref_heat).max() < 3e-3
+    poses, allk = demo.run_frame(net, img, 256)
+    assert poses.shape == (0,) and allk.shape == (0,)   # random-init weights stay below the 0.1 threshold
+
+
+def test_three_refinement_stages_pipeline(env):
+    """BASELINE.json configs[3] at a small size: R = 3 network through the batched pipeline."""
+    torch, _ = env
+    from lwpose_b200 import synth
+    from lwpose_b200.models.with_mobilenet import PoseEstimationWithMobileNet
+    from lwpose_b200.pipeline import PosePipeline
+    from oracle import net as onet
+    torch.manual_seed(0)
+    net = PoseEstimationWithMobileNet(num_refinement_stages=3).eval()
+    synth.randomize_bn_(net, seed=5)
+    x = synth.synthetic_net_input(3, 64, 96, seed=4)
+    ref = onet.forward(net.state_dict(), x)
+    net = net.cuda()
+    pipe = PosePipeline(net, 3, 64, 96, precision="bf16")
+    pipe(x.pin_memory()).check()
+    assert pipe.error_flag() == 0
+    heads = pipe.heads.cpu().numpy()
+    ref_heads = np.concatenate([ref[-2].numpy(), ref[-1].numpy()], 1).transpose(0, 2, 3, 1)
+    assert np.abs(heads[..., :57] - ref_heads).max() < 3e-2
+    outs = net(x.cuda())
+    assert len(outs) == 8
+    for o, r in zip(outs, ref):
+        assert float((o.cpu() - r).abs().max()) < 3e-3   # module forward defaults to tf32
+
+
+def test_streaming_submit_collect_order(env):
+    """Two batches in flight come back in submission order with their own results."""
+    torch, net = env
+    from lwpose_b200 import synth
+    from lwpose_b200.pipeline import PosePipeline
+    B, H, W = 2, 64, 96
+    marks = []
+    for k in (1, 2):
+        hm, paf, _ = synth.synthetic_pose_maps(B, H // 8, W // 8, seed=20 + k, persons=k)
+        inj = np.zeros((B, H // 8, W // 8, 64), np.float32)
+        inj[..., :19] = hm.transpose(0, 2, 3, 1)
+        inj[..., 19:57] = paf.transpose(0, 2, 3, 1)
+        marks.append(torch.from_numpy(inj).cuda())
+    state = {"i": 0}
+    pipe = PosePipeline(net, B, H, W, precision="bf16", heads_hook=lambda t, lo: t.add_(marks[state["i"]][lo:lo + t.shape[0]]))
+    x = synth.synthetic_net_input(B, H, W, seed=2).pin_memory()
+    expect = []
+    for k in (0, 1):   # synchronous calls give the expected tables of each batch
+        state["i"] = k
+        r = pipe(x).check()
+        expect.append((r.n_poses.copy(), r.pose_entries.copy()))
+    assert expect[0][0].sum() >= 1 and not np.array_equal(expect[0][1], expect[1][1])
+    state["i"] = 0
+    pipe.submit(x)
+    state["i"] = 1
+    pipe.submit(x)
+    with pytest.raises(RuntimeError):
+        pipe.submit(x)   # depth 2
+    for k in (0, 1):
+        r = pipe.collect()
+        assert np.array_equal(r.n_poses, expect[k][0])
+        for b in range(B):
+            n = int(r.n_poses[b])
+            assert np.array_equal(r.pose_entries[b, :n], expect[k][1][b, :n])
