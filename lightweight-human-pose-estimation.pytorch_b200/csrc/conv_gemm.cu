@@ -97,7 +97,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < p.acc_stages; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tempty_bar[a], kEpiWarps);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -176,11 +176,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const size_t pix = ((size_t)tc.img * p.H + y) * (size_t)p.W + x;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
       if (p.tma_store) {
-        staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)q * 2 * kStageOutBytes, 2, sbuf_idx, t_row, tc.n0,
-                                    p.block_n, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld, valid, pix, lane,
-                                    tc.x0 + (q * 32) % p.tile_w, tc.y0 + (q * 32) / p.tile_w, tc.img);
+        staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)(warp - 2) * kStageOutBytes, 1, sbuf_idx, t_row,
+                                    tc.n0, p.block_n, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld, valid, pix,
+                                    lane, tc.x0 + (q * 32) % p.tile_w, tc.y0 + (q * 32) / p.tile_w, tc.img,
+                                    (warp - 2) >> 2, kEpiWarps / 4);
       } else {
-        for (int c = 0; c < p.block_n; c += 32) {
+        for (int c = ((warp - 2) >> 2) * 32; c < p.block_n; c += 32 * (kEpiWarps / 4)) {  // the quarter's two warps alternate
           uint32_t r[32];
           ptx::tmem_ld_32x32(t_row + (uint32_t)c, r);
           ptx::tmem_ld_wait();

@@ -7,7 +7,8 @@
 
 namespace lwp {
 
-constexpr int kGemmThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kEpiWarps = 8;         // two epilogue warps per TMEM lane quarter (alternate 128-byte chunks)
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
 constexpr int kBlockM = 128;        // pixels per tile == UMMA M == TMEM lanes
 constexpr int kKBlockBytes = 128;   // one SWIZZLE_128B row of K per pipeline stage
 constexpr int kATileBytes = kBlockM * kKBlockBytes;
@@ -45,7 +46,7 @@ struct GemmParams {
   int store_bw, store_bh;  // pixel box of one warp's 32 rows (store_bw * store_bh == 32)
 };
 
-constexpr int kStagingBytes = 4 * 2 * kStageOutBytes;  // 4 epilogue warps x double buffer
+constexpr int kStagingBytes = kEpiWarps * kStageOutBytes;  // one staging buffer per epilogue warp
 
 size_t conv_gemm_smem_bytes(const GemmParams &p);
 int conv_gemm_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,

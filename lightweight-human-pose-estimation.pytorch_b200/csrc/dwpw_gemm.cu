@@ -21,8 +21,9 @@
 
 namespace lwp {
 
-constexpr int kDwpwThreads = 448;  // 14 warps
-constexpr int kDwWarp0 = 6, kDwWarps = 8;
+constexpr int kDwpwEpiWarps = 4;   // the depthwise warps need the registers: one epilogue warp per TMEM lane quarter here
+constexpr int kDwWarp0 = 2 + kDwpwEpiWarps, kDwWarps = 8;   // warps 0/1: TMA / MMA, then epilogue warps, then depthwise warps
+constexpr int kDwpwThreads = (kDwWarp0 + kDwWarps) * 32;  // 448
 
 struct DwpwSmem {
   uint32_t a_off, b_off, staging_off, in_off, scale_off, shift_off, bars_off, total;
@@ -33,7 +34,7 @@ __host__ __device__ inline DwpwSmem dwpw_smem_layout(const DwpwParams &p) {
   L.a_off = 0;
   L.b_off = L.a_off + (uint32_t)p.a_stages * kATileBytes;
   L.staging_off = L.b_off + (uint32_t)p.b_stages * p.b_stage_bytes;
-  L.in_off = L.staging_off + 4u * (uint32_t)p.staging_bufs * kStageOutBytes;
+  L.in_off = L.staging_off + (uint32_t)kDwpwEpiWarps * (uint32_t)p.staging_bufs * kStageOutBytes;
   L.scale_off = (L.in_off + (uint32_t)p.in_stages * p.in_stage_bytes + 127u) & ~127u;
   L.shift_off = L.scale_off + (uint32_t)p.cout_pad * 4;
   L.bars_off = L.shift_off + (uint32_t)p.cout_pad * 4;
@@ -164,7 +165,7 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     for (int s = 0; s < p.in_stages; ++s) { ptx::mbar_init(&in_full[s], 1); ptx::mbar_init(&in_empty[s], kDwWarps); }
     for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(&a_full[s], kDwWarps); ptx::mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < p.acc_stages; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < p.acc_stages; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], kDwpwEpiWarps); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -257,9 +258,10 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
       const size_t pix = ((size_t)img * p.H + y) * (size_t)p.W + x;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.cout_pad);
       if (!(p.debug & 2))
-      staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)q * p.staging_bufs * kStageOutBytes, p.staging_bufs,
-                                  sbuf_idx, t_row, 0, p.cout_pad, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld,
-                                  valid, pix, lane, x0 + (q * 32) % p.tile_w, y0 + (q * 32) / p.tile_w, img, p.debug >> 3);
+        staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)(warp - 2) * p.staging_bufs * kStageOutBytes,
+                                    p.staging_bufs, sbuf_idx, t_row, 0, p.cout_pad, p.n_store, s_scale, s_shift, p.act,
+                                    p.residual, p.res_ld, valid, pix, lane, x0 + (q * 32) % p.tile_w,
+                                    y0 + (q * 32) / p.tile_w, img, (warp - 2) >> 2, kDwpwEpiWarps / 4, p.debug >> 3);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);

@@ -84,54 +84,64 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&r)[32], uint8_t *
   }
 }
 
+// `part` of `nparts` epilogue warps share one TMEM lane quarter: each takes every nparts-th 128-byte chunk.
 template <bool kTf32>
 __device__ __forceinline__ void staged_epilogue_tile(const CUtensorMap *tmC, uint8_t *stage_base, int nbuf, int &sbuf_idx,
                                                      uint32_t t_row, int n0, int block_n, int n_store,
                                                      const float *s_scale, const float *s_shift, int act,
                                                      const void *residual, int res_ld, bool valid, size_t pix, int lane,
-                                                     int store_x, int store_y, int img, int dbg = 0) {
+                                                     int store_x, int store_y, int img, int part = 0, int nparts = 1,
+                                                     int dbg = 0) {
   constexpr int kUnitsPerChunk = kTf32 ? 1 : 2;   // 128 output bytes = 32 fp32 / 64 bf16 columns
+  constexpr int kChunkCols = 32 * kUnitsPerChunk;
   const bool fast_relu = act == LWP_ACT_RELU && residual == nullptr;
   const bool res_ok = residual != nullptr && valid;
   int cols = n_store - n0;                          // columns of this tile that are stored (whole chunks)
   if (cols > block_n) cols = block_n;
   if (cols <= 0) return;
-  const int units = cols / 32;
+  const int chunks = cols / kChunkCols;
   uint32_t ra[32], rb[32];
-  ptx::tmem_ld_32x32(t_row, ra);
-  ptx::tmem_ld_wait(ra);
-
-  auto do_unit = [&](int u, const uint32_t (&r)[32]) {
+  if (part < chunks) {
+    ptx::tmem_ld_32x32(t_row + (uint32_t)(part * kChunkCols), ra);
+    ptx::tmem_ld_wait(ra);
+  }
+  for (int c = part; c < chunks; c += nparts) {
+    const int col0 = c * kChunkCols;
     uint8_t *sbuf = stage_base + (size_t)sbuf_idx * kStageOutBytes;
-    const int in_chunk = u % kUnitsPerChunk;
-    if (in_chunk == 0) {  // first unit of a chunk: the tensor store that last read this staging buffer must be done reading
-      if (lane == 0) {
-        if (nbuf == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
-      }
-      __syncwarp();
+    if (lane == 0) {  // the tensor store that last read this staging buffer must be done reading it
+      if (nbuf == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
     }
-    if (!(dbg & 2))
-      epilogue_unit<kTf32>(r, sbuf, lane, in_chunk * 32, n0 + u * 32, s_scale, s_shift, act, fast_relu, residual, res_ld,
-                           res_ok, pix);
-    if (in_chunk == kUnitsPerChunk - 1) {  // chunk complete -> one TMA tensor store of the warp's 32 x 128-byte box
-      ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
-      __syncwarp();
-      if (lane == 0 && !(dbg & 1)) {
-        ptx::tma_store_4d(tmC, sbuf, n0 + (u / kUnitsPerChunk) * (kUnitsPerChunk * 32), store_x, store_y, img);
-        ptx::bulk_commit();
-      }
-      sbuf_idx = nbuf == 2 ? (sbuf_idx ^ 1) : 0;
-    }
-  };
-
-  for (int u = 0; u < units; u += 2) {
-    if (u + 1 < units) ptx::tmem_ld_32x32(t_row + (uint32_t)((u + 1) * 32), rb);  // in flight during do_unit(u)
-    do_unit(u, ra);
-    if (u + 1 < units) {
+    __syncwarp();
+    const int cn = c + nparts;  // this warp's next chunk
+    if constexpr (kUnitsPerChunk == 2) {
+      ptx::tmem_ld_32x32(t_row + (uint32_t)(col0 + 32), rb);          // in flight during the first unit's math
+      if (!(dbg & 2))
+        epilogue_unit<kTf32>(ra, sbuf, lane, 0, n0 + col0, s_scale, s_shift, act, fast_relu, residual, res_ld, res_ok, pix);
       ptx::tmem_ld_wait(rb);
-      if (u + 2 < units) ptx::tmem_ld_32x32(t_row + (uint32_t)((u + 2) * 32), ra);  // in flight during do_unit(u + 1)
-      do_unit(u + 1, rb);
-      if (u + 2 < units) ptx::tmem_ld_wait(ra);
+      if (cn < chunks) ptx::tmem_ld_32x32(t_row + (uint32_t)(cn * kChunkCols), ra);  // next chunk, in flight
+      if (!(dbg & 2))
+        epilogue_unit<kTf32>(rb, sbuf, lane, 32, n0 + col0 + 32, s_scale, s_shift, act, fast_relu, residual, res_ld, res_ok,
+                             pix);
+    } else {
+      if (cn < chunks) ptx::tmem_ld_32x32(t_row + (uint32_t)(cn * kChunkCols), rb);
+      if (!(dbg & 2))
+        epilogue_unit<kTf32>(ra, sbuf, lane, 0, n0 + col0, s_scale, s_shift, act, fast_relu, residual, res_ld, res_ok, pix);
+    }
+    ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0 && !(dbg & 1)) {  // one TMA tensor store of the warp's 32 x 128-byte box
+      ptx::tma_store_4d(tmC, sbuf, n0 + col0, store_x, store_y, img);
+      ptx::bulk_commit();
+    }
+    sbuf_idx = nbuf == 2 ? (sbuf_idx ^ 1) : 0;
+    if (cn < chunks) {
+      if constexpr (kUnitsPerChunk == 2) {
+        ptx::tmem_ld_wait(ra);
+      } else {
+        ptx::tmem_ld_wait(rb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ra[i] = rb[i];
+      }
     }
   }
 }
