@@ -52,5 +52,10 @@ size_t conv_gemm_smem_bytes(const GemmParams &p);
 int conv_gemm_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
                      const GemmParams &p, int grid, cudaStream_t st);
 int conv_gemm_init();
+// CTA-pair (cta_group::2) variant, conv_gemm2.cu
+size_t conv_gemm2_smem_bytes(const GemmParams &p);
+int conv_gemm2_init();
+int conv_gemm2_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+                      const GemmParams &p, int grid, cudaStream_t st);
 
 }  // namespace lwp

@@ -46,6 +46,7 @@ struct Op {
   // gemm (tmA is also the input map of the TMA depthwise kernel)
   CUtensorMap tmA, tmB, tmC;
   GemmParams gp;
+  bool two_cta = false;   // conv_gemm2_kernel: CTA pairs, tcgen05.mma.cta_group::2
   DwpwParams fp;
   int grid = 0;
 };
@@ -225,6 +226,24 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   g.m_tiles = g.NIMG * g.tiles_x * g.tiles_y;
   long long total_tiles = (long long)g.m_tiles * g.n_tiles;
   op.grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+  // CTA pairs (cta_group::2, M = 256): layers whose epilogue is the plain TMA-store one and that have enough tiles
+  {
+    const char *e2 = getenv("LWP_GEMM_2CTA");
+    const int mode = e2 ? atoi(e2) : 0;   // 0 off, 1: 3x3 layers, 2: every eligible layer
+    const bool plain = out != nullptr && out_f32 == nullptr && g.n_store % (kKBlockBytes / es) == 0;
+    if (mode > 0 && plain && g.block_n >= 128 && (mode >= 3 || g.m_tiles >= 2 * num_sms()) && (mode >= 2 || taps == 9) &&
+        conv_gemm2_init() == LWP_OK) {
+      op.two_cta = true;
+      g.idesc = make_umma_idesc(tf32, 2 * kBlockM, g.block_n);
+      const int stage2 = kATileBytes + (g.block_n / 2) * kKBlockBytes;
+      int st2 = (200 * 1024 - kStagingBytes) / stage2;
+      g.num_stages = st2 > kMaxStages ? kMaxStages : st2;
+      const long long pairs = (long long)((g.m_tiles + 1) / 2) * g.n_tiles;
+      long long gr = 2 * pairs;
+      const int cap = num_sms() / 2 * 2;
+      op.grid = (int)(gr < cap ? gr : cap);
+    }
+  }
 
   EncodeTiledFn enc = get_encode_fn();
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -241,7 +260,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
     const cuuint64_t ktot = (cuuint64_t)taps * Cin;
     cuuint64_t dims[2] = {ktot, (cuuint64_t)cout_pad};
     cuuint64_t strides[1] = {ktot * es};
-    cuuint32_t box[2] = {(cuuint32_t)kb_elems, (cuuint32_t)g.block_n};
+    cuuint32_t box[2] = {(cuuint32_t)kb_elems, (cuuint32_t)(op.two_cta ? g.block_n / 2 : g.block_n)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&op.tmB, dt, 2, const_cast<void *>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -387,7 +406,8 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int la
                                 op.dil, op.act, st);
         break;
       case OP_GEMM:
-        rc = conv_gemm_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st);
+        rc = op.two_cta ? conv_gemm2_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st)
+                        : conv_gemm_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st);
         break;
       case OP_DWPW:
         rc = dwpw_launch(f32, op.tmA, op.tmB, op.tmC, op.fp, op.grid, st);

@@ -262,3 +262,24 @@ def test_forward_rejects_cpu_tensors(env):
     net = PoseEstimationWithMobileNet(1).eval().cuda()
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 3, 64, 64))
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_cta_pair_gemm_network(env, precision, monkeypatch):
+    """Opt-in CTA-pair kernel (tcgen05.mma.cta_group::2, M = 256 over two CTAs, half the weight tile per CTA):
+    forced on for every eligible layer, the whole network still matches the reference golden outputs."""
+    torch, _lib, engine = env
+    from lwpose_b200 import synth
+    monkeypatch.setenv("LWP_GEMM_2CTA", "3")
+    name, R, H, W, B, gain = gc.net_cases()[1]
+    g = gc.load("net_golden.npz")
+    net = _build_net(torch, name, R, gain).cuda()
+    net.precision = precision
+    x = synth.synthetic_net_input(B, H, W, seed=3).cuda()
+    outs = net(x)
+    torch.cuda.synchronize()
+    assert net.engine().plan(precision, B, H, W).error_flag() == 0
+    tol = 3e-3 if precision == "tf32" else 3e-2
+    for i, y in enumerate(outs):
+        ref = torch.from_numpy(g["net_%s_out%d" % (name, i)])
+        assert _rel(y.cpu(), ref) < tol, i
