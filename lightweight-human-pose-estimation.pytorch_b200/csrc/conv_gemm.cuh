@@ -30,6 +30,7 @@ struct GemmParams {
   uint32_t idesc;          // UMMA instruction descriptor (M = 128, N = block_n)
   int act;                 // LWP_ACT_*
   int num_stages;
+  int kps;                 // K blocks per pipeline stage (1 or 2): one mbarrier round trip covers kps x 128 bytes of K
   uint32_t tmem_cols;      // power of two >= acc_stages * block_n
   int acc_stages;          // TMEM accumulator ring depth (2..8)
   const float *scale, *shift;
@@ -42,6 +43,7 @@ struct GemmParams {
   int *err_flag;           // set non-zero if a pipeline wait timed out
   // epilogue through shared memory + TMA store (plain single-output layers): each epilogue warp stages its
   // 32 pixel rows x 128 bytes of output and one lane issues a 4-D tensor store of that box
+  int debug;               // timing experiments only (LWP_DEBUG_GEMM): 1 skip MMA, 2 skip epilogue, 4 skip A loads, 8 skip B loads
   int tma_store;           // 0: direct register -> global stores
   int store_bw, store_bh;  // pixel box of one warp's 32 rows (store_bw * store_bh == 32)
 };
