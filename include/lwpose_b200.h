@@ -151,6 +151,15 @@ int lwp_plan_add_stem(lwp_plan *p, const float *w, const float *scale, const flo
                       int W);
 
 /*
+ * Same stem, but fed by the raw frame: x at run time is uint8 [n][H][W][3] (BGR, already at the network size) and
+ * the kernel applies val.normalize ((pixel - mean[c]) * img_scale, val.py:30-33 / demo.py:60) on the fly, evaluated in
+ * double and rounded to float32 exactly like the reference's NumPy expression followed by .float().  Zero padding of
+ * the convolution applies to the normalised values.  4x fewer input bytes over PCIe / HBM than float32 NCHW.
+ */
+int lwp_plan_add_stem_u8(lwp_plan *p, const float *w, const float *scale, const float *shift, void *out, int n, int H,
+                         int W, const double *img_mean3, double img_scale);
+
+/*
  * Depthwise 3x3 conv (groups == channels, bias=False) + per-channel scale/shift + activation
  * (modules/conv.py:15-17 conv_dw, :27-28 conv_dw_no_bn).  NHWC in / NHWC out, plan dtype.
  * w: [9][C] float32, tap-major (tap = ky*3 + kx; the host mirror transposes the state_dict's [C][1][3][3]);
@@ -190,10 +199,11 @@ int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w, const floa
 int lwp_plan_add_nhwc_to_nchw(lwp_plan *p, const void *in, int in_ld, int in_is_f32, int c0, int c, float *out, int n,
                               int H, int W);
 
-/* Enqueue every recorded op on `stream`.  x: NCHW float32 input of the stem (may be NULL if no stem). */
-int lwp_plan_run(lwp_plan *p, const float *x, void *stream);
+/* Enqueue every recorded op on `stream`.  x: input of the stem -- NCHW float32, or uint8 NHWC for a plan built with
+ * lwp_plan_add_stem_u8 (may be NULL if the plan has no stem). */
+int lwp_plan_run(lwp_plan *p, const void *x, void *stream);
 /* Enqueue ops [first, last) only (per-layer timing / parity tests). */
-int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int last, void *stream);
+int lwp_plan_run_range(lwp_plan *p, const void *x, int first, int last, void *stream);
 /* number of kernel launches one lwp_plan_run issues */
 int lwp_plan_num_launches(const lwp_plan *p);
 /* Synchronising read of the plan's device error flag: 0 = ok, else the id of the pipeline wait that timed

@@ -35,6 +35,8 @@ SIGNATURES = {
     "lwp_plan_destroy": (None, [_c_void_p]),
     "lwp_plan_num_ops": (_c_int, [_c_void_p]),
     "lwp_plan_add_stem": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
+    "lwp_plan_add_stem_u8": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
+                                      ctypes.POINTER(_c_double), _c_double]),
     "lwp_plan_add_depthwise": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
                                         _c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
     "lwp_plan_add_conv_gemm": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,

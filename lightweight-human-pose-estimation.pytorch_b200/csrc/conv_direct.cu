@@ -51,10 +51,18 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // from shared memory (LDS.128 = two pairs) feeds two packed FFMA2s, the 5 input columns the two pixels
 // share are loaded once.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+struct StemNorm {  // (pixel - mean[c]) * scale of val.normalize, evaluated in double like NumPy does, then rounded to fp32
+  double mean[3];
+  double scale;
+};
+
+template <typename T, bool kU8>
 __global__ void __launch_bounds__(128)
-stem_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ scale,
-            const float *__restrict__ shift, T *__restrict__ out, int n, int H, int W, int Ho, int Wo) {
+stem_kernel(const void *__restrict__ xin, const float *__restrict__ w, const float *__restrict__ scale,
+            const float *__restrict__ shift, T *__restrict__ out, int n, int H, int W, int Ho, int Wo,
+            const StemNorm nrm) {
+  const float *x = reinterpret_cast<const float *>(xin);          // kU8 == false: NCHW float32
+  const uint8_t *x8 = reinterpret_cast<const uint8_t *>(xin);     // kU8 == true: [n][H][W][3] uint8 (BGR frame)
   __shared__ __align__(16) float s_w[27][32];  // [ci*9 + ky*3 + kx][co]
   __shared__ __align__(16) float s_scale[32], s_shift[32];
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) {
@@ -79,6 +87,7 @@ stem_kernel(const float *__restrict__ x, const float *__restrict__ w, const floa
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[q][j] = make_float2(0.f, 0.f);
     const float *xb = x + (size_t)img * 3 * H * W;
+    const uint8_t *xb8 = x8 + (size_t)img * 3 * H * W;
     const int xi0 = 2 * xo - 1;            // leftmost input column (pixel 0 taps xi0..xi0+2, pixel 1 taps xi0+2..xi0+4)
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
@@ -87,11 +96,18 @@ stem_kernel(const float *__restrict__ x, const float *__restrict__ w, const floa
         const int yi = 2 * yo - 1 + ky;
         if (yi < 0 || yi >= H) continue;
         const float *row = xb + ((size_t)ci * H + yi) * W;
+        const uint8_t *row8 = xb8 + (size_t)yi * W * 3 + ci;
         float v[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
           const int xi = xi0 + c;
-          v[c] = (xi >= 0 && xi < W) ? __ldg(row + xi) : 0.f;
+          if constexpr (kU8) {  // zero padding applies to the NORMALISED image, as in the reference (pad_value 0 after normalize)
+            v[c] = (xi >= 0 && xi < W)
+                       ? __double2float_rn(__dmul_rn(__dsub_rn((double)__ldg(row8 + (size_t)xi * 3), nrm.mean[ci]), nrm.scale))
+                       : 0.f;
+          } else {
+            v[c] = (xi >= 0 && xi < W) ? __ldg(row + xi) : 0.f;
+          }
         }
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
@@ -370,13 +386,21 @@ static int grid_for(long long total, int block, int per_sm) {
   return (int)b;
 }
 
-int stem_launch(bool f32, const float *x, const float *w, const float *scale, const float *shift, void *out, int n,
-                int H, int W, cudaStream_t st) {
+int stem_launch(bool f32, const void *x, bool x_is_u8, const double *mean3, double img_scale, const float *w,
+                const float *scale, const float *shift, void *out, int n, int H, int W, cudaStream_t st) {
   const int Ho = H / 2, Wo = W / 2;
   long long total = (long long)n * Ho * ((Wo + 1) / 2);
   int grid = grid_for(total, 128, 16);
-  if (f32) stem_kernel<float><<<grid, 128, 0, st>>>(x, w, scale, shift, (float *)out, n, H, W, Ho, Wo);
-  else stem_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(x, w, scale, shift, (__nv_bfloat16 *)out, n, H, W, Ho, Wo);
+  StemNorm nrm;
+  nrm.mean[0] = mean3 ? mean3[0] : 0; nrm.mean[1] = mean3 ? mean3[1] : 0; nrm.mean[2] = mean3 ? mean3[2] : 0;
+  nrm.scale = img_scale;
+  if (x_is_u8) {
+    if (f32) stem_kernel<float, true><<<grid, 128, 0, st>>>(x, w, scale, shift, (float *)out, n, H, W, Ho, Wo, nrm);
+    else stem_kernel<__nv_bfloat16, true><<<grid, 128, 0, st>>>(x, w, scale, shift, (__nv_bfloat16 *)out, n, H, W, Ho, Wo, nrm);
+  } else {
+    if (f32) stem_kernel<float, false><<<grid, 128, 0, st>>>(x, w, scale, shift, (float *)out, n, H, W, Ho, Wo, nrm);
+    else stem_kernel<__nv_bfloat16, false><<<grid, 128, 0, st>>>(x, w, scale, shift, (__nv_bfloat16 *)out, n, H, W, Ho, Wo, nrm);
+  }
   LWP_LAUNCH_CHECK();
   return LWP_OK;
 }

@@ -41,6 +41,8 @@ struct Op {
   const float *w = nullptr, *scale = nullptr, *shift = nullptr;
   int n = 0, H = 0, W = 0, C = 0, stride = 1, dil = 1, act = 0;
   int ld = 0, c0 = 0, in_f32 = 0;
+  bool stem_u8 = false;          // stem reads a uint8 HWC frame and normalises it on the fly
+  double mean[3] = {0, 0, 0}, img_scale = 1.0;
   DwTileGeom dwg;
   bool dw_tma = false;
   // gemm (tmA is also the input map of the TMA depthwise kernel)
@@ -105,6 +107,18 @@ extern "C" int lwp_plan_add_stem(lwp_plan *p, const float *w, const float *scale
   op.kind = OP_STEM;
   op.w = w; op.scale = scale; op.shift = shift; op.out = out; op.n = n; op.H = H; op.W = W;
   p->ops.push_back(op);
+  return LWP_OK;
+}
+
+extern "C" int lwp_plan_add_stem_u8(lwp_plan *p, const float *w, const float *scale, const float *shift, void *out,
+                                    int n, int H, int W, const double *img_mean3, double img_scale) {
+  LWP_REQUIRE(img_mean3 != nullptr, "lwp_plan_add_stem_u8: null mean");
+  int rc = lwp_plan_add_stem(p, w, scale, shift, out, n, H, W);
+  if (rc != LWP_OK) return rc;
+  Op &op = p->ops.back();
+  op.stem_u8 = true;
+  op.mean[0] = img_mean3[0]; op.mean[1] = img_mean3[1]; op.mean[2] = img_mean3[2];
+  op.img_scale = img_scale;
   return LWP_OK;
 }
 
@@ -395,7 +409,7 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
   return LWP_OK;
 }
 
-extern "C" int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int last, void *stream) {
+extern "C" int lwp_plan_run_range(lwp_plan *p, const void *x, int first, int last, void *stream) {
   LWP_REQUIRE(p != nullptr, "lwp_plan_run: null plan");
   LWP_REQUIRE(first >= 0 && last <= (int)p->ops.size() && first <= last, "lwp_plan_run_range: bad range");
   cudaStream_t st = (cudaStream_t)stream;
@@ -406,7 +420,7 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int la
     switch (op.kind) {
       case OP_STEM:
         LWP_REQUIRE(x != nullptr, "lwp_plan_run: the plan has a stem but x is NULL");
-        rc = stem_launch(f32, x, op.w, op.scale, op.shift, op.out, op.n, op.H, op.W, st);
+        rc = stem_launch(f32, x, op.stem_u8, op.mean, op.img_scale, op.w, op.scale, op.shift, op.out, op.n, op.H, op.W, st);
         break;
       case OP_DW:
         if (op.dw_tma)
@@ -432,7 +446,7 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const float *x, int first, int la
   return LWP_OK;
 }
 
-extern "C" int lwp_plan_run(lwp_plan *p, const float *x, void *stream) {
+extern "C" int lwp_plan_run(lwp_plan *p, const void *x, void *stream) {
   LWP_REQUIRE(p != nullptr, "lwp_plan_run: null plan");
   return lwp_plan_run_range(p, x, 0, (int)p->ops.size(), stream);
 }

@@ -155,7 +155,7 @@ class _Packed:
 class Plan:
     """One recorded launch list + its buffers for a fixed (precision, N, H, W)."""
 
-    def __init__(self, packed, precision, n, H, W, n_stages_out, num_heatmaps, num_pafs, device):
+    def __init__(self, packed, precision, n, H, W, n_stages_out, num_heatmaps, num_pafs, device, input_u8=None):
         if H % 8 or W % 8:
             raise ValueError("input height/width must be multiples of 8 (got %dx%d)" % (H, W))
         self.lib = _lib.load()
@@ -166,6 +166,8 @@ class Plan:
         self.tdtype = tdtype
         self.device = device
         self.packed = packed  # keeps the packed weights alive
+        # input_u8 = (mean3, scale): the stem reads uint8 [n,H,W,3] frames and applies val.normalize on the fly
+        self.input_u8 = input_u8
         handle = _lib._c_void_p()
         _lib.check(self.lib.lwp_plan_create(code, handle), "lwp_plan_create")
         self.handle = handle
@@ -258,8 +260,15 @@ class Plan:
         pp = [self._buf(biggest), self._buf(biggest)]
 
         w_, s_, b_ = P.stem
-        _lib.check(self.lib.lwp_plan_add_stem(self.handle, w_.data_ptr(), s_.data_ptr(), b_.data_ptr(),
-                                              pp[0].data_ptr(), n, H, W), "lwp_plan_add_stem")
+        if self.input_u8 is None:
+            _lib.check(self.lib.lwp_plan_add_stem(self.handle, w_.data_ptr(), s_.data_ptr(), b_.data_ptr(),
+                                                  pp[0].data_ptr(), n, H, W), "lwp_plan_add_stem")
+        else:
+            mean3, img_scale = self.input_u8
+            mean_arr = (_lib._c_double * 3)(*[float(m) for m in mean3])
+            _lib.check(self.lib.lwp_plan_add_stem_u8(self.handle, w_.data_ptr(), s_.data_ptr(), b_.data_ptr(),
+                                                     pp[0].data_ptr(), n, H, W, mean_arr, float(img_scale)),
+                       "lwp_plan_add_stem_u8")
         self.op_names.append("model.0")
         es_ = 2 if self.tdtype == torch.bfloat16 else 4
         self.op_meta.append(dict(kind="stem", flops=2.0 * 27 * 32 * n * (H // 2) * (W // 2),
@@ -349,8 +358,12 @@ class Plan:
 
     # -- execution ----------------------------------------------------------------------------
     def run(self, x, first=0, last=None):
-        """Enqueue ops [first, last) on the current stream.  x: contiguous float32 cuda [n,3,H,W]."""
-        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (self.n, 3, self.H, self.W)
+        """Enqueue ops [first, last) on the current stream.  x: contiguous cuda tensor, float32 [n,3,H,W] or (plans
+        built with input_u8) uint8 [n,H,W,3]."""
+        if self.input_u8 is None:
+            assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (self.n, 3, self.H, self.W)
+        else:
+            assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and tuple(x.shape) == (self.n, self.H, self.W, 3)
         last = len(self.op_names) if last is None else last
         _lib.check(self.lib.lwp_plan_run_range(self.handle, x.data_ptr(), first, last, _lib.current_stream()),
                    "lwp_plan_run")
@@ -386,15 +399,16 @@ class NetEngine:
                 self._packed[precision] = _Packed(self.net, _PREC[precision][1])
         return self._packed[precision]
 
-    def plan(self, precision, n, H, W, slot=0):
+    def plan(self, precision, n, H, W, slot=0, input_u8=None):
         """Launch plan (with its own activation buffers) for one shape; `slot` distinguishes independent
-        instances of the same shape that run concurrently on different streams."""
-        key = (precision, n, H, W, slot)
+        instances of the same shape that run concurrently on different streams; input_u8 = (mean3, scale) makes
+        the stem take raw uint8 [n,H,W,3] frames."""
+        key = (precision, n, H, W, slot, None if input_u8 is None else (tuple(input_u8[0]), float(input_u8[1])))
         if key not in self._plans:
             net = self.net
             with torch.cuda.device(self.device):
                 self._plans[key] = Plan(self.packed(precision), precision, n, H, W, 1 + len(net.refinement_stages),
-                                        net.num_heatmaps, net.num_pafs, self.device)
+                                        net.num_heatmaps, net.num_pafs, self.device, input_u8=input_u8)
         return self._plans[key]
 
     def forward(self, x, precision="tf32"):

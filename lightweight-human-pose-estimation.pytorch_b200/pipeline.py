@@ -50,7 +50,7 @@ class _Chunk:
         self.pipe, self.lo, self.n = pipe, lo, n
         dev = pipe.device
         eng = pipe.net.engine()
-        self.plan = eng.plan(pipe.precision, n, pipe.H, pipe.W, slot=slot)
+        self.plan = eng.plan(pipe.precision, n, pipe.H, pipe.W, slot=slot, input_u8=pipe.input_u8)
         ck, cc, cp, cn = pipe.caps
         L = pipe.L
         if not pipe.fused:
@@ -122,7 +122,10 @@ class _Slot:
 
     def __init__(self, pipe):
         b, (ck, _, cp, _) = pipe.n, pipe.caps
-        self.x_dev = torch.empty((b, 3, pipe.H, pipe.W), dtype=torch.float32, device=pipe.device)
+        if pipe.input_u8 is None:
+            self.x_dev = torch.empty((b, 3, pipe.H, pipe.W), dtype=torch.float32, device=pipe.device)
+        else:
+            self.x_dev = torch.empty((b, pipe.H, pipe.W, 3), dtype=torch.uint8, device=pipe.device)
         pin = dict(pin_memory=True)
         self.h_pose_entries = torch.empty((b, cp, postproc.POSE_ENTRY), dtype=torch.float64, **pin)
         self.h_n_poses = torch.empty((b,), dtype=torch.int32, **pin)
@@ -150,7 +153,8 @@ class PosePipeline:
 
     def __init__(self, net, batch, height, width, precision="bf16", upsample_ratio=4, demo=True,
                  min_paf_score=0.05, cap_kpts=128, cap_candidates=2048, cap_poses=256, cap_connections=2048,
-                 heads_hook=None, fused=True, chunk=None, depth=2, overlap_postproc=True):
+                 heads_hook=None, fused=True, chunk=None, depth=2, overlap_postproc=True, input_format="f32_nchw",
+                 img_mean=(128, 128, 128), img_scale=1 / 256):
         _lib.require_cuda()
         self.net, self.precision = net, precision
         self.n, self.H, self.W = batch, height, width
@@ -163,6 +167,11 @@ class PosePipeline:
         self.fused = bool(fused) and upsample_ratio >= 3
         # post-processing of batch i on a second stream, overlapping the network of batch i+1
         self.overlap_postproc = bool(overlap_postproc)
+        # "f32_nchw": normalised float32 [n,3,H,W] like the reference's tensor_img; "u8_nhwc": raw BGR frames uint8
+        # [n,H,W,3] already at the network size -- (img - mean) * scale (val.normalize) is fused into the stem kernel
+        if input_format not in ("f32_nchw", "u8_nhwc"):
+            raise ValueError("input_format must be 'f32_nchw' or 'u8_nhwc'")
+        self.input_u8 = (tuple(img_mean), float(img_scale)) if input_format == "u8_nhwc" else None
         self.device = net.engine().device
         self.h, self.w = height // 8, width // 8
         self.Hu, self.Wu = self.h * upsample_ratio, self.w * upsample_ratio
@@ -181,7 +190,7 @@ class PosePipeline:
             self.pp_stream = torch.cuda.Stream(device=self.device)
         self._next, self._pending = 0, []
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0].tables())
-        self.h2d_bytes = batch * 3 * height * width * 4
+        self.h2d_bytes = batch * 3 * height * width * (4 if self.input_u8 is None else 1)
 
     @property
     def heads(self):

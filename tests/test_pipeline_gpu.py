@@ -210,3 +210,23 @@ def test_streaming_submit_collect_order(env):
         for b in range(B):
             n = int(r.n_poses[b])
             assert np.array_equal(r.pose_entries[b, :n], expect[k][1][b, :n])
+
+
+def test_uint8_frames_equal_normalised_float_input(env):
+    """input_format='u8_nhwc': raw BGR frames with val.normalize fused into the stem give bit-identical heads and pose
+    tables to feeding the reference's normalised float32 NCHW tensor."""
+    torch, net = env
+    from lwpose_b200 import synth, val
+    from lwpose_b200.pipeline import PosePipeline
+    B, H, W = 3, 64, 96
+    frames = synth.synthetic_frames(B, H, W, seed=3)
+    x_f32 = torch.from_numpy(np.stack([val.normalize(f, (128, 128, 128), 1 / 256) for f in frames])).permute(0, 3, 1, 2).float().contiguous()
+    pf = PosePipeline(net, B, H, W, precision="bf16")
+    p8 = PosePipeline(net, B, H, W, precision="bf16", input_format="u8_nhwc")
+    rf = pf(x_f32.pin_memory()).check()
+    hf = pf.heads.cpu().numpy()
+    r8 = p8(torch.from_numpy(frames).pin_memory()).check()
+    h8 = p8.heads.cpu().numpy()
+    assert np.array_equal(hf.view(np.int32), h8.view(np.int32))
+    assert np.array_equal(rf.n_poses, r8.n_poses)
+    assert p8.h2d_bytes * 4 == pf.h2d_bytes
