@@ -240,12 +240,14 @@ struct DwTileParams {
 };
 
 template <typename T> struct SmemVec8;  // 8 channels from shared memory as four packed fp32 pairs
+__device__ __forceinline__ float2 bf16x2_to_f32x2(uint32_t x) {  // PRMT + LOP3: keeps the FMA pipe for the FFMA2s
+  return make_float2(__uint_as_float(__byte_perm(x, 0u, 0x1044)), __uint_as_float(x & 0xffff0000u));
+}
 template <> struct SmemVec8<__nv_bfloat16> {
   static __device__ __forceinline__ void load(const uint8_t *p, float2 (&v)[4]) {
-    uint4 raw = *reinterpret_cast<const uint4 *>(p);
-    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = __bfloat1622float2(h[j]);
+    const uint4 raw = *reinterpret_cast<const uint4 *>(p);
+    v[0] = bf16x2_to_f32x2(raw.x); v[1] = bf16x2_to_f32x2(raw.y);
+    v[2] = bf16x2_to_f32x2(raw.z); v[3] = bf16x2_to_f32x2(raw.w);
   }
 };
 template <> struct SmemVec8<float> {

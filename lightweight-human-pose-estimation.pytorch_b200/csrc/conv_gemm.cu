@@ -30,9 +30,9 @@ struct SmemLayout {
   uint32_t scale_off, shift_off, bars_off, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int block_n, int num_stages, int cout_pad, int kps) {
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int num_stages, int cout_pad) {
   SmemLayout L;
-  L.stage_bytes = (uint32_t)kps * (kATileBytes + (uint32_t)block_n * kKBlockBytes);  // [A x kps][B x kps]
+  L.stage_bytes = kATileBytes + (uint32_t)block_n * kKBlockBytes;
   L.stages_off = 0;
   L.staging_off = L.stage_bytes * (uint32_t)num_stages;
   L.scale_off = L.staging_off + kStagingBytes;
@@ -43,7 +43,7 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int num_stages, i
 }
 
 size_t conv_gemm_smem_bytes(const GemmParams &p) {
-  return (size_t)smem_layout(p.block_n, p.num_stages, p.cout_pad, p.kps).total + 1024;  // + alignment slack
+  return (size_t)smem_layout(p.block_n, p.num_stages, p.cout_pad).total + 1024;  // + alignment slack
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -74,8 +74,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SmemLayout L = smem_layout(p.block_n, p.num_stages, p.cout_pad, p.kps);
-  const uint32_t b_tile_bytes = (uint32_t)p.block_n * kKBlockBytes;
+  const SmemLayout L = smem_layout(p.block_n, p.num_stages, p.cout_pad);
   float *s_scale = reinterpret_cast<float *>(smem + L.scale_off);
   float *s_shift = reinterpret_cast<float *>(smem + L.shift_off);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L.bars_off);
@@ -93,7 +92,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tmap(&tmB);
     if (p.tma_store) ptx::prefetch_tmap(&tmC);
     for (int s = 0; s < p.num_stages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&full_bar[s], 2);   // the activation producer and the weight producer each arrive once (+ their bytes)
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < p.acc_stages; ++a) {
@@ -113,34 +112,47 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: activation tiles =====================
+    // (the issue rate of the single producer thread bounds short-K layers: activations and weights are issued by
+    //  two different warps, each with the leanest possible loop)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
       for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
-        for (int it0 = 0; it0 < k_iters; it0 += p.kps) {
-          const int nk = min(p.kps, k_iters - it0);   // K blocks in this stage
-          if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; atomicExch(p.err_flag, 1); break; }
-          uint8_t *sa = smem + (size_t)stage * L.stage_bytes;
-          uint8_t *sb = sa + (size_t)p.kps * kATileBytes;
-          const uint32_t bytes = (uint32_t)nk * (((p.debug & 4) ? 0u : (uint32_t)kATileBytes) +
-                                                 ((p.debug & 8) ? 0u : b_tile_bytes));
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], bytes);
-          for (int j = 0; j < nk; ++j) {
-            const int it = it0 + j;
-            const int tap = it / p.kblocks_per_tap, kb = it - tap * p.kblocks_per_tap;
-            const int dy = p.taps == 1 ? 0 : (tap / 3 - 1) * p.dil;
-            const int dx = p.taps == 1 ? 0 : (tap % 3 - 1) * p.dil;
-            if (!(p.debug & 4))
-              ptx::tma_load_4d(sa + (size_t)j * kATileBytes, &tmA, &full_bar[stage], kb * p.kb_elems, tc.x0 + dx,
-                               tc.y0 + dy, tc.img);
-            if (!(p.debug & 8))
-              ptx::tma_load_2d(sb + (size_t)j * b_tile_bytes, &tmB, &full_bar[stage], tap * p.cin + kb * p.kb_elems,
-                               tc.n0);
+        for (int tap = 0; tap < p.taps && ok; ++tap) {
+          const int dy = p.taps == 1 ? 0 : (tap / 3 - 1) * p.dil;
+          const int dx = p.taps == 1 ? 0 : (tap % 3 - 1) * p.dil;
+          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
+            if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; atomicExch(p.err_flag, 1); break; }
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)kATileBytes);
+            ptx::tma_load_4d(smem + (size_t)stage * L.stage_bytes, &tmA, &full_bar[stage], kb * p.kb_elems, tc.x0 + dx,
+                             tc.y0 + dy, tc.img);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
           }
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kBProducerWarp) {
+    // ===================== TMA producer: weight tiles =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      const uint32_t b_bytes = L.stage_bytes - (uint32_t)kATileBytes;
+      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
+        const int n0 = (t % p.n_tiles) * p.block_n;
+        int kcoord = 0;
+        for (int tap = 0; tap < p.taps && ok; ++tap) {
+          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
+            if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; atomicExch(p.err_flag, 5); break; }
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
+            ptx::tma_load_2d(smem + (size_t)stage * L.stage_bytes + kATileBytes, &tmB, &full_bar[stage],
+                             kcoord + kb * p.kb_elems, n0);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          }
+          kcoord += p.cin;
         }
       }
     }
@@ -154,21 +166,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u)) { atomicExch(p.err_flag, 2); break; }
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
-        for (int it0 = 0; it0 < k_iters; it0 += p.kps) {
-          const int nk = min(p.kps, k_iters - it0);
+        for (int it = 0; it < k_iters; ++it) {
           if (!ptx::mbar_wait(&full_bar[stage], phase)) { ok = false; atomicExch(p.err_flag, 3); break; }
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * L.stage_bytes);
-          const uint32_t sb = sa + (uint32_t)p.kps * kATileBytes;
-          for (int j = 0; j < nk; ++j) {
-            const uint64_t da = ptx::umma_desc_k_sw128(sa + (uint32_t)j * kATileBytes);
-            const uint64_t db = ptx::umma_desc_k_sw128(sb + (uint32_t)j * b_tile_bytes);
+          const uint64_t da = ptx::umma_desc_k_sw128(sa);
+          const uint64_t db = ptx::umma_desc_k_sw128(sa + kATileBytes);
 #pragma unroll
-            for (int k = 0; k < kKBlockBytes / 32; ++k)  // 32 bytes of K per instruction: advance start address by 2
-              if (!(p.debug & 1))
-                ptx::umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
-                                 (uint32_t)((it0 | j | k) != 0));
-          }
+          for (int k = 0; k < kKBlockBytes / 32; ++k)  // 32 bytes of K per instruction: advance start address by 2
+            ptx::umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (uint32_t)((it | k) != 0));
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
@@ -177,8 +183,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
       }
     }
-  } else {
-    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+  } else if (warp < 2 + kEpiWarps) {
+    // ===================== epilogue (8 warps, two per TMEM lane quarter) =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int ty = row / p.tile_w, tx = row - ty * p.tile_w;
@@ -192,8 +198,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool valid = y < p.H && x < p.W;
       const size_t pix = ((size_t)tc.img * p.H + y) * (size_t)p.W + x;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
-      if (p.debug & 2) {
-      } else if (p.tma_store) {
+      if (p.tma_store) {
         staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)(warp - 2) * kStageOutBytes, 1, sbuf_idx, t_row,
                                     tc.n0, p.block_n, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld, valid, pix,
                                     lane, tc.x0 + (q * 32) % p.tile_w, tc.y0 + (q * 32) / p.tile_w, tc.img,

@@ -8,7 +8,8 @@
 namespace lwp {
 
 constexpr int kEpiWarps = 8;         // two epilogue warps per TMEM lane quarter (alternate 128-byte chunks)
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps + 32;  // warp 0: TMA producer (activations), warp 1: MMA issuer + TMEM owner, 8 epilogue warps, last warp: TMA producer (weights)
+constexpr int kBProducerWarp = 2 + kEpiWarps;
 constexpr int kBlockM = 128;        // pixels per tile == UMMA M == TMEM lanes
 constexpr int kKBlockBytes = 128;   // one SWIZZLE_128B row of K per pipeline stage
 constexpr int kATileBytes = kBlockM * kKBlockBytes;
@@ -30,7 +31,6 @@ struct GemmParams {
   uint32_t idesc;          // UMMA instruction descriptor (M = 128, N = block_n)
   int act;                 // LWP_ACT_*
   int num_stages;
-  int kps;                 // K blocks per pipeline stage (1 or 2): one mbarrier round trip covers kps x 128 bytes of K
   uint32_t tmem_cols;      // power of two >= acc_stages * block_n
   int acc_stages;          // TMEM accumulator ring depth (2..8)
   const float *scale, *shift;
@@ -43,7 +43,6 @@ struct GemmParams {
   int *err_flag;           // set non-zero if a pipeline wait timed out
   // epilogue through shared memory + TMA store (plain single-output layers): each epilogue warp stages its
   // 32 pixel rows x 128 bytes of output and one lane issues a 4-D tensor store of that box
-  int debug;               // timing experiments only (LWP_DEBUG_GEMM): 1 skip MMA, 2 skip epilogue, 4 skip A loads, 8 skip B loads
   int tma_store;           // 0: direct register -> global stores
   int store_bw, store_bh;  // pixel box of one warp's 32 rows (store_bw * store_bh == 32)
 };

@@ -153,7 +153,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
       }
     }
-  } else {
+  } else if (warp < 2 + kEpiWarps) {
     // ===================== epilogue (8 warps per CTA, its own 128 accumulator rows) =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;

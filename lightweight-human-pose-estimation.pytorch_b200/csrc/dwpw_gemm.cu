@@ -51,12 +51,16 @@ __device__ __forceinline__ float dw_act(float v, int act) {
 }
 
 template <bool kTf32> struct TileIn;  // 8 channels of the smem halo tile as four fp32 pairs
+// bf16 pair -> fp32 pair with two ALU-pipe instructions (PRMT, LOP3): the compiler's own choice (IMAD.U32 for the
+// shift) lands on the FMA pipe, which the FFMA2 stream needs
+__device__ __forceinline__ float2 bf16x2_to_f32x2(uint32_t x) {
+  return make_float2(__uint_as_float(__byte_perm(x, 0u, 0x1044)), __uint_as_float(x & 0xffff0000u));
+}
 template <> struct TileIn<false> {
   static __device__ __forceinline__ void load(const uint8_t *p, float2 (&v)[4]) {
-    uint4 raw = *reinterpret_cast<const uint4 *>(p);
-    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = __bfloat1622float2(h[j]);
+    const uint4 raw = *reinterpret_cast<const uint4 *>(p);
+    v[0] = bf16x2_to_f32x2(raw.x); v[1] = bf16x2_to_f32x2(raw.y);
+    v[2] = bf16x2_to_f32x2(raw.z); v[3] = bf16x2_to_f32x2(raw.w);
   }
 };
 template <> struct TileIn<true> {

@@ -210,19 +210,11 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   g.residual = residual; g.res_ld = res_ld;
   g.out = out; g.out_ld = out_ld; g.out_f32 = out_f32; g.out_f32_ld = out_f32_ld;
   g.err_flag = p->err_flag;
-  g.debug = getenv("LWP_DEBUG_GEMM") ? atoi(getenv("LWP_DEBUG_GEMM")) : 0;
-  if (const char *sv = getenv("LWP_GEMM_STAGES")) g.debug |= atoi(sv) << 8;
-  // optional: two K blocks per pipeline stage (halves the mbarrier round trips of the producer / MMA threads); measured
-  // neutral on the 3x3 layers (0.097 vs 0.096 ms), so the deeper single-block ring stays the default
   const int smem_budget = 232448 - 1024 - kStagingBytes - 2 * cout_pad * 4 - 512;
-  g.kps = 1;
-  if (taps * g.kblocks_per_tap >= 2 && getenv("LWP_GEMM_KPS2") != nullptr &&
-      smem_budget / (2 * (kATileBytes + g.block_n * kKBlockBytes)) >= 3)
-    g.kps = 2;
-  const int stage_bytes = g.kps * (kATileBytes + g.block_n * kKBlockBytes);
+  const int stage_bytes = kATileBytes + g.block_n * kKBlockBytes;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if ((g.debug >> 8) >= 2 && (g.debug >> 8) < stages) stages = g.debug >> 8;
+  if (const char *sv = getenv("LWP_GEMM_STAGES")) { int v = atoi(sv); if (v >= 2 && v < stages) stages = v; }
   g.num_stages = stages;
   g.acc_stages = 512 / g.block_n;  // the CTA owns the SM (smem > half), so it can take all 512 TMEM columns
   if (g.acc_stages > kMaxAccStages) g.acc_stages = kMaxAccStages;
@@ -258,7 +250,6 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
     if (mode > 0 && plain && g.block_n >= 128 && (mode >= 3 || g.m_tiles >= 2 * num_sms()) && (mode >= 2 || taps == 9) &&
         conv_gemm2_init() == LWP_OK) {
       op.two_cta = true;
-      g.kps = 1;
       g.idesc = make_umma_idesc(tf32, 2 * kBlockM, g.block_n);
       const int stage2 = kATileBytes + (g.block_n / 2) * kKBlockBytes;
       int st2 = (200 * 1024 - kStagingBytes) / stage2;
