@@ -359,12 +359,18 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
   // shared-memory budget: prefer deep B / A rings, then a second input stage, then double-buffered staging
   f.b_stages = f.n_mma + 1; f.a_stages = 2; f.in_stages = 1; f.staging_bufs = 1;
   const size_t limit = 232448;
-  { DwpwParams t = f; t.in_stages = 2; if (dwpw_smem_bytes(t) <= limit) f = t; }
-  { DwpwParams t = f; t.staging_bufs = 2; if (dwpw_smem_bytes(t) <= limit) f = t; }
-  { DwpwParams t = f; t.b_stages = f.b_stages + 1; if (t.b_stages <= 4 && dwpw_smem_bytes(t) <= limit) f = t; }
-  { DwpwParams t = f; t.a_stages = 3; if (dwpw_smem_bytes(t) <= limit) f = t; }
-  { DwpwParams t = f; t.in_stages = 3; if (dwpw_smem_bytes(t) <= limit) f = t; }
-  { DwpwParams t = f; t.b_stages = f.b_stages + 1; if (t.b_stages <= 4 && dwpw_smem_bytes(t) <= limit) f = t; }
+  // upgrade order (LWP_DWPW_ORDER, default "iisab i b"): the input ring first -- its TMA latency is what the depthwise
+  // warps wait for -- then double-buffered staging, a third A stage, deeper weight ring
+  const char *order = getenv("LWP_DWPW_ORDER") ? getenv("LWP_DWPW_ORDER") : "iisabib";
+  for (const char *c = order; *c; ++c) {
+    DwpwParams t = f;
+    if (*c == 'i') { if (t.in_stages >= 4) continue; t.in_stages++; }
+    else if (*c == 's') { if (t.staging_bufs >= 2) continue; t.staging_bufs = 2; }
+    else if (*c == 'a') { if (t.a_stages >= 4) continue; t.a_stages++; }
+    else if (*c == 'b') { if (t.b_stages >= 4) continue; t.b_stages++; }
+    else continue;
+    if (dwpw_smem_bytes(t) <= limit) f = t;
+  }
   if (dwpw_smem_bytes(f) > limit) { set_error("lwp_plan_add_dwpw: shared memory budget exceeded"); return LWP_ECAP; }
   op.grid = f.m_tiles < num_sms() ? f.m_tiles : num_sms();
 
