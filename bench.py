@@ -215,6 +215,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     import lwpose_b200  # noqa: F401
     from lwpose_b200 import parallel, synth
