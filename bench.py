@@ -334,17 +334,19 @@ def main():
 
 
 def ncu_traffic(prefixes):
-    """Average dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernels from the committed
-    ncu --set full capture (profiles/r01d_dram_traffic_bytes.json); None when the file is absent."""
-    path = os.path.join(ROOT, "profiles", "r01d_dram_traffic_bytes.json")
-    if not os.path.exists(path):
+    """Average dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernels from the newest committed
+    ncu --set full capture (profiles/r*_dram_traffic_bytes.json); None when there is none."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_dram_traffic_bytes.json")))
+    if not files:
         return None, None
-    with open(path) as f:
+    with open(files[-1]) as f:
         data = json.load(f)
     vals = [b for k, layers in data.items() if any(k.startswith(p) for p in prefixes) for b in layers.values()]
     if not vals:
         return None, None
-    return sum(vals) / len(vals), "profiles/r01d_ncu_full_layers.csv (mean over the %d captured launches)" % len(vals)
+    return sum(vals) / len(vals), "%s (mean over the %d captured launches)" % (
+        os.path.relpath(files[-1], ROOT).replace("dram_traffic_bytes.json", "ncu_full_layers.csv"), len(vals))
 
 
 def roofline_pass(pipe, x_dev, args):
@@ -384,9 +386,10 @@ def roofline_pass(pipe, x_dev, args):
     gemm_launches = sum(agg[k]["launches"] for k in tc_kinds)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak = pk["bf16"] if args.precision == "bf16" else pk["bf16"] / 2.0
-    traffic, traffic_src = ncu_traffic(("conv_gemm_kernel", "dwpw_gemm_kernel"))
-    res = {"roofline": {"kernel": "tcgen05 implicit-GEMM kernels conv_gemm_kernel + dwpw_gemm_kernel (all %d launches of a "
-                                  "step; %.0f %% of the step)" % (gemm_launches, 100.0 * gemm_ms / max(sum(times), 1e-9)),
+    traffic, traffic_src = ncu_traffic(("conv_gemm", "dwpw_gemm_kernel"))
+    res = {"roofline": {"kernel": "tcgen05 implicit-GEMM kernels conv_gemm_kernel / conv_gemm2_kernel%s (all %d launches of a "
+                                  "step; %.0f %% of the network time)" % (" / dwpw_gemm_kernel" if "dwpw" in agg else "", gemm_launches,
+                                                                         100.0 * gemm_ms / max(sum(times), 1e-9)),
                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": pk["source"] + (" bf16 sustained" if args.precision == "bf16"
@@ -399,6 +402,17 @@ def roofline_pass(pipe, x_dev, args):
         res["roofline_gemm3x3"] = {"kernel": "conv_gemm_kernel, dense 3x3 layers (%d launches)" % d["launches"],
                                    "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
                                    "ms_per_step": d["ms"]}
+    if "gemm1x1" in agg:
+        d = agg["gemm1x1"]
+        tf = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        res["roofline_pointwise"] = {"kernel": "conv_gemm_kernel / conv_gemm2_kernel (CTA pairs), 1x1 layers (%d launches)" % d["launches"],
+                                     "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                                     "ms_per_step": d["ms"]}
+        big = [(plan0.op_meta[i]["flops"] * len(pipe.chunks), times[i]) for i in range(nops)
+               if plan0.op_meta[i]["kind"] == "gemm1x1" and plan0.op_names[i] in ("model.%d.pw" % k for k in range(7, 12))]
+        if big:
+            tfb = sum(f for f, _ in big) / (sum(t for _, t in big) * 1e-3) / 1e12
+            res["roofline_pointwise"]["backbone_512x512"] = {"achieved": tfb, "frac": tfb / peak, "launches": len(big)}
     if "dwpw" in agg:
         d = agg["dwpw"]
         gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9

@@ -222,146 +222,198 @@ depthwise3x3_kernel(const T *__restrict__ in, T *__restrict__ out, const float *
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 3x3, NHWC, shared-memory halo tiles fed by TMA.
-// A tile = TH x TW output pixels x CB channels (CB*sizeof(T) <= 128 bytes per pixel).  One elected thread
-// TMA-loads the (IH x IW x CB) input halo box of the NEXT tile into the other smem buffer while all
-// 256 threads compute the current one; out-of-image parts of the box are zero-filled by TMA, which is
-// the convolution's zero padding.  A thread owns 8 channels x 4 consecutive output columns of one row
-// and slides a register window over the 3 x NCOL smem vectors it needs.
+// depthwise 3x3, NHWC, shared-memory halo tiles fed by TMA (reference: the groups=Cin Conv2d of
+// modules/conv.py:15,27 + BatchNorm/ReLU or ELU).
+// A tile = TH x TW output pixels x CB channels (CB*sizeof(T) <= 128 bytes per pixel).  A CTA keeps ONE channel
+// block for its whole life, so the 9 taps and the folded BN of a thread's 4 channels live in registers and
+// shared-memory bandwidth is spent on activations only.  One elected thread keeps a ring of NS halo boxes in
+// flight by TMA (out-of-image parts are zero-filled = the convolution's padding); all 256 threads compute.
+// A thread owns 4 channels x (2 rows x 4 columns) of outputs: the (2-1)*S+2*D+1 by (4-1)*S+2*D+1 input
+// window is read once from shared memory (LDS.64 for bf16) and feeds packed fp32 FFMA2s in the same tap
+// order (ky-major) for every output, i.e. the same bits whatever the tile shape.
 // ------------------------------------------------------------------------------------------------
 struct DwTileParams {
   int n, H, W, C, Ho, Wo;
-  int tw, th;          // output tile (tw multiple of 4, (tw/4)*th*cv == 256)
+  int tw, th;          // output tile (tw multiple of 4, th multiple of 2, (tw/4)*(th/2)*cq == 256)
   int iw, ih;          // input box
-  int cb, cv;          // channels per tile, 8-channel vectors per pixel (cb/8)
-  int tiles_x, tiles_y, cblocks, num_tiles;
-  int act;
+  int cb, cq;          // channels per tile, 4-channel groups per pixel (cb/4)
+  int tiles_x, tiles_y, cblocks, sp_tiles;   // sp_tiles = n * tiles_x * tiles_y spatial tiles per channel block
+  int act, stages;
   uint32_t stage_bytes;
 };
 
-template <typename T> struct SmemVec8;  // 8 channels from shared memory as four packed fp32 pairs
 __device__ __forceinline__ float2 bf16x2_to_f32x2(uint32_t x) {  // PRMT + LOP3: keeps the FMA pipe for the FFMA2s
   return make_float2(__uint_as_float(__byte_perm(x, 0u, 0x1044)), __uint_as_float(x & 0xffff0000u));
 }
-template <> struct SmemVec8<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const uint8_t *p, float2 (&v)[4]) {
-    const uint4 raw = *reinterpret_cast<const uint4 *>(p);
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : __expf(v) - 1.f; }  // ELU(alpha = 1) as in the fused block: abs error ~1e-7
+template <typename T> struct SmemVec4;  // 4 channels from shared memory as two packed fp32 pairs; activation + store of 4 channels
+template <> struct SmemVec4<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(uint32_t saddr, float2 (&v)[2]) {
+    uint2 raw;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(raw.x), "=r"(raw.y) : "r"(saddr));
     v[0] = bf16x2_to_f32x2(raw.x); v[1] = bf16x2_to_f32x2(raw.y);
-    v[2] = bf16x2_to_f32x2(raw.z); v[3] = bf16x2_to_f32x2(raw.w);
+  }
+  template <int ACT>
+  static __device__ __forceinline__ void store(__nv_bfloat16 *p, float2 a, float2 b) {
+    if constexpr (ACT == LWP_ACT_ELU) { a.x = elu1(a.x); a.y = elu1(a.y); b.x = elu1(b.x); b.y = elu1(b.y); }
+    __nv_bfloat162 lo = __float22bfloat162_rn(a), hi = __float22bfloat162_rn(b);
+    if constexpr (ACT == LWP_ACT_RELU) {  // ReLU after rounding == rounding after ReLU
+      const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
+      lo = __hmax2(lo, zero2); hi = __hmax2(hi, zero2);
+    }
+    *reinterpret_cast<uint2 *>(p) = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
   }
 };
-template <> struct SmemVec8<float> {
-  static __device__ __forceinline__ void load(const uint8_t *p, float2 (&v)[4]) {
-    float4 a = reinterpret_cast<const float4 *>(p)[0], b = reinterpret_cast<const float4 *>(p)[1];
+template <> struct SmemVec4<float> {
+  static __device__ __forceinline__ void load(uint32_t saddr, float2 (&v)[2]) {
+    float4 a;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(saddr));
     v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
-    v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+  }
+  template <int ACT>
+  static __device__ __forceinline__ void store(float *p, float2 a, float2 b) {
+    if constexpr (ACT == LWP_ACT_ELU) { a.x = elu1(a.x); a.y = elu1(a.y); b.x = elu1(b.x); b.y = elu1(b.y); }
+    if constexpr (ACT == LWP_ACT_RELU) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); }
+    *reinterpret_cast<float4 *>(p) = make_float4(a.x, a.y, b.x, b.y);
   }
 };
-__device__ __forceinline__ void ldg_pairs(const float *p, float2 (&v)[4]) {
-  float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
-  v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
-  v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
-}
 
-template <typename T, int S, int D>
-__global__ void __launch_bounds__(256)
+constexpr int kDwMaxStages = 4;
+
+struct DwTileCursor {  // (image, tile row, tile column) of a spatial tile index, advanced by a fixed stride without divisions
+  int img, ty, tx;
+  __device__ __forceinline__ void init(int j, int per_img, int tiles_x) {
+    img = j / per_img;
+    const int rem = j - img * per_img;
+    ty = rem / tiles_x;
+    tx = rem - ty * tiles_x;
+  }
+  __device__ __forceinline__ void advance(const DwTileCursor &d, int tiles_x, int tiles_y) {
+    tx += d.tx;
+    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    ty += d.ty;
+    if (ty >= tiles_y) { ty -= tiles_y; ++img; }
+    img += d.img;
+  }
+};
+
+template <typename T, int S, int D, int ACT, int PIXB>   // PIXB: bytes of one pixel of the smem tile (cb * sizeof(T): 64 or 128)
+__global__ void __launch_bounds__(256, 2)
 depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict__ out,
                         const float *__restrict__ w9c, const float *__restrict__ scale,
                         const float *__restrict__ shift, const DwTileParams p) {
-  constexpr int TWT = 4;                                  // outputs per thread along x
-  constexpr int NCOL = (TWT - 1) * S + 2 * D + 1;
+  constexpr int R = 2, CC = 4;                            // outputs per thread: R rows x CC columns (x 4 channels)
+  constexpr int NROW = (R - 1) * S + 2 * D + 1, NCOL = (CC - 1) * S + 2 * D + 1;
   extern __shared__ uint8_t dw_smem_raw[];
   uint8_t *smem = dw_smem_raw + ((128u - (ptx::smem_u32(dw_smem_raw) & 127u)) & 127u);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);   // 2 "full" barriers
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);   // one "full" barrier per stage
   uint8_t *bufs = smem + 128;
   const int tid = threadIdx.x;
   if (tid == 0) {
     ptx::prefetch_tmap(&tm_in);
-    ptx::mbar_init(&bars[0], 1);
-    ptx::mbar_init(&bars[1], 1);
+    for (int s = 0; s < p.stages; ++s) ptx::mbar_init(&bars[s], 1);
     ptx::fence_barrier_init();
   }
   __syncthreads();
-  const int cv = tid % p.cv, pt = tid / p.cv;
-  const int xgroups = p.tw / TWT;
-  const int xg = pt % xgroups, ty = pt / xgroups;
-  const int per_img = p.tiles_x * p.tiles_y * p.cblocks;
+  const int cq = tid % p.cq, pb = tid / p.cq;
+  const int xgroups = p.tw / CC;
+  const int xg = pb % xgroups, yg = pb / xgroups;
+  const int cblk = blockIdx.x % p.cblocks;               // neighbouring CTAs: same pixels, adjacent channel blocks
+  const int j0 = blockIdx.x / p.cblocks, jstride = gridDim.x / p.cblocks;
+  const int per_img = p.tiles_x * p.tiles_y;
+  const int c0 = cblk * p.cb + cq * 4;
+  DwTileCursor step, cur, nxt;                            // nxt: the tile the producer thread loads next
+  step.init(jstride, per_img, p.tiles_x);
+  cur.init(j0, per_img, p.tiles_x);
+  nxt = cur;
 
-  auto issue = [&](int tile, int buf) {
-    const int img = tile / per_img;
-    int rem = tile - img * per_img;
-    const int cblk = rem % p.cblocks;
-    rem /= p.cblocks;
-    const int tx = rem % p.tiles_x, tyy = rem / p.tiles_x;
+  auto issue = [&](const DwTileCursor &t, int buf) {
     ptx::mbar_arrive_expect_tx(&bars[buf], p.stage_bytes);
-    ptx::tma_load_4d(bufs + (size_t)buf * p.stage_bytes, &tm_in, &bars[buf], cblk * p.cb, tx * p.tw * S - D,
-                     tyy * p.th * S - D, img);
+    ptx::tma_load_4d(bufs + (size_t)buf * p.stage_bytes, &tm_in, &bars[buf], cblk * p.cb, t.tx * p.tw * S - D,
+                     t.ty * p.th * S - D, t.img);
   };
+  int jn = j0;                                            // index of nxt
+  if (tid == 0) {
+    for (int s = 0; s < p.stages - 1; ++s) {
+      if (jn < p.sp_tiles) issue(nxt, s);
+      nxt.advance(step, p.tiles_x, p.tiles_y);
+      jn += jstride;
+    }
+  }
 
-  int it = 0;
-  if (tid == 0 && (int)blockIdx.x < p.num_tiles) issue(blockIdx.x, 0);
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const int next = tile + gridDim.x;
-    if (tid == 0 && next < p.num_tiles) issue(next, buf ^ 1);  // buffer buf^1 was released by the previous __syncthreads
-    if (!ptx::mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1))) return;  // never spin forever
-    const int img = tile / per_img;
-    int rem = tile - img * per_img;
-    const int cblk = rem % p.cblocks;
-    rem /= p.cblocks;
-    const int tx = rem % p.tiles_x, tyy = rem / p.tiles_x;
-    const int c0 = cblk * p.cb + cv * 8;
-    const int yo = tyy * p.th + ty, xo0 = tx * p.tw + xg * TWT;
-    const uint8_t *sbuf = bufs + (size_t)buf * p.stage_bytes;
-    const int pix_bytes = p.cb * (int)sizeof(T);
-    float2 acc[TWT][4];  // packed fp32 pairs: one FFMA2 does two channels
+  // this thread's constants: 9 taps, folded BN scale/shift of 4 channels
+  float2 wk[9][2], sc[2], sh[2];
 #pragma unroll
-    for (int a = 0; a < TWT; ++a)
+  for (int k = 0; k < 9; ++k) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(w9c + (size_t)k * p.C + c0));
+    wk[k][0] = make_float2(a.x, a.y); wk[k][1] = make_float2(a.z, a.w);
+  }
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(scale + c0)), b = __ldg(reinterpret_cast<const float4 *>(shift + c0));
+    sc[0] = make_float2(a.x, a.y); sc[1] = make_float2(a.z, a.w);
+    sh[0] = make_float2(b.x, b.y); sh[1] = make_float2(b.z, b.w);
+  }
+  const int row_bytes = p.iw * PIXB;
+  const uint32_t win_off = (uint32_t)((yg * R * S) * row_bytes + xg * CC * S * PIXB + cq * 4 * (int)sizeof(T));
+  const uint32_t bufs_s = ptx::smem_u32(bufs);
+  const size_t opix = (size_t)p.C;                        // elements between horizontally adjacent output pixels
+  const size_t orow = (size_t)p.Wo * p.C;
+
+  int buf = 0;
+  uint32_t phase = 0;
+  for (int j = j0; j < p.sp_tiles; j += jstride) {
+    if (tid == 0) {  // refill the buffer every thread left at the end of the previous iteration
+      if (jn < p.sp_tiles) issue(nxt, buf == 0 ? p.stages - 1 : buf - 1);
+      nxt.advance(step, p.tiles_x, p.tiles_y);
+      jn += jstride;
+    }
+    if (!ptx::mbar_wait(&bars[buf], phase)) return;  // never spin forever
+    const uint32_t win = bufs_s + (uint32_t)buf * p.stage_bytes + win_off;
+    float2 acc[R][CC][2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[a][j] = make_float2(0.f, 0.f);
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      float2 wk[3][4];
+      for (int c = 0; c < CC; ++c) acc[r][c][0] = acc[r][c][1] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) ldg_pairs(w9c + (size_t)(ky * 3 + kx) * p.C + c0, wk[kx]);
-      const uint8_t *rowp = sbuf + ((size_t)(ty * S + ky * D) * p.iw + (size_t)xg * TWT * S) * pix_bytes +
-                            cv * 8 * (int)sizeof(T);
+    for (int iy = 0; iy < NROW; ++iy) {
+      const uint32_t rowp = win + (uint32_t)(iy * row_bytes);
 #pragma unroll
-      for (int ci = 0; ci < NCOL; ++ci) {
-        float2 v[4];
-        SmemVec8<T>::load(rowp + (size_t)ci * pix_bytes, v);
+      for (int ic = 0; ic < NCOL; ++ic) {
+        float2 v[2];
+        SmemVec4<T>::load(rowp + ic * PIXB, v);
 #pragma unroll
-        for (int a = 0; a < TWT; ++a) {
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            if (a * S + kx * D == ci) {
+          for (int ky = 0; ky < 3; ++ky)
+            if (r * S + ky * D == iy) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) acc[a][j] = __ffma2_rn(v[j], wk[kx][j], acc[a][j]);
+              for (int c = 0; c < CC; ++c)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+                  if (c * S + kx * D == ic) {
+                    acc[r][c][0] = __ffma2_rn(v[0], wk[ky * 3 + kx][0], acc[r][c][0]);
+                    acc[r][c][1] = __ffma2_rn(v[1], wk[ky * 3 + kx][1], acc[r][c][1]);
+                  }
             }
-          }
-        }
       }
     }
-    if (yo < p.Ho) {
-      float2 sc[4], sh[4];
-      ldg_pairs(scale + c0, sc);
-      ldg_pairs(shift + c0, sh);
+    const int yo0 = cur.ty * p.th + yg * R, xo0 = cur.tx * p.tw + xg * CC;
+    T *op = out + (((size_t)cur.img * p.Ho + yo0) * p.Wo + xo0) * p.C + c0;
+    const bool full = yo0 + R <= p.Ho && xo0 + CC <= p.Wo;
 #pragma unroll
-      for (int a = 0; a < TWT; ++a) {
-        const int xo = xo0 + a;
-        if (xo < p.Wo) {
-          float o[8];
+    for (int r = 0; r < R; ++r) {
+      T *oq = op;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 r = __ffma2_rn(acc[a][j], sc[j], sh[j]);
-            o[2 * j] = act_apply(r.x, p.act);
-            o[2 * j + 1] = act_apply(r.y, p.act);
-          }
-          Vec8<T>::store(out + (((size_t)img * p.Ho + yo) * p.Wo + xo) * p.C + c0, o);
-        }
+      for (int c = 0; c < CC; ++c) {
+        if (full || (yo0 + r < p.Ho && xo0 + c < p.Wo))
+          SmemVec4<T>::template store<ACT>(oq, __ffma2_rn(acc[r][c][0], sc[0], sh[0]), __ffma2_rn(acc[r][c][1], sc[1], sh[1]));
+        oq += opix;
       }
+      op += orow;
     }
-    __syncthreads();  // everyone is done with buffer `buf` before it is refilled two tiles from now
+    cur.advance(step, p.tiles_x, p.tiles_y);
+    __syncthreads();  // everyone is done with buffer `buf` before it is refilled at the top of the next iteration
+    if (++buf == p.stages) { buf = 0; phase ^= 1u; }
   }
 }
 
@@ -442,13 +494,12 @@ int depthwise_launch(bool f32, const void *in, void *out, const float *w9c, cons
 int depthwise_tma_geometry(bool f32, int n, int H, int W, int C, int stride, int dil, DwTileGeom *g) {
   const int es = f32 ? 4 : 2;
   const int cb = C * es <= 128 ? C : 128 / es;
-  if (C % cb != 0 || cb % 8 != 0) return LWP_EINVAL;
-  const int cv = cb / 8, pts = 256 / cv;
+  if (C % cb != 0 || (cb * es != 64 && cb * es != 128)) return LWP_EINVAL;   // other widths: the direct kernel
+  const int cq = cb / 4, blocks = 256 / cq;   // 2x4-pixel blocks per tile
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   long long best = -1;
-  for (int tw = 4; tw <= pts * 4; tw <<= 1) {
-    if (pts % (tw / 4)) continue;
-    const int th = pts / (tw / 4);
+  for (int bx = 1; bx <= blocks; bx <<= 1) {
+    const int tw = 4 * bx, th = 2 * (blocks / bx);
     const int iw = (tw - 1) * stride + 2 * dil + 1, ih = (th - 1) * stride + 2 * dil + 1;
     if (iw > 256 || ih > 256) continue;
     if ((long long)iw * ih * cb * es > 100 * 1024) continue;
@@ -458,9 +509,9 @@ int depthwise_tma_geometry(bool f32, int n, int H, int W, int C, int stride, int
     if (best < 0 || cost < best) { best = cost; g->tw = tw; g->th = th; g->iw = iw; g->ih = ih; }
   }
   if (best < 0) return LWP_EINVAL;
-  g->cb = cb; g->cv = cv; g->Ho = Ho; g->Wo = Wo;
+  g->cb = cb; g->cv = cq; g->Ho = Ho; g->Wo = Wo;
   g->tiles_x = ceil_div(Wo, g->tw); g->tiles_y = ceil_div(Ho, g->th); g->cblocks = C / cb;
-  g->num_tiles = n * g->tiles_x * g->tiles_y * g->cblocks;
+  g->num_tiles = n * g->tiles_x * g->tiles_y;   // spatial tiles per channel block
   g->stage_bytes = (uint32_t)(g->iw * g->ih * cb * es);
   return LWP_OK;
 }
@@ -468,27 +519,53 @@ int depthwise_tma_geometry(bool f32, int n, int H, int W, int C, int stride, int
 int depthwise_tma_init() {
   static bool done = false;
   if (done) return LWP_OK;
+#define LWP_DW_ATTR1(T, S, D, A) \
+  LWP_CUDA_CHECK(cudaFuncSetAttribute(depthwise3x3_tma_kernel<T, S, D, A, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024)); \
+  LWP_CUDA_CHECK(cudaFuncSetAttribute(depthwise3x3_tma_kernel<T, S, D, A, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024))
 #define LWP_DW_ATTR(T, S, D) \
-  LWP_CUDA_CHECK(cudaFuncSetAttribute(depthwise3x3_tma_kernel<T, S, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024))
+  LWP_DW_ATTR1(T, S, D, LWP_ACT_NONE); LWP_DW_ATTR1(T, S, D, LWP_ACT_RELU); LWP_DW_ATTR1(T, S, D, LWP_ACT_ELU)
   LWP_DW_ATTR(float, 1, 1); LWP_DW_ATTR(float, 2, 1); LWP_DW_ATTR(float, 1, 2);
   LWP_DW_ATTR(__nv_bfloat16, 1, 1); LWP_DW_ATTR(__nv_bfloat16, 2, 1); LWP_DW_ATTR(__nv_bfloat16, 1, 2);
 #undef LWP_DW_ATTR
+#undef LWP_DW_ATTR1
   done = true;
   return LWP_OK;
 }
 
 template <typename T>
 static int depthwise_tma_launch_t(const CUtensorMap &tm, T *out, const float *w9c, const float *scale,
-                                  const float *shift, const DwTileParams &p, int stride, int dil, cudaStream_t st) {
-  const size_t smem = 128 + 128 + 2 * (size_t)p.stage_bytes;
-  int per_sm = (int)((200 * 1024) / smem);
-  if (per_sm > 4) per_sm = 4;
-  if (per_sm < 1) per_sm = 1;
-  int grid = num_sms() * per_sm;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  if (stride == 1 && dil == 1) depthwise3x3_tma_kernel<T, 1, 1><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p);
-  else if (stride == 2 && dil == 1) depthwise3x3_tma_kernel<T, 2, 1><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p);
-  else if (stride == 1 && dil == 2) depthwise3x3_tma_kernel<T, 1, 2><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p);
+                                  const float *shift, DwTileParams p, int stride, int dil, cudaStream_t st) {
+  // two CTAs per SM with a ring of up to 4 halo boxes each; big (stride-2) boxes: one CTA per SM
+  int per_sm = 2;
+  int stages = (int)((100 * 1024) / p.stage_bytes);
+  if (stages < 2) { per_sm = 1; stages = (int)((200 * 1024) / p.stage_bytes); }
+  if (stages > kDwMaxStages) stages = kDwMaxStages;
+  if (stages < 2) { set_error("depthwise: halo box of %u bytes does not fit twice in shared memory", p.stage_bytes); return LWP_ECAP; }
+  if (const char *e = getenv("LWP_DW_STAGES")) { int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
+  p.stages = stages;
+  const size_t smem = 128 + 128 + (size_t)stages * p.stage_bytes;
+  int per_cblk = num_sms() * per_sm / p.cblocks;
+  if (per_cblk < 1) per_cblk = 1;
+  if (per_cblk > p.sp_tiles) per_cblk = p.sp_tiles;
+  const int grid = per_cblk * p.cblocks;
+  const int pixb = p.cb * (int)sizeof(T);
+  if (pixb != 64 && pixb != 128) { set_error("depthwise: %d bytes per tile pixel (need 64 or 128)", pixb); return LWP_EINVAL; }
+#define LWP_DW_GO(S_, D_)                                                                                             \
+  do {                                                                                                              \
+    if (pixb == 128) {                                                                                              \
+      if (p.act == LWP_ACT_RELU) depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_RELU, 128><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
+      else if (p.act == LWP_ACT_ELU) depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_ELU, 128><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
+      else depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_NONE, 128><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
+    } else {                                                                                                        \
+      if (p.act == LWP_ACT_RELU) depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_RELU, 64><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
+      else if (p.act == LWP_ACT_ELU) depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_ELU, 64><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
+      else depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_NONE, 64><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
+    }                                                                                                               \
+  } while (0)
+  if (stride == 1 && dil == 1) LWP_DW_GO(1, 1);
+  else if (stride == 2 && dil == 1) LWP_DW_GO(2, 1);
+  else if (stride == 1 && dil == 2) LWP_DW_GO(1, 2);
+#undef LWP_DW_GO
   else { set_error("depthwise: unsupported stride %d / dilation %d", stride, dil); return LWP_EINVAL; }
   LWP_LAUNCH_CHECK();
   return LWP_OK;
@@ -499,8 +576,8 @@ int depthwise_tma_launch(bool f32, const CUtensorMap &tm, void *out, const float
                          const DwTileGeom &g, cudaStream_t st) {
   DwTileParams p;
   p.n = n; p.H = H; p.W = W; p.C = C; p.Ho = g.Ho; p.Wo = g.Wo; p.tw = g.tw; p.th = g.th; p.iw = g.iw; p.ih = g.ih;
-  p.cb = g.cb; p.cv = g.cv; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y; p.cblocks = g.cblocks;
-  p.num_tiles = g.num_tiles; p.act = act; p.stage_bytes = g.stage_bytes;
+  p.cb = g.cb; p.cq = g.cv; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y; p.cblocks = g.cblocks;
+  p.sp_tiles = g.num_tiles; p.act = act; p.stage_bytes = g.stage_bytes; p.stages = 2;
   if (f32) return depthwise_tma_launch_t<float>(tm, (float *)out, w9c, scale, shift, p, stride, dil, st);
   return depthwise_tma_launch_t<__nv_bfloat16>(tm, (__nv_bfloat16 *)out, w9c, scale, shift, p, stride, dil, st);
 }

@@ -6,10 +6,13 @@
 //
 // Per 128-pixel tile and per 128-byte K block (64 bf16 / 32 tf32 channels):
 //   warp 0      TMA: the input halo box (tile + 2*dil rows/cols, zero-filled outside the image = the depthwise
-//               padding) and the K block of the 1x1 weights
+//               padding), the K block's depthwise constants (9 taps, folded BN scale/shift; a 1-D bulk copy into the
+//               same stage -- with the dynamic smem carve-out at its maximum there is no L1 left to serve them from
+//               global memory) and the K block of the 1x1 weights
 //   warps 6-13  depthwise: 8 channels x 4 columns per thread with a register window over the smem halo tile,
 //               fp32 FFMA2 accumulate, scale/shift/activation, round to the plan dtype, store into the K-major
 //               SWIZZLE_128B A tile (same bits the unfused depthwise kernel would have written to HBM)
+//   warp 14     TMA: the 1x1 weights ring (its own thread: the two rings must not throttle each other)
 //   warp 1      one thread issues tcgen05.mma (M = 128, N = Cout up to 512 as 1-2 instructions), fp32 in TMEM
 //   warps 2-5   epilogue: TMEM -> scale/shift/activation (+ residual) -> swizzled smem -> TMA tensor store
 // The depthwise output never exists in global memory: per block the HBM traffic is input + output only.
@@ -23,7 +26,8 @@ namespace lwp {
 
 constexpr int kDwpwEpiWarps = 4;   // the depthwise warps need the registers: one epilogue warp per TMEM lane quarter here
 constexpr int kDwWarp0 = 2 + kDwpwEpiWarps, kDwWarps = 8;   // warps 0/1: TMA / MMA, then epilogue warps, then depthwise warps
-constexpr int kDwpwThreads = (kDwWarp0 + kDwWarps) * 32;  // 448
+constexpr int kDwpwBWarp = kDwWarp0 + kDwWarps;            // last warp: TMA producer of the 1x1 weights
+constexpr int kDwpwThreads = (kDwpwBWarp + 1) * 32;        // 480
 
 struct DwpwSmem {
   uint32_t a_off, b_off, staging_off, in_off, scale_off, shift_off, bars_off, total;
@@ -70,8 +74,8 @@ template <> struct TileIn<true> {
     v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
   }
 };
-__device__ __forceinline__ void ldg4pairs(const float *p, float2 (&v)[4]) {
-  float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+__device__ __forceinline__ void ldg4pairs(const float *p, float2 (&v)[4]) {  // p: the K block's constants in shared memory
+  float4 a = reinterpret_cast<const float4 *>(p)[0], b = reinterpret_cast<const float4 *>(p)[1];
   v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
   v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
 }
@@ -81,8 +85,9 @@ __device__ __forceinline__ void ldg4pairs(const float *p, float2 (&v)[4]) {
 // activation and writes the four 16-byte (bf16) / 32-byte (fp32) pieces into the swizzled A tile.
 // All addressing is 32-bit; the activation is a compile-time choice.
 template <bool kTf32, int D, int ACT>
-__device__ __forceinline__ void dw_block(const uint8_t *in0, int row_bytes, const float *w0, int cin, const float *sc0,
-                                         const float *sh0, uint8_t *abuf, int r0, int cv) {
+__device__ __forceinline__ void dw_block(const uint8_t *in0, int row_bytes, const float *w0, int cin, uint8_t *abuf,
+                                         int r0, int cv) {
+  const float *sc0 = w0 + 9 * cin, *sh0 = w0 + 10 * cin;  // (cin = row stride of the constants block = kb_ch)
   constexpr int TWT = 4, NCOL = (TWT - 1) + 2 * D + 1;
   float2 acc[TWT][4];
 #pragma unroll
@@ -184,10 +189,11 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
   const int per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: input halo tiles + depthwise constants =====================
+    // (its own thread, so that input tiles run ahead of the depthwise warps independently of the weights ring)
     if (lane == 0) {
-      int is = 0, bs = 0;
-      uint32_t iph = 0, bph = 0;
+      int is = 0;
+      uint32_t iph = 0;
       bool ok = true;
       for (int t = blockIdx.x; t < p.m_tiles && ok; t += gridDim.x) {
         const int img = t / per_img, rem = t - img * per_img;
@@ -196,10 +202,23 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         for (int kb = 0; kb < p.kblocks; ++kb) {
           if (!ptx::mbar_wait(&in_empty[is], iph ^ 1u)) { ok = false; atomicExch(p.err_flag, 11); break; }
           ptx::mbar_arrive_expect_tx(&in_full[is], p.in_stage_bytes);
-          ptx::tma_load_4d(smem + L.in_off + (size_t)is * p.in_stage_bytes, &tmIn, &in_full[is], kb * p.kb_ch, x0 - D,
-                           y0 - D, img);
+          uint8_t *stage = smem + L.in_off + (size_t)is * p.in_stage_bytes;
+          ptx::tma_load_4d(stage, &tmIn, &in_full[is], kb * p.kb_ch, x0 - D, y0 - D, img);
+          ptx::bulk_load_1d(stage + p.in_tile_bytes, reinterpret_cast<const uint8_t *>(p.dw_consts) + (size_t)kb * p.dw_const_bytes,
+                            p.dw_const_bytes, &in_full[is]);
           if (++is == p.in_stages) { is = 0; iph ^= 1u; }
-          for (int h = 0; h < p.n_mma && ok; ++h) {  // the weights ring works in halves of N (<= 256 rows each)
+        }
+      }
+    }
+  } else if (warp == kDwpwBWarp) {
+    // ===================== TMA producer: 1x1 weights (ring in halves of N, <= 256 rows each) =====================
+    if (lane == 0) {
+      int bs = 0;
+      uint32_t bph = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < p.m_tiles && ok; t += gridDim.x) {
+        for (int kb = 0; kb < p.kblocks && ok; ++kb) {
+          for (int h = 0; h < p.n_mma; ++h) {
             if (!ptx::mbar_wait(&b_empty[bs], bph ^ 1u)) { ok = false; atomicExch(p.err_flag, 12); break; }
             ptx::mbar_arrive_expect_tx(&b_full[bs], p.b_stage_bytes);
             ptx::tma_load_2d(smem + L.b_off + (size_t)bs * p.b_stage_bytes, &tmB, &b_full[bs], kb * p.kb_ch,
@@ -300,15 +319,13 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
           const int c0 = kb * p.kb_ch + cv * 8;
           if (c0 < p.cin) {
             const uint8_t *in0 = sbuf + in_off0;
+            const float *wc = reinterpret_cast<const float *>(sbuf + p.in_tile_bytes) + cv * 8;
             if (p.dw_act == LWP_ACT_RELU)
-              dw_block<kTf32, D, LWP_ACT_RELU>(in0, row_bytes, p.dw_w9c + c0, p.cin, p.dw_scale + c0, p.dw_shift + c0, abuf,
-                                               r0, cv);
+              dw_block<kTf32, D, LWP_ACT_RELU>(in0, row_bytes, wc, p.kb_ch, abuf, r0, cv);
             else if (p.dw_act == LWP_ACT_ELU)
-              dw_block<kTf32, D, LWP_ACT_ELU>(in0, row_bytes, p.dw_w9c + c0, p.cin, p.dw_scale + c0, p.dw_shift + c0, abuf,
-                                              r0, cv);
+              dw_block<kTf32, D, LWP_ACT_ELU>(in0, row_bytes, wc, p.kb_ch, abuf, r0, cv);
             else
-              dw_block<kTf32, D, LWP_ACT_NONE>(in0, row_bytes, p.dw_w9c + c0, p.cin, p.dw_scale + c0, p.dw_shift + c0, abuf,
-                                               r0, cv);
+              dw_block<kTf32, D, LWP_ACT_NONE>(in0, row_bytes, wc, p.kb_ch, abuf, r0, cv);
           } else {
             // channels past Cin (a layer thinner than one K block): the GEMM weights there are zero-filled by TMA;
             // write zeros so no NaN garbage can reach the tensor core

@@ -17,9 +17,10 @@ struct DwpwParams {
   uint32_t idesc;
   int acc_stages;                 // 512 / cout_pad TMEM accumulator stages
   int in_stages, a_stages, b_stages, staging_bufs;
-  uint32_t in_stage_bytes, b_stage_bytes;
+  uint32_t in_stage_bytes, b_stage_bytes;   // in_stage_bytes = halo tile + the K block's depthwise constants
+  uint32_t in_tile_bytes, dw_const_bytes;   // dw constants of one K block: [9 taps | scale | shift][kb_ch] fp32
   int dw_act, act;
-  const float *dw_w9c, *dw_scale, *dw_shift;   // depthwise: [9][cin] weights, folded BN
+  const float *dw_consts;                      // depthwise: [kblocks][9 taps | scale | shift][kb_ch] fp32 (folded BN)
   const float *scale, *shift;                  // pointwise epilogue
   const void *residual;
   int res_ld;

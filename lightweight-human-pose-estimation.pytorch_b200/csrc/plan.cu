@@ -59,6 +59,7 @@ struct lwp_plan {
   int dtype;
   std::vector<lwp::Op> ops;
   int *err_flag = nullptr;
+  std::vector<void *> owned;   // device blobs built while recording (re-laid-out constants), freed with the plan
 };
 
 using namespace lwp;
@@ -85,6 +86,7 @@ extern "C" int lwp_plan_create(int dtype, lwp_plan **out) {
 extern "C" void lwp_plan_destroy(lwp_plan *p) {
   if (p == nullptr) return;
   if (p->err_flag) cudaFree(p->err_flag);
+  for (void *d : p->owned) cudaFree(d);
   delete p;
 }
 
@@ -244,11 +246,14 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   op.grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
   // CTA pairs (cta_group::2, M = 256): layers whose epilogue is the plain TMA-store one and that have enough tiles
   {
+    // default (measured, 64 x 368x656 bf16): pairs win on the 1x1 layers with 256-wide N tiles (512->512: 138 -> 122 us,
+    // the weight tile is half of the smem traffic there) and lose on the 128-wide 3x3 layers (90 -> 98 us)
     const char *e2 = getenv("LWP_GEMM_2CTA");
-    const int mode = e2 ? atoi(e2) : 0;   // 0 off, 1: 3x3 layers, 2: every eligible layer
+    const int mode = e2 ? atoi(e2) : -1;   // -1 default policy, 0 off, 1: 3x3 layers, 2: every eligible layer, 3: also small layers
     const bool plain = out != nullptr && out_f32 == nullptr && g.n_store % (kKBlockBytes / es) == 0;
-    if (mode > 0 && plain && g.block_n >= 128 && (mode >= 3 || g.m_tiles >= 2 * num_sms()) && (mode >= 2 || taps == 9) &&
-        conv_gemm2_init() == LWP_OK) {
+    const bool want = mode < 0 ? (taps == 1 && g.block_n == 256 && g.m_tiles >= 2 * num_sms())
+                               : (mode > 0 && g.block_n >= 128 && (mode >= 3 || g.m_tiles >= 2 * num_sms()) && (mode >= 2 || taps == 9));
+    if (want && plain && conv_gemm2_init() == LWP_OK) {
       op.two_cta = true;
       g.idesc = make_umma_idesc(tf32, 2 * kBlockM, g.block_n);
       const int stage2 = kATileBytes + (g.block_n / 2) * kKBlockBytes;
@@ -338,7 +343,26 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
   f.acc_stages = 512 / cout_pad;
   if (f.acc_stages > 4) f.acc_stages = 4;
   f.dw_act = dw_act; f.act = act;
-  f.dw_w9c = dw_w; f.dw_scale = dw_scale; f.dw_shift = dw_shift; f.scale = scale; f.shift = shift;
+  f.scale = scale; f.shift = shift;
+  {
+    // depthwise constants re-laid-out per K block: [kblocks][9 taps | scale | shift][kb_ch] fp32, zero beyond Cin, so
+    // that one 1-D bulk copy per K block brings them into the input stage
+    f.dw_const_bytes = (uint32_t)(11 * kb_ch * sizeof(float));
+    const size_t blob = (size_t)f.kblocks * f.dw_const_bytes;
+    float *d = nullptr;
+    LWP_CUDA_CHECK(cudaMalloc(&d, blob));
+    p->owned.push_back(d);
+    LWP_CUDA_CHECK(cudaMemset(d, 0, blob));
+    for (int kb = 0; kb < f.kblocks; ++kb) {
+      const int c0 = kb * kb_ch, nc = Cin - c0 < kb_ch ? Cin - c0 : kb_ch;
+      float *dst = d + (size_t)kb * 11 * kb_ch;
+      LWP_CUDA_CHECK(cudaMemcpy2D(dst, kb_ch * sizeof(float), dw_w + c0, (size_t)Cin * sizeof(float), nc * sizeof(float), 9,
+                                  cudaMemcpyDeviceToDevice));
+      LWP_CUDA_CHECK(cudaMemcpy(dst + 9 * kb_ch, dw_scale + c0, nc * sizeof(float), cudaMemcpyDeviceToDevice));
+      LWP_CUDA_CHECK(cudaMemcpy(dst + 10 * kb_ch, dw_shift + c0, nc * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    f.dw_consts = d;
+  }
   f.residual = residual; f.res_ld = res_ld; f.err_flag = p->err_flag;
   f.debug = getenv("LWP_DEBUG_DWPW") ? atoi(getenv("LWP_DEBUG_DWPW")) : 0;
   // tile: rectangle of 128 pixels, width a multiple of 4 (a depthwise thread owns 4 consecutive columns)
@@ -354,7 +378,8 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
   LWP_REQUIRE(best >= 0, "lwp_plan_add_dwpw: no tile shape fits");
   f.tiles_x = ceil_div(W, f.tile_w); f.tiles_y = ceil_div(H, f.tile_h);
   f.m_tiles = n * f.tiles_x * f.tiles_y;
-  f.in_stage_bytes = (uint32_t)(f.iw * f.ih * kKBlockBytes);
+  f.in_tile_bytes = (uint32_t)(f.iw * f.ih * kKBlockBytes);
+  f.in_stage_bytes = f.in_tile_bytes + f.dw_const_bytes;
   f.b_stage_bytes = (uint32_t)(f.n_per_mma * kKBlockBytes);  // the weights ring works in halves of N when N > 256
   // shared-memory budget: prefer deep B / A rings, then a second input stage, then double-buffered staging
   f.b_stages = f.n_mma + 1; f.a_stages = 2; f.in_stages = 1; f.staging_bufs = 1;

@@ -171,7 +171,12 @@ class Plan:
         handle = _lib._c_void_p()
         _lib.check(self.lib.lwp_plan_create(code, handle), "lwp_plan_create")
         self.handle = handle
-        self.fuse_dwpw = os.environ.get("LWP_NO_DWPW_FUSION") is None
+        # depthwise -> 1x1 fusion policy: the two-kernel form (TMA depthwise at ~75 % of HBM peak + tcgen05 GEMM at ~50 %
+        # tensor pipe) is faster than the fused block on every layer of this network, so fusion is opt-in:
+        # LWP_DWPW_FUSION=1 fuses every block the fused kernel can take, or a comma-separated list of op names
+        fuse = os.environ.get("LWP_DWPW_FUSION", "0")
+        self.fuse_dwpw = fuse not in ("", "0")
+        self.fuse_only = None if fuse in ("", "0", "1", "all") else set(fuse.split(","))
         self.bufs = []
         self.op_names = []
         self.op_meta = []  # per op: kind, algorithmic flops and bytes (real channel counts, no padding)
@@ -221,9 +226,11 @@ class Plan:
         self.op_meta.append(dict(kind="depthwise", flops=2.0 * 9 * n * ho * wo * d.c,
                                  bytes=float((n * H * W * d.c + n * ho * wo * d.c) * es + 9 * d.c * 4)))
 
-    def _fusable(self, d, g):
-        """Depthwise (stride 1) + pointwise pair that the fused tcgen05 kernel can take."""
+    def _fusable(self, d, g, name=None):
+        """Depthwise (stride 1) + pointwise pair that the fused tcgen05 kernel can take (and the policy asks for)."""
         kb_ch = 64 if self.tdtype == torch.bfloat16 else 32
+        if self.fuse_only is not None and name not in self.fuse_only:
+            return False
         return (self.fuse_dwpw and d.stride == 1 and d.dilation in (1, 2) and g.taps == 1 and d.c == g.cin
                 and (d.c % kb_ch == 0 or d.c < kb_ch) and d.c % 8 == 0 and g.cout_pad <= 512
                 and 512 % g.cout_pad == 0)
@@ -277,7 +284,7 @@ class Plan:
         for i, (dw, pw) in enumerate(P.backbone):
             ho, wo = (hh - 1) // dw.stride + 1, (ww - 1) // dw.stride + 1
             # fused: the depthwise result goes straight into the GEMM's smem A operand
-            if self._fusable(dw, pw) and self._dwpw("model.%d.dwpw" % (i + 1), pp[cur], dw, pw, n, hh, ww, pp[cur ^ 1],
+            if self._fusable(dw, pw, "model.%d.dwpw" % (i + 1)) and self._dwpw("model.%d.dwpw" % (i + 1), pp[cur], dw, pw, n, hh, ww, pp[cur ^ 1],
                                                     pw.cout_pad):
                 cur ^= 1
             else:
@@ -303,7 +310,7 @@ class Plan:
             last = i == len(P.cpm_trunk) - 1
             res = A if last else None  # x + trunk(x) fused into the last epilogue
             dst = t1 if src is t0 else t0
-            if self._fusable(dw, pw) and self._dwpw("cpm.trunk.%d.dwpw" % i, src, dw, pw, n, h, w, dst, nc,
+            if self._fusable(dw, pw, "cpm.trunk.%d.dwpw" % i) and self._dwpw("cpm.trunk.%d.dwpw" % i, src, dw, pw, n, h, w, dst, nc,
                                                     residual=res, res_ld=nc):
                 pass
             else:
