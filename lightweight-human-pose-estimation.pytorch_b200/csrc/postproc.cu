@@ -117,6 +117,33 @@ __device__ __forceinline__ void upsampled_at(const UpSrc &u, int img, int e, int
   for (int c = 0; c < NCH; ++c) out[c] = cubic_vsum(T[c], cy, d * u.c_layout + ch[c] < body);
 }
 
+// Same arithmetic as upsampled_at<2>, source = this block's copy of the two PAF channels in shared memory
+// ([h][w] float2): one LDS.64 per tap serves both channels.
+__device__ __forceinline__ void upsampled_at_smem2(const UpSrc &u, const float2 *s, int e, int d, int ch0, int ch1,
+                                                   float (&out)[2]) {
+  float cx[4], cy[4];
+  const int sx = cubic_axis(d, u.scale_x, cx);
+  const int sy = cubic_axis(e, u.scale_y, cy);
+  const bool border = (sx < 1) || (sx + 2 >= u.w);
+  const int i0 = clampi(sx - 1, 0, u.w - 1), i1 = clampi(sx, 0, u.w - 1);
+  const int i2 = clampi(sx + 1, 0, u.w - 1), i3 = clampi(sx + 2, 0, u.w - 1);
+  const int rowlen = u.W * u.c_layout;
+  const int body = rowlen - (rowlen & 3);
+  float T[2][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float2 *p = s + clampi(sy - 1 + r, 0, u.h - 1) * u.w;
+    const float2 a0 = p[i0], a1 = p[i1], a2 = p[i2], a3 = p[i3];
+    float x0 = __fmul_rn(a0.x, cx[0]), x1 = __fmul_rn(a1.x, cx[1]), x2 = __fmul_rn(a2.x, cx[2]), x3 = __fmul_rn(a3.x, cx[3]);
+    float y0 = __fmul_rn(a0.y, cx[0]), y1 = __fmul_rn(a1.y, cx[1]), y2 = __fmul_rn(a2.y, cx[2]), y3 = __fmul_rn(a3.y, cx[3]);
+    float vx = border ? __fadd_rn(0.f, x0) : x0, vy = border ? __fadd_rn(0.f, y0) : y0;
+    vx = __fadd_rn(vx, x1); vx = __fadd_rn(vx, x2); T[0][r] = __fadd_rn(vx, x3);
+    vy = __fadd_rn(vy, y1); vy = __fadd_rn(vy, y2); T[1][r] = __fadd_rn(vy, y3);
+  }
+  out[0] = cubic_vsum(T[0], cy, d * u.c_layout + ch0 < body);
+  out[1] = cubic_vsum(T[1], cy, d * u.c_layout + ch1 < body);
+}
+
 __global__ void __launch_bounds__(256)
 upsample_cubic_kernel(const UpSrc u, float *__restrict__ dst, long long total) {
   const int rowlen = u.W * u.c_layout;
@@ -183,7 +210,7 @@ constexpr int kPkCols = 30, kPkRows = 32, kPkSrcMax = 16, kPkWarps = 6, kPkMaxCh
 __global__ void __launch_bounds__(kPkWarps * 32)
 peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__restrict__ cand,
                              int *__restrict__ cand_count, int cap, int *__restrict__ overflow) {
-  __shared__ float s_cy[kPkRows + 2][4];
+  __shared__ __align__(16) float s_cy[kPkRows + 2][4];
   __shared__ int s_sy[kPkRows + 2];
   __shared__ int s_win[4];  // sx_lo, ncols, sy_lo, nrows
   extern __shared__ float pk_smem[];
@@ -225,11 +252,21 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
     return;
   }
   // 1. source window -> smem [ry][c][rx]; replicate border by clamping the coordinates
-  for (int idx = tid; idx < nrows * ncols * n_ch; idx += blockDim.x) {
-    const int c = idx % n_ch, rx = (idx / n_ch) % ncols, ry = idx / (n_ch * ncols);
-    s_src[((size_t)ry * n_ch + c) * kPkSrcMax + rx] =
-        __ldg(u.src + (((size_t)img * u.h + clampi(sy_lo + ry, 0, u.h - 1)) * u.w + clampi(sx_lo + rx, 0, u.w - 1)) *
-                          (size_t)u.ld + c);
+  {
+    // (channel, column, row) of this thread's first element, then advanced by blockDim.x elements without divisions
+    int c = tid % n_ch, rx = (tid / n_ch) % ncols, ry = tid / (n_ch * ncols);
+    const int dc = (int)blockDim.x % n_ch, dpos = (int)blockDim.x / n_ch;
+    const int drx = dpos % ncols, dry = dpos / ncols;
+    const float *src_img = u.src + (size_t)img * u.h * u.w * u.ld;
+    for (int idx = tid; idx < nrows * ncols * n_ch; idx += blockDim.x) {
+      s_src[(ry * n_ch + c) * kPkSrcMax + rx] =
+          __ldg(src_img + (size_t)((clampi(sy_lo + ry, 0, u.h - 1) * u.w + clampi(sx_lo + rx, 0, u.w - 1)) * u.ld + c));
+      c += dc;
+      int carry = 0;
+      if (c >= n_ch) { c -= n_ch; carry = 1; }
+      rx += drx + carry; ry += dry;
+      if (rx >= ncols) { rx -= ncols; ++ry; }
+    }
   }
   __syncthreads();
   // 2. horizontal pass: T[ry][c][lane]
@@ -256,25 +293,40 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
   for (int c = warp; c < n_ch; c += kPkWarps) {
     const bool simd_body = d * u.c_layout + c < body;
     float v0 = 0.f, v1 = 0.f;  // rows i-2, i-1
+    // the four horizontally-resized source rows of the current output row stay in registers: consecutive output
+    // rows share them (x4: four rows per source row), a step of one source row shifts the window by one load
+    float T[4] = {0.f, 0.f, 0.f, 0.f};
+    int cur_sy = kInvalid;
     for (int i = 0; i < kPkRows + 2; ++i) {
-      const int sy = s_sy[i];
+      const int sy = s_sy[i];                   // warp-uniform
       float v2 = 0.f;
-      if (sy != kInvalid && col_ok) {
-        const float *t = s_T + ((size_t)(sy - 1 - sy_lo) * n_ch + c) * 32 + lane;
-        const float T[4] = {t[0], t[n_ch * 32], t[2 * n_ch * 32], t[3 * n_ch * 32]};
-        const float cyv[4] = {s_cy[i][0], s_cy[i][1], s_cy[i][2], s_cy[i][3]};
-        v2 = thr01(cubic_vsum(T, cyv, simd_body));
+      if (sy != kInvalid) {
+        if (sy != cur_sy) {
+          const float *t = s_T + ((size_t)(sy - 1 - sy_lo) * n_ch + c) * 32 + lane;
+          if (sy == cur_sy + 1) {
+            T[0] = T[1]; T[1] = T[2]; T[2] = T[3]; T[3] = t[3 * n_ch * 32];
+          } else {
+            T[0] = t[0]; T[1] = t[n_ch * 32]; T[2] = t[2 * n_ch * 32]; T[3] = t[3 * n_ch * 32];
+          }
+          cur_sy = sy;
+        }
+        const float4 cy4 = *reinterpret_cast<const float4 *>(s_cy[i]);
+        const float cyv[4] = {cy4.x, cy4.y, cy4.z, cy4.w};
+        if (col_ok) v2 = thr01(cubic_vsum(T, cyv, simd_body));
       }
-      const float vl = __shfl_up_sync(0xffffffffu, v1, 1), vr = __shfl_down_sync(0xffffffffu, v1, 1);
-      // centre = row i-1 (tile rows are i-1 in [1, kPkRows]), interior lanes only
-      if (i >= 2 && lane >= 1 && lane <= kPkCols && col_ok && v1 > 0.f && v1 > vl && v1 > vr && v1 > v0 && v1 > v2) {
-        const int e = oy0 - 1 + (i - 1);
-        if (e < u.H) {
-          int slot = atomicAdd(&cand_count[img * n_ch + c], 1);
-          if (slot < cap) {
-            unsigned long long key =
-                ((unsigned long long)(((unsigned)d << 16) | (unsigned)e) << 32) | __float_as_uint(v1);
-            cand[((size_t)img * n_ch + c) * cap + slot] = key;
+      // centre = row i-1 (tile rows are i-1 in [1, kPkRows]), interior lanes only; rows without any value >= 0.1
+      // (the common case) skip the neighbour exchange altogether
+      if (i >= 2 && __any_sync(0xffffffffu, v1 > 0.f)) {
+        const float vl = __shfl_up_sync(0xffffffffu, v1, 1), vr = __shfl_down_sync(0xffffffffu, v1, 1);
+        if (lane >= 1 && lane <= kPkCols && col_ok && v1 > 0.f && v1 > vl && v1 > vr && v1 > v0 && v1 > v2) {
+          const int e = oy0 - 1 + (i - 1);
+          if (e < u.H) {
+            int slot = atomicAdd(&cand_count[img * n_ch + c], 1);
+            if (slot < cap) {
+              unsigned long long key =
+                  ((unsigned long long)(((unsigned)d << 16) | (unsigned)e) << 32) | __float_as_uint(v1);
+              cand[((size_t)img * n_ch + c) * cap + slot] = key;
+            }
           }
         }
       }
@@ -407,11 +459,40 @@ struct ConnBefore {  // ratio descending; ties keep (i, j) generation order (sta
   }
 };
 
-// PAF line integral: a warp scores 3 candidate pairs at a time, 10 lanes per pair, lane k takes
-// sample k of linspace2d; the sum is then re-done in k order so the float64 result is the
-// reference's.  grid = (blocks per limb, 19 limbs, images).
-template <bool kFused>
-__global__ void __launch_bounds__(256)
+// One sample of the line integral: point k of linspace2d(a, b, 10) (modules/keypoints.py:11-13,119-131), the PAF
+// vector there (on-the-fly cubic from the stride-8 map when kFused) projected on the unit limb vector.
+template <bool kFused, bool kSmem>
+__device__ __forceinline__ double paf_sample(const float *paf, int W, int ld, const UpSrc &up, const float2 *s_src, int img,
+                                             int demo, int ax, int ay, int vx, int vy, double ux, double uy, int k, int cx,
+                                             int cy) {
+  const double fx = __dadd_rn(__dmul_rn(__dmul_rn(1.0 / 9, (double)vx), (double)k), (double)ax);
+  const double fy = __dadd_rn(__dmul_rn(__dmul_rn(1.0 / 9, (double)vy), (double)k), (double)ay);
+  const int ix = demo ? __double2int_rz(fx) : __double2int_rn(fx);
+  const int iy = demo ? __double2int_rz(fy) : __double2int_rn(fy);
+  float pv[2];
+  if constexpr (kFused) {  // the up-sampled PAF pixel is computed on the fly, bit-identical to the materialised map
+    if constexpr (kSmem) {
+      upsampled_at_smem2(up, s_src, iy, ix, cx, cy, pv);
+    } else {
+      const int ch[2] = {cx, cy};
+      upsampled_at<2>(up, img, iy, ix, ch, pv);
+    }
+  } else {
+    const float *pp = paf + ((size_t)iy * W + ix) * ld;
+    pv[0] = __ldg(pp + cx); pv[1] = __ldg(pp + cy);
+  }
+  return __dadd_rn(__dmul_rn(ux, (double)pv[0]), __dmul_rn(uy, (double)pv[1]));
+}
+
+// PAF line integral in two phases.  A connection needs at least 9 of its 10 samples above min_paf_score
+// (success_ratio > 0.8, keypoints.py:137), so a pair whose two probe samples (k = 3 and k = 6, interior points of
+// the segment) both fail can never be one: phase 1 gives every lane one candidate pair and evaluates only the probes;
+// phase 2 scores the surviving pairs in full, 3 at a time, 10 lanes per pair, lane k taking sample k of linspace2d;
+// the sum is then re-done in k order so the float64 result is the reference's.  Which pairs are connections and
+// their ratios are exactly the reference's; only work on hopeless pairs is skipped.
+// grid = (blocks per limb, 19 limbs, images).
+template <bool kFused, bool kSmem>   // kSmem (fused only): the limb's two stride-8 PAF channels are staged in shared memory
+__global__ void __launch_bounds__(128)
 paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ counts, int cap_kpts,
                  const float *__restrict__ pafs, int H, int W, int ld, const UpSrc up, int demo,
                  double min_paf_score, Conn *__restrict__ conn, int *__restrict__ conn_count, int cap_conn) {
@@ -429,53 +510,80 @@ paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ 
   const double height_n = (double)(H / 2);  // pafs.shape[0] // 2
   Conn *out = conn + ((size_t)img * LWP_NUM_LIMBS + limb) * cap_conn;
   int *out_count = conn_count + img * LWP_NUM_LIMBS + limb;
+  if (blockIdx.x * wpb * 32 >= total) return;   // no pair for this block
+  extern __shared__ __align__(16) unsigned char ps_smem[];
+  const float2 *s_src = reinterpret_cast<const float2 *>(ps_smem);
+  if constexpr (kFused && kSmem) {
+    float2 *s_w = reinterpret_cast<float2 *>(ps_smem);
+    const float *src = up.src + (size_t)img * up.h * up.w * up.ld;
+    for (int idx = threadIdx.x; idx < up.h * up.w; idx += blockDim.x) {
+      const float *pp = src + (size_t)idx * up.ld;
+      s_w[idx] = make_float2(__ldg(pp + cx), __ldg(pp + cy));
+    }
+    __syncthreads();
+  }
 
-  for (int base = (blockIdx.x * wpb + warp) * 3; base < total; base += gridDim.x * wpb * 3) {
-    const int p = base + g;
-    const bool active = g < 3 && p < total;
-    int i = 0, j = 0;
-    double v = 0.0, ux = 0.0, uy = 0.0, norm = 0.0;
-    bool pass = false;
-    if (active) {
-      i = p / nB; j = p - i * nB;
-      lwp_keypoint a = A[i], b = B[j];
-      int vx = b.x - a.x, vy = b.y - a.y;
-      norm = __dsqrt_rn((double)((long long)vx * vx + (long long)vy * vy));
+  for (int base = (blockIdx.x * wpb + warp) * 32; base < total; base += gridDim.x * wpb * 32) {
+    // ---- phase 1: lane = pair, two probe samples ----
+    const int p1 = base + lane;
+    bool survive = false;
+    if (p1 < total) {
+      const int i = p1 / nB, j = p1 - i * nB;
+      const lwp_keypoint a = A[i], b = B[j];
+      const int vx = b.x - a.x, vy = b.y - a.y;
+      const double norm = __dsqrt_rn((double)((long long)vx * vx + (long long)vy * vy));
       if (norm != 0.0) {
-        ux = __ddiv_rn((double)vx, norm);
-        uy = __ddiv_rn((double)vy, norm);
-        double fx = __dadd_rn(__dmul_rn(__dmul_rn(1.0 / 9, (double)vx), (double)k), (double)a.x);
-        double fy = __dadd_rn(__dmul_rn(__dmul_rn(1.0 / 9, (double)vy), (double)k), (double)a.y);
-        int ix = demo ? __double2int_rz(fx) : __double2int_rn(fx);
-        int iy = demo ? __double2int_rz(fy) : __double2int_rn(fy);
-        float pv[2];
-        if constexpr (kFused) {  // the up-sampled PAF pixel is computed on the fly, bit-identical to the materialised map
-          const int ch[2] = {cx, cy};
-          upsampled_at<2>(up, img, iy, ix, ch, pv);
-        } else {
-          const float *pp = paf + ((size_t)iy * W + ix) * ld;
-          pv[0] = __ldg(pp + cx); pv[1] = __ldg(pp + cy);
-        }
-        v = __dadd_rn(__dmul_rn(ux, (double)pv[0]), __dmul_rn(uy, (double)pv[1]));
-        pass = v > min_paf_score;
+        const double ux = __ddiv_rn((double)vx, norm), uy = __ddiv_rn((double)vy, norm);
+        survive = paf_sample<kFused, kSmem>(paf, W, ld, up, s_src, img, demo, a.x, a.y, vx, vy, ux, uy, 3, cx, cy) > min_paf_score;
+        if (!survive)
+          survive = paf_sample<kFused, kSmem>(paf, W, ld, up, s_src, img, demo, a.x, a.y, vx, vy, ux, uy, 6, cx, cy) > min_paf_score;
       }
     }
-    double sum = 0.0;
-    int cnt = 0;
+    unsigned alive = __ballot_sync(0xffffffffu, survive);
+    // ---- phase 2: full score of the survivors, 3 pairs x 10 lanes per pass ----
+    while (alive != 0u) {
+      int src = -1;   // lane of phase 1 that holds this group's pair
+      {
+        unsigned m = alive;
 #pragma unroll
-    for (int kk = 0; kk < 10; ++kk) {
-      int srcl = (g * 10 + kk) & 31;
-      double vk = __shfl_sync(0xffffffffu, v, srcl);
-      int pk = __shfl_sync(0xffffffffu, (int)pass, srcl);
-      if (pk) { sum = __dadd_rn(sum, vk); ++cnt; }
-    }
-    if (active && k == 0 && norm != 0.0) {
-      double ratio = cnt > 0 ? __ddiv_rn(sum, (double)cnt) : 0.0;
-      double pen = __dsub_rn(__ddiv_rn(height_n, norm), 1.0);
-      if (pen < 0.0) ratio = __dadd_rn(ratio, pen);
-      if (ratio > 0.0 && cnt >= 9) {  // success_ratio = cnt / 10 > 0.8
-        int slot = atomicAdd(out_count, 1);
-        if (slot < cap_conn) { Conn c; c.ratio = ratio; c.i = i; c.j = j; out[slot] = c; }
+        for (int q = 0; q < 3; ++q) {
+          const int bpos = m ? __ffs(m) - 1 : -1;
+          if (q == g) src = bpos;
+          if (m) m &= m - 1;
+        }
+        alive = m;
+      }
+      const bool active = g < 3 && src >= 0;
+      const int p = base + (active ? src : 0);
+      int i = 0, j = 0;
+      double v = 0.0, norm = 0.0;
+      bool pass = false;
+      if (active) {
+        i = p / nB; j = p - i * nB;
+        const lwp_keypoint a = A[i], b = B[j];
+        const int vx = b.x - a.x, vy = b.y - a.y;
+        norm = __dsqrt_rn((double)((long long)vx * vx + (long long)vy * vy));
+        const double ux = __ddiv_rn((double)vx, norm), uy = __ddiv_rn((double)vy, norm);
+        v = paf_sample<kFused, kSmem>(paf, W, ld, up, s_src, img, demo, a.x, a.y, vx, vy, ux, uy, k, cx, cy);
+        pass = v > min_paf_score;
+      }
+      double sum = 0.0;
+      int cnt = 0;
+#pragma unroll
+      for (int kk = 0; kk < 10; ++kk) {
+        int srcl = (g * 10 + kk) & 31;
+        double vk = __shfl_sync(0xffffffffu, v, srcl);
+        int pk = __shfl_sync(0xffffffffu, (int)pass, srcl);
+        if (pk) { sum = __dadd_rn(sum, vk); ++cnt; }
+      }
+      if (active && k == 0) {
+        double ratio = cnt > 0 ? __ddiv_rn(sum, (double)cnt) : 0.0;
+        double pen = __dsub_rn(__ddiv_rn(height_n, norm), 1.0);
+        if (pen < 0.0) ratio = __dadd_rn(ratio, pen);
+        if (ratio > 0.0 && cnt >= 9) {  // success_ratio = cnt / 10 > 0.8
+          int slot = atomicAdd(out_count, 1);
+          if (slot < cap_conn) { Conn c; c.ratio = ratio; c.i = i; c.j = j; out[slot] = c; }
+        }
       }
     }
   }
@@ -834,14 +942,24 @@ static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *cou
   bx = bx < 8 ? 8 : (bx > 32 ? 32 : bx);
   UpSrc u0;
   memset(&u0, 0, sizeof(u0));
-  if (fused)
-    paf_score_kernel<true><<<dim3(bx, LWP_NUM_LIMBS, n), 256, 0, st>>>(kpts, counts, cap_kpts, nullptr, H, W, paf_ld, *up,
-                                                                       demo, min_paf_score, w.conn, w.conn_count,
-                                                                       cap_connections);
-  else
-    paf_score_kernel<false><<<dim3(bx, LWP_NUM_LIMBS, n), 256, 0, st>>>(kpts, counts, cap_kpts, pafs, H, W, paf_ld, u0,
-                                                                        demo, min_paf_score, w.conn, w.conn_count,
-                                                                        cap_connections);
+  if (fused) {
+    const size_t src_bytes = (size_t)up->h * up->w * sizeof(float2);   // the limb's two PAF channels of one image
+    static bool ps_attr = false;
+    if (!ps_attr) {
+      LWP_CUDA_CHECK(cudaFuncSetAttribute(paf_score_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      ps_attr = true;
+    }
+    if (src_bytes <= 200 * 1024)
+      paf_score_kernel<true, true><<<dim3(bx, LWP_NUM_LIMBS, n), 128, src_bytes, st>>>(
+          kpts, counts, cap_kpts, nullptr, H, W, paf_ld, *up, demo, min_paf_score, w.conn, w.conn_count, cap_connections);
+    else
+      paf_score_kernel<true, false><<<dim3(bx, LWP_NUM_LIMBS, n), 128, 0, st>>>(
+          kpts, counts, cap_kpts, nullptr, H, W, paf_ld, *up, demo, min_paf_score, w.conn, w.conn_count, cap_connections);
+  } else {
+    paf_score_kernel<false, false><<<dim3(bx, LWP_NUM_LIMBS, n), 128, 0, st>>>(kpts, counts, cap_kpts, pafs, H, W, paf_ld, u0,
+                                                                               demo, min_paf_score, w.conn, w.conn_count,
+                                                                               cap_connections);
+  }
   LWP_LAUNCH_CHECK();
   static bool attr_set = false;
   if (!attr_set) {
