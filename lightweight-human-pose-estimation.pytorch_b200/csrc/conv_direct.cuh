@@ -7,6 +7,10 @@
 namespace lwp {
 int stem_launch(bool f32, const void *x, bool x_is_u8, const double *mean3, double img_scale, const float *w,
                 const float *scale, const float *shift, void *out, int n, int H, int W, cudaStream_t st);
+// the same layer as an im2col GEMM on tcgen05 (stem_gemm.cu); err_flag: the plan's pipeline-timeout flag
+int stem_gemm_launch(bool f32, const void *x, bool x_is_u8, const double *mean3, double img_scale, const float *w,
+                     const float *scale, const float *shift, void *out, int n, int H, int W, int *err_flag,
+                     cudaStream_t st);
 int depthwise_launch(bool f32, const void *in, void *out, const float *w9c, const float *scale, const float *shift,
                      int n, int H, int W, int C, int stride, int dil, int act, cudaStream_t st);
 struct DwTileGeom {

@@ -59,6 +59,7 @@ struct lwp_plan {
   int dtype;
   std::vector<lwp::Op> ops;
   int *err_flag = nullptr;
+  bool stem_direct = false;
   std::vector<void *> owned;   // device blobs built while recording (re-laid-out constants), freed with the plan
 };
 
@@ -76,6 +77,7 @@ extern "C" int lwp_plan_create(int dtype, lwp_plan **out) {
   if (rc != LWP_OK) return rc;
   lwp_plan *p = new lwp_plan();
   p->dtype = dtype;
+  p->stem_direct = getenv("LWP_STEM_DIRECT") != nullptr && atoi(getenv("LWP_STEM_DIRECT")) != 0;
   cudaError_t e = cudaMalloc(&p->err_flag, sizeof(int));
   if (e != cudaSuccess) { delete p; set_error("cudaMalloc err_flag: %s", cudaGetErrorString(e)); return LWP_ECUDA; }
   cudaMemset(p->err_flag, 0, sizeof(int));
@@ -442,7 +444,11 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const void *x, int first, int las
     switch (op.kind) {
       case OP_STEM:
         LWP_REQUIRE(x != nullptr, "lwp_plan_run: the plan has a stem but x is NULL");
-        rc = stem_launch(f32, x, op.stem_u8, op.mean, op.img_scale, op.w, op.scale, op.shift, op.out, op.n, op.H, op.W, st);
+        if (p->stem_direct)   // LWP_STEM_DIRECT=1: the CUDA-core FFMA2 kernel (fp32 inputs and weights, not rounded to the plan dtype)
+          rc = stem_launch(f32, x, op.stem_u8, op.mean, op.img_scale, op.w, op.scale, op.shift, op.out, op.n, op.H, op.W, st);
+        else
+          rc = stem_gemm_launch(f32, x, op.stem_u8, op.mean, op.img_scale, op.w, op.scale, op.shift, op.out, op.n, op.H,
+                                op.W, p->err_flag, st);
         break;
       case OP_DW:
         if (op.dw_tma)

@@ -191,9 +191,16 @@ def test_fused_dwpw_vs_torch(env, precision, shape):
     assert _rel(got, ref) < tol * max(1.0, float(ref.abs().max())), _rel(got, ref)
 
 
+@pytest.mark.parametrize("impl", ["gemm", "direct"])
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
-def test_stem_vs_torch(env, precision):
+def test_stem_vs_torch(env, precision, impl, monkeypatch):
+    """Stem conv: the default im2col tcgen05 GEMM (inputs and weights rounded to the plan dtype: TF32 / bf16
+    products, fp32 accumulate) and the opt-in direct FFMA kernel (LWP_STEM_DIRECT=1, fp32 products)."""
     torch, _lib, engine = env
+    if impl == "direct":
+        monkeypatch.setenv("LWP_STEM_DIRECT", "1")
+    else:
+        monkeypatch.delenv("LWP_STEM_DIRECT", raising=False)
     g = torch.Generator().manual_seed(11)
     tdtype = engine._PREC[precision][1]
     n, H, W = 2, 48, 72
@@ -208,8 +215,9 @@ def test_stem_vs_torch(env, precision):
     _lib.check(p.L.lwp_plan_add_stem(p.h, wd.data_ptr(), sc.data_ptr(), sh.data_ptr(), out.data_ptr(), n, H, W), "add")
     p.run(xd)
     got = out.permute(0, 3, 1, 2).float().cpu()
+    assert p.L.lwp_plan_error_flag(p.h) == 0
     p.close()
-    tol = 1e-5 if precision == "tf32" else 2e-2
+    tol = 2e-2 if precision == "bf16" else (1e-5 if impl == "direct" else 6e-3)
     assert _rel(got, ref) < tol * max(1.0, float(ref.abs().max()))
 
 
@@ -262,6 +270,29 @@ def test_forward_rejects_cpu_tensors(env):
     net = PoseEstimationWithMobileNet(1).eval().cuda()
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 3, 64, 64))
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_fused_dwpw_network(env, precision, monkeypatch):
+    """Opt-in fused depthwise -> 1x1 blocks (LWP_DWPW_FUSION=1; the default is the two-kernel form): the whole
+    network still matches the reference golden outputs."""
+    torch, _lib, engine = env
+    from lwpose_b200 import synth
+    monkeypatch.setenv("LWP_DWPW_FUSION", "1")
+    name, R, H, W, B, gain = gc.net_cases()[1]
+    g = gc.load("net_golden.npz")
+    net = _build_net(torch, name, R, gain).cuda()
+    net.precision = precision
+    x = synth.synthetic_net_input(B, H, W, seed=3).cuda()
+    outs = net(x)
+    torch.cuda.synchronize()
+    plan = net.engine().plan(precision, B, H, W)
+    assert plan.error_flag() == 0
+    assert any(nm.endswith(".dwpw") for nm in plan.op_names)
+    tol = 3e-3 if precision == "tf32" else 3e-2
+    for i, y in enumerate(outs):
+        ref = torch.from_numpy(g["net_%s_out%d" % (name, i)])
+        assert _rel(y.cpu(), ref) < tol, i
 
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
