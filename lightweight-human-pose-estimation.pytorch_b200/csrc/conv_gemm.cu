@@ -30,12 +30,12 @@ struct SmemLayout {
   uint32_t scale_off, shift_off, bars_off, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int block_n, int num_stages, int cout_pad) {
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int num_stages, int cout_pad, int kb_bytes, int staging_bufs) {
   SmemLayout L;
-  L.stage_bytes = kATileBytes + (uint32_t)block_n * kKBlockBytes;
+  L.stage_bytes = (uint32_t)(kBlockM + block_n) * (uint32_t)kb_bytes;
   L.stages_off = 0;
   L.staging_off = L.stage_bytes * (uint32_t)num_stages;
-  L.scale_off = L.staging_off + kStagingBytes;
+  L.scale_off = L.staging_off + (uint32_t)staging_bufs * kStagingBytes;
   L.shift_off = L.scale_off + (uint32_t)cout_pad * 4;
   L.bars_off = (L.shift_off + (uint32_t)cout_pad * 4 + 15u) & ~15u;
   L.total = L.bars_off + (2 * kMaxStages + 2 * kMaxAccStages) * 8 + 16;
@@ -43,7 +43,7 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int num_stages, i
 }
 
 size_t conv_gemm_smem_bytes(const GemmParams &p) {
-  return (size_t)smem_layout(p.block_n, p.num_stages, p.cout_pad).total + 1024;  // + alignment slack
+  return (size_t)smem_layout(p.block_n, p.num_stages, p.cout_pad, p.kb_bytes, p.staging_bufs).total + 1024;  // + alignment slack
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -74,7 +74,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SmemLayout L = smem_layout(p.block_n, p.num_stages, p.cout_pad);
+  const SmemLayout L = smem_layout(p.block_n, p.num_stages, p.cout_pad, p.kb_bytes, p.staging_bufs);
+  const uint32_t a_bytes = (uint32_t)kBlockM * (uint32_t)p.kb_bytes;
   float *s_scale = reinterpret_cast<float *>(smem + L.scale_off);
   float *s_shift = reinterpret_cast<float *>(smem + L.shift_off);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L.bars_off);
@@ -126,7 +127,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int dx = p.taps == 1 ? 0 : (tap % 3 - 1) * p.dil;
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
             if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; atomicExch(p.err_flag, 1); break; }
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)kATileBytes);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes);
             ptx::tma_load_4d(smem + (size_t)stage * L.stage_bytes, &tmA, &full_bar[stage], kb * p.kb_elems, tc.x0 + dx,
                              tc.y0 + dy, tc.img);
             if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
@@ -140,7 +141,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      const uint32_t b_bytes = L.stage_bytes - (uint32_t)kATileBytes;
+      const uint32_t b_bytes = L.stage_bytes - a_bytes;
       for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
         const int n0 = (t % p.n_tiles) * p.block_n;
         int kcoord = 0;
@@ -148,7 +149,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
             if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; atomicExch(p.err_flag, 5); break; }
             ptx::mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
-            ptx::tma_load_2d(smem + (size_t)stage * L.stage_bytes + kATileBytes, &tmB, &full_bar[stage],
+            ptx::tma_load_2d(smem + (size_t)stage * L.stage_bytes + a_bytes, &tmB, &full_bar[stage],
                              kcoord + kb * p.kb_elems, n0);
             if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
           }
@@ -170,11 +171,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!ptx::mbar_wait(&full_bar[stage], phase)) { ok = false; atomicExch(p.err_flag, 3); break; }
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * L.stage_bytes);
-          const uint64_t da = ptx::umma_desc_k_sw128(sa);
-          const uint64_t db = ptx::umma_desc_k_sw128(sa + kATileBytes);
+          if (p.kb_bytes == kKBlockBytes) {
+            const uint64_t da = ptx::umma_desc_k_sw128(sa);
+            const uint64_t db = ptx::umma_desc_k_sw128(sa + kATileBytes);
 #pragma unroll
-          for (int k = 0; k < kKBlockBytes / 32; ++k)  // 32 bytes of K per instruction: advance start address by 2
-            ptx::umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (uint32_t)((it | k) != 0));
+            for (int k = 0; k < kKBlockBytes / 32; ++k)  // 32 bytes of K per instruction: advance start address by 2
+              ptx::umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (uint32_t)((it | k) != 0));
+          } else {  // 64-byte rows (thin single-K-block layer)
+            const uint64_t da = ptx::umma_desc_k_sw64(sa);
+            const uint64_t db = ptx::umma_desc_k_sw64(sa + a_bytes);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              ptx::umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (uint32_t)((it | k) != 0));
+          }
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
@@ -188,9 +197,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int ty = row / p.tile_w, tx = row - ty * p.tile_w;
-    int acc = 0, sbuf_idx = 0;
+    int acc = 0, sbuf_idx = 0, tile_it = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_it) {
       if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase)) { atomicExch(p.err_flag, 4); break; }
       ptx::tc_fence_after();
       const TileCoord tc = decode_tile(p, t);
@@ -199,10 +208,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const size_t pix = ((size_t)tc.img * p.H + y) * (size_t)p.W + x;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
       if (p.tma_store) {
-        staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)(warp - 2) * kStageOutBytes, 1, sbuf_idx, t_row,
-                                    tc.n0, p.block_n, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld, valid, pix,
-                                    lane, tc.x0 + (q * 32) % p.tile_w, tc.y0 + (q * 32) / p.tile_w, tc.img,
-                                    (warp - 2) >> 2, kEpiWarps / 4);
+        // the two warps of a lane quarter alternate 128-byte chunks; a tile with a single chunk (N = 64 bf16) would leave
+        // one of them idle, so there they alternate TILES instead (the store latency of one hides behind the other)
+        int part = (warp - 2) >> 2, nparts = kEpiWarps / 4;
+        int cols = p.n_store - tc.n0;
+        if (cols > p.block_n) cols = p.block_n;
+        bool mine = true;
+        if (cols * (kTf32 ? 4 : 2) < nparts * kKBlockBytes) {
+          mine = (tile_it % nparts) == part;
+          part = 0; nparts = 1;
+        }
+        if (mine)
+          staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)(warp - 2) * p.staging_bufs * kStageOutBytes,
+                                      p.staging_bufs, sbuf_idx, t_row,
+                                      tc.n0, p.block_n, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld, valid, pix,
+                                      lane, tc.x0 + (q * 32) % p.tile_w, tc.y0 + (q * 32) / p.tile_w, tc.img, part, nparts);
       } else {
         for (int c = ((warp - 2) >> 2) * 32; c < p.block_n; c += 32 * (kEpiWarps / 4)) {  // the quarter's two warps alternate
           uint32_t r[32];

@@ -25,7 +25,10 @@ struct GemmParams {
   int block_n;             // UMMA N (multiple of 32, <= 256)
   int taps, dil;           // 1 or 9; tap offset = (k - 1) * dil
   int kblocks_per_tap;     // ceil(Cin * elem_size / 128)
-  int kb_elems;            // elements per K block: 64 (bf16) or 32 (tf32)
+  int kb_elems;            // elements per K block: 64 (bf16) or 32 (tf32); half of that for a 64-byte K block
+  int kb_bytes;            // bytes of one K-block row in shared memory: 128 (SWIZZLE_128B), or 64 (SWIZZLE_64B) for a
+                           // single-K-block layer whose Cin is exactly 64 bytes (a 128-byte box would be half out of
+                           // bounds, which the TMA unit fills very slowly)
   int cin;                 // B's K coordinate of tap t, block b = t * cin + b * kb_elems
   int cout_pad, n_store;   // columns computed / columns written (multiple of 8)
   uint32_t idesc;          // UMMA instruction descriptor (M = 128, N = block_n)
@@ -45,6 +48,8 @@ struct GemmParams {
   // 32 pixel rows x 128 bytes of output and one lane issues a 4-D tensor store of that box
   int tma_store;           // 0: direct register -> global stores
   int store_bw, store_bh;  // pixel box of one warp's 32 rows (store_bw * store_bh == 32)
+  int staging_bufs;        // 1 or 2 staging buffers per epilogue warp (2: the next chunk is converted while the
+                           // tensor store of the previous one still reads its buffer); conv_gemm_kernel only
 };
 
 constexpr int kStagingBytes = kEpiWarps * kStageOutBytes;  // one staging buffer per epilogue warp

@@ -177,7 +177,10 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   LWP_REQUIRE(n > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && dilation >= 1, "lwp_plan_add_conv_gemm: bad shape");
   const bool tf32 = p->dtype == LWP_DTYPE_TF32;
   const int es = tf32 ? 4 : 2;
-  const int kb_elems = kKBlockBytes / es;
+  // thin 1x1 layer whose whole K is 64 bytes: 64-byte K block (SWIZZLE_64B) instead of a half-empty 128-byte one
+  const bool thin64 = taps == 1 && Cin * es == 64 && getenv("LWP_NO_SW64") == nullptr;
+  const int kb_bytes = thin64 ? 64 : kKBlockBytes;
+  const int kb_elems = kb_bytes / es;
   LWP_REQUIRE(Cin % 8 == 0 && in_ld % 8 == 0 && in_ld >= Cin, "lwp_plan_add_conv_gemm: Cin/in_ld must be multiples of 8");
   LWP_REQUIRE(taps == 1 || Cin % kb_elems == 0, "lwp_plan_add_conv_gemm: 3x3 needs Cin %% %d == 0", kb_elems);
   const int cout_pad = (Cout + 63) / 64 * 64;
@@ -190,7 +193,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   Op op;
   op.kind = OP_GEMM;
   GemmParams &g = op.gp;
-  g.taps = taps; g.dil = dilation; g.cin = Cin; g.kb_elems = kb_elems;
+  g.taps = taps; g.dil = dilation; g.cin = Cin; g.kb_elems = kb_elems; g.kb_bytes = kb_bytes;
   g.kblocks_per_tap = (Cin + kb_elems - 1) / kb_elems;
   g.cout_pad = cout_pad;
   g.block_n = cout_pad % 256 == 0 ? 256 : cout_pad % 128 == 0 ? 128 : 64;
@@ -215,9 +218,15 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   g.out = out; g.out_ld = out_ld; g.out_f32 = out_f32; g.out_f32_ld = out_f32_ld;
   g.err_flag = p->err_flag;
   const int smem_budget = 232448 - 1024 - kStagingBytes - 2 * cout_pad * 4 - 512;
-  const int stage_bytes = kATileBytes + g.block_n * kKBlockBytes;
+  const int stage_bytes = (kBlockM + g.block_n) * kb_bytes;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  // opt-in (LWP_STAGING=2) second staging buffer per epilogue warp; measured: no gain on any layer of this network
+  g.staging_bufs = 1;
+  if (const char *e = getenv("LWP_STAGING")) {
+    const int st2 = (smem_budget - kStagingBytes) / stage_bytes;
+    if (atoi(e) == 2 && st2 >= 2) { g.staging_bufs = 2; stages = st2 > kMaxStages ? kMaxStages : st2; }
+  }
   if (const char *sv = getenv("LWP_GEMM_STAGES")) { int v = atoi(sv); if (v >= 2 && v < stages) stages = v; }
   g.num_stages = stages;
   g.acc_stages = 512 / g.block_n;  // the CTA owns the SM (smem > half), so it can take all 512 TMEM columns
@@ -253,7 +262,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
     const char *e2 = getenv("LWP_GEMM_2CTA");
     const int mode = e2 ? atoi(e2) : -1;   // -1 default policy, 0 off, 1: 3x3 layers, 2: every eligible layer, 3: also small layers
     const bool plain = out != nullptr && out_f32 == nullptr && g.n_store % (kKBlockBytes / es) == 0;
-    const bool want = mode < 0 ? (taps == 1 && g.block_n == 256 && g.m_tiles >= 2 * num_sms())
+    const bool want = thin64 ? false : mode < 0 ? (taps == 1 && g.block_n == 256 && g.m_tiles >= 2 * num_sms())
                                : (mode > 0 && g.block_n >= 128 && (mode >= 3 || g.m_tiles >= 2 * num_sms()) && (mode >= 2 || taps == 9));
     if (want && plain && conv_gemm2_init() == LWP_OK) {
       op.two_cta = true;
@@ -276,7 +285,8 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
     cuuint32_t box[4] = {(cuuint32_t)kb_elems, (cuuint32_t)g.tile_w, (cuuint32_t)g.tile_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&op.tmA, dt, 4, const_cast<void *>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     thin64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return LWP_ECUDA; }
   }
   {
@@ -286,7 +296,8 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
     cuuint32_t box[2] = {(cuuint32_t)kb_elems, (cuuint32_t)(op.two_cta ? g.block_n / 2 : g.block_n)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&op.tmB, dt, 2, const_cast<void *>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     thin64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return LWP_ECUDA; }
   }
   // epilogue through smem + TMA tensor store for plain single-output layers whose stored width is whole 128-byte chunks

@@ -200,6 +200,18 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Same for a tile whose rows are 64 bytes (one SWIZZLE_64B span; thin layers with Cin * elem_size == 64):
+// 8-row groups are 512 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                       // SWIZZLE_64B
+  return d;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 template <bool kTf32>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
