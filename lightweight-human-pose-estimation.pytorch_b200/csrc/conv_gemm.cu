@@ -30,9 +30,10 @@ struct SmemLayout {
   uint32_t scale_off, shift_off, bars_off, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int block_n, int num_stages, int cout_pad, int kb_bytes, int staging_bufs) {
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int num_stages, int cout_pad, int kb_bytes, int staging_bufs,
+                                                  int kbps) {
   SmemLayout L;
-  L.stage_bytes = (uint32_t)(kBlockM + block_n) * (uint32_t)kb_bytes;
+  L.stage_bytes = (uint32_t)(kBlockM + block_n) * (uint32_t)kb_bytes * (uint32_t)kbps;
   L.stages_off = 0;
   L.staging_off = L.stage_bytes * (uint32_t)num_stages;
   L.scale_off = L.staging_off + (uint32_t)staging_bufs * kStagingBytes;
@@ -43,7 +44,7 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int num_stages, i
 }
 
 size_t conv_gemm_smem_bytes(const GemmParams &p) {
-  return (size_t)smem_layout(p.block_n, p.num_stages, p.cout_pad, p.kb_bytes, p.staging_bufs).total + 1024;  // + alignment slack
+  return (size_t)smem_layout(p.block_n, p.num_stages, p.cout_pad, p.kb_bytes, p.staging_bufs, p.kbps).total + 1024;  // + alignment slack
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -74,7 +75,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SmemLayout L = smem_layout(p.block_n, p.num_stages, p.cout_pad, p.kb_bytes, p.staging_bufs);
+  const SmemLayout L = smem_layout(p.block_n, p.num_stages, p.cout_pad, p.kb_bytes, p.staging_bufs, p.kbps);
   const uint32_t a_bytes = (uint32_t)kBlockM * (uint32_t)p.kb_bytes;
   float *s_scale = reinterpret_cast<float *>(smem + L.scale_off);
   float *s_shift = reinterpret_cast<float *>(smem + L.shift_off);
@@ -86,7 +87,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
-  const int k_iters = p.taps * p.kblocks_per_tap;
+  const int k_iters = p.taps * p.kblocks_per_tap / p.kbps;
+  const uint32_t mini_bytes = (uint32_t)(kBlockM + p.block_n) * (uint32_t)p.kb_bytes;   // one [A tile | B tile] pair
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -112,85 +114,116 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The three pipeline roles below run WARP-UNIFORM (all 32 lanes execute the loops, one elected lane issues the
+  // asynchronous instruction): every loop variable is then provably uniform, so the compiler keeps stage counters,
+  // barrier / shared-memory addresses and TMA / UMMA operands in the uniform datapath instead of converting vector
+  // registers for each issue.  A lone thread retires ~1 instruction per 6 cycles; at 256 tensor-pipe cycles per
+  // K block (N = 128) the length of these loops IS the speed of the short-K layers.
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
   if (warp == 0) {
     // ===================== TMA producer: activation tiles =====================
-    // (the issue rate of the single producer thread bounds short-K layers: activations and weights are issued by
-    //  two different warps, each with the leanest possible loop)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
-        for (int tap = 0; tap < p.taps && ok; ++tap) {
-          const int dy = p.taps == 1 ? 0 : (tap / 3 - 1) * p.dil;
-          const int dx = p.taps == 1 ? 0 : (tap % 3 - 1) * p.dil;
-          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
-            if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; atomicExch(p.err_flag, 1); break; }
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes);
-            ptx::tma_load_4d(smem + (size_t)stage * L.stage_bytes, &tmA, &full_bar[stage], kb * p.kb_elems, tc.x0 + dx,
-                             tc.y0 + dy, tc.img);
-            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+    const bool skip = (p.debug & 1) != 0;
+    const int taps_y = p.taps == 1 ? 1 : 3;
+    int stage = 0;
+    uint32_t phase = 0, dst = smem_base;
+    bool ok = true;
+    for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      for (int ty = 0; ty < taps_y && ok; ++ty) {
+        const int cy = tc.y0 + (p.taps == 1 ? 0 : (ty - 1) * p.dil);
+        for (int tx = 0; tx < taps_y && ok; ++tx) {
+          const int cx = tc.x0 + (p.taps == 1 ? 0 : (tx - 1) * p.dil);
+          for (int kb = 0; kb < p.kblocks_per_tap; kb += p.kbps) {
+            if (!ptx::mbar_wait_u32(empty0 + 8u * stage, phase ^ 1u)) { ok = false; if (lane == 0) atomicExch(p.err_flag, 1); break; }
+            if (ptx::elect_one()) {
+              if (skip) {
+                ptx::mbar_arrive_u32(full0 + 8u * stage);
+              } else {
+                ptx::mbar_arrive_expect_tx_u32(full0 + 8u * stage, a_bytes * (uint32_t)p.kbps);
+                ptx::tma_load_4d_u32(dst, &tmA, full0 + 8u * stage, kb * p.kb_elems, cx, cy, tc.img);
+                if (p.kbps == 2) ptx::tma_load_4d_u32(dst + mini_bytes, &tmA, full0 + 8u * stage, (kb + 1) * p.kb_elems, cx, cy, tc.img);
+              }
+            }
+            dst += L.stage_bytes;
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; dst = smem_base; }
           }
         }
       }
     }
   } else if (warp == kBProducerWarp) {
     // ===================== TMA producer: weight tiles =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      const uint32_t b_bytes = L.stage_bytes - a_bytes;
-      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
-        const int n0 = (t % p.n_tiles) * p.block_n;
-        int kcoord = 0;
-        for (int tap = 0; tap < p.taps && ok; ++tap) {
-          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
-            if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; atomicExch(p.err_flag, 5); break; }
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
-            ptx::tma_load_2d(smem + (size_t)stage * L.stage_bytes + a_bytes, &tmB, &full_bar[stage],
-                             kcoord + kb * p.kb_elems, n0);
-            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+    const bool skip = (p.debug & 2) != 0;
+    int stage = 0;
+    uint32_t phase = 0, dst = smem_base + a_bytes;
+    bool ok = true;
+    const uint32_t b_bytes = mini_bytes - a_bytes;
+    for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
+      const int n0 = (t % p.n_tiles) * p.block_n;
+      int kcoord = 0;
+      for (int tap = 0; tap < p.taps && ok; ++tap) {
+        for (int kb = 0; kb < p.kblocks_per_tap; kb += p.kbps) {
+          if (!ptx::mbar_wait_u32(empty0 + 8u * stage, phase ^ 1u)) { ok = false; if (lane == 0) atomicExch(p.err_flag, 5); break; }
+          if (ptx::elect_one()) {
+            if (skip) {
+              ptx::mbar_arrive_u32(full0 + 8u * stage);
+            } else {
+              ptx::mbar_arrive_expect_tx_u32(full0 + 8u * stage, b_bytes * (uint32_t)p.kbps);
+              ptx::tma_load_2d_u32(dst, &tmB, full0 + 8u * stage, kcoord + kb * p.kb_elems, n0);
+              if (p.kbps == 2) ptx::tma_load_2d_u32(dst + mini_bytes, &tmB, full0 + 8u * stage, kcoord + (kb + 1) * p.kb_elems, n0);
+            }
           }
-          kcoord += p.cin;
+          dst += L.stage_bytes;
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; dst = smem_base + a_bytes; }
         }
+        kcoord += p.cin;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      bool ok = true;
-      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
-        if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u)) { atomicExch(p.err_flag, 2); break; }
+    const bool do_mma = (p.debug & 4) == 0;
+    const bool thin = p.kb_bytes != kKBlockBytes;
+    // descriptor without the start address; the address field is added per stage / per 32-byte K step (+2)
+    const uint64_t desc_hi = thin ? ptx::umma_desc_k_sw64(0) : ptx::umma_desc_k_sw128(0);
+    const uint32_t a_off16 = a_bytes >> 4, stage16 = L.stage_bytes >> 4, base16 = (smem_base & 0x3FFFFu) >> 4;
+    const uint32_t idesc = p.idesc, mini16 = mini_bytes >> 4;
+    const bool two = p.kbps == 2;
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0, sa16 = base16;
+    bool ok = true;
+    for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
+      if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u)) { if (lane == 0) atomicExch(p.err_flag, 2); break; }
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+      for (int it = 0; it < k_iters; ++it) {
+        if (!ptx::mbar_wait_u32(full0 + 8u * stage, phase)) { ok = false; if (lane == 0) atomicExch(p.err_flag, 3); break; }
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
-        for (int it = 0; it < k_iters; ++it) {
-          if (!ptx::mbar_wait(&full_bar[stage], phase)) { ok = false; atomicExch(p.err_flag, 3); break; }
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * L.stage_bytes);
-          if (p.kb_bytes == kKBlockBytes) {
-            const uint64_t da = ptx::umma_desc_k_sw128(sa);
-            const uint64_t db = ptx::umma_desc_k_sw128(sa + kATileBytes);
-#pragma unroll
-            for (int k = 0; k < kKBlockBytes / 32; ++k)  // 32 bytes of K per instruction: advance start address by 2
-              ptx::umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (uint32_t)((it | k) != 0));
-          } else {  // 64-byte rows (thin single-K-block layer)
-            const uint64_t da = ptx::umma_desc_k_sw64(sa);
-            const uint64_t db = ptx::umma_desc_k_sw64(sa + a_bytes);
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              ptx::umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (uint32_t)((it | k) != 0));
+        if (ptx::elect_one()) {
+          if (do_mma) {
+            const uint64_t da = desc_hi | (uint64_t)sa16, db = desc_hi | (uint64_t)(sa16 + a_off16);
+            ptx::umma<kTf32>(d_tmem, da, db, idesc, (uint32_t)(it != 0));
+            ptx::umma<kTf32>(d_tmem, da + 2u, db + 2u, idesc, 1u);   // 32 bytes of K per instruction: start address + 2
+            if (!thin) {
+              ptx::umma<kTf32>(d_tmem, da + 4u, db + 4u, idesc, 1u);
+              ptx::umma<kTf32>(d_tmem, da + 6u, db + 6u, idesc, 1u);
+            }
+            if (two) {   // second K block of the stage
+              const uint64_t da2 = da + mini16, db2 = db + mini16;
+              ptx::umma<kTf32>(d_tmem, da2, db2, idesc, 1u);
+              ptx::umma<kTf32>(d_tmem, da2 + 2u, db2 + 2u, idesc, 1u);
+              ptx::umma<kTf32>(d_tmem, da2 + 4u, db2 + 4u, idesc, 1u);
+              ptx::umma<kTf32>(d_tmem, da2 + 6u, db2 + 6u, idesc, 1u);
+            }
           }
-          ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          ptx::umma_commit_u32(empty0 + 8u * stage);  // frees the smem stage once these MMAs retire
         }
-        if (!ok) break;
-        ptx::umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
-        if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+        sa16 += stage16;
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; sa16 = base16; }
       }
+      if (!ok) break;
+      if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp < 2 + kEpiWarps) {
     // ===================== epilogue (8 warps, two per TMEM lane quarter) =====================
@@ -218,7 +251,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mine = (tile_it % nparts) == part;
           part = 0; nparts = 1;
         }
-        if (mine)
+        if (mine && !(p.debug & 8))
           staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)(warp - 2) * p.staging_bufs * kStageOutBytes,
                                       p.staging_bufs, sbuf_idx, t_row,
                                       tc.n0, p.block_n, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld, valid, pix,

@@ -44,10 +44,13 @@ struct GemmParams {
   float *out_f32;          // optional float32 copy, pixel stride out_f32_ld
   int out_f32_ld;
   int *err_flag;           // set non-zero if a pipeline wait timed out
+  int debug;               // timing experiments only (LWP_DEBUG_GEMM): bit 0 skip A loads, 1 skip B loads, 2 skip MMAs, 3 skip epilogue
   // epilogue through shared memory + TMA store (plain single-output layers): each epilogue warp stages its
   // 32 pixel rows x 128 bytes of output and one lane issues a 4-D tensor store of that box
   int tma_store;           // 0: direct register -> global stores
   int store_bw, store_bh;  // pixel box of one warp's 32 rows (store_bw * store_bh == 32)
+  int kbps;                // K blocks per pipeline stage (1 or 2): one barrier round trip then covers 4 or 8 MMAs;
+                           // a stage is kbps consecutive [A tile | B tile] pairs (conv_gemm_kernel only)
   int staging_bufs;        // 1 or 2 staging buffers per epilogue warp (2: the next chunk is converted while the
                            // tensor store of the previous one still reads its buffer); conv_gemm_kernel only
 };

@@ -217,14 +217,27 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   g.residual = residual; g.res_ld = res_ld;
   g.out = out; g.out_ld = out_ld; g.out_f32 = out_f32; g.out_f32_ld = out_f32_ld;
   g.err_flag = p->err_flag;
+  g.debug = getenv("LWP_DEBUG_GEMM") ? atoi(getenv("LWP_DEBUG_GEMM")) : 0;
   const int smem_budget = 232448 - 1024 - kStagingBytes - 2 * cout_pad * 4 - 512;
   const int stage_bytes = (kBlockM + g.block_n) * kb_bytes;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  // two K blocks per stage when that still leaves 3 stages: halves the barrier round trips per MMA (the pipeline
+  // loops of the single-lane producer / issuer roles, not the tensor pipe, bound the N = 128 layers)
+  g.kbps = 1;
+  {
+    const char *e = getenv("LWP_KBPS");
+    const int want = e ? atoi(e) : 2;
+    if (want == 2 && !thin64 && g.kblocks_per_tap % 2 == 0 && smem_budget / (2 * stage_bytes) >= 3) {
+      g.kbps = 2;
+      stages = smem_budget / (2 * stage_bytes);
+      if (stages > kMaxStages) stages = kMaxStages;
+    }
+  }
   // opt-in (LWP_STAGING=2) second staging buffer per epilogue warp; measured: no gain on any layer of this network
   g.staging_bufs = 1;
   if (const char *e = getenv("LWP_STAGING")) {
-    const int st2 = (smem_budget - kStagingBytes) / stage_bytes;
+    const int st2 = (smem_budget - kStagingBytes) / (stage_bytes * g.kbps);
     if (atoi(e) == 2 && st2 >= 2) { g.staging_bufs = 2; stages = st2 > kMaxStages ? kMaxStages : st2; }
   }
   if (const char *sv = getenv("LWP_GEMM_STAGES")) { int v = atoi(sv); if (v >= 2 && v < stages) stages = v; }
@@ -266,6 +279,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
                                : (mode > 0 && g.block_n >= 128 && (mode >= 3 || g.m_tiles >= 2 * num_sms()) && (mode >= 2 || taps == 9));
     if (want && plain && conv_gemm2_init() == LWP_OK) {
       op.two_cta = true;
+      g.kbps = 1;   // conv_gemm2_kernel: one K block per stage
       g.idesc = make_umma_idesc(tf32, 2 * kBlockM, g.block_n);
       const int stage2 = kATileBytes + (g.block_n / 2) * kKBlockBytes;
       int st2 = (200 * 1024 - kStagingBytes) / stage2;
