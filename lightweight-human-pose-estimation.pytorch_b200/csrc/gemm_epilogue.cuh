@@ -17,10 +17,26 @@ namespace lwp {
 constexpr int kStageOutBytes = 32 * 128;  // one warp, one 128-byte column chunk
 
 // one unit = 32 accumulator columns of this thread's row -> 64 (bf16) / 128 (fp32) bytes of the staged row
+// bf16 residual of one unit (32 columns = 64 bytes of this thread's pixel row), fetched ahead of the unit's math so its
+// latency hides behind the previous unit / the TMEM load (the wait on tcgen05.ld is a compiler barrier: loads
+// issued inside the unit could not be hoisted above it)
+struct ResPrefetch {
+  uint4 v[4];
+};
+__device__ __forceinline__ void res_prefetch(ResPrefetch &rp, const void *residual, int res_ld, bool res_ok, size_t pix,
+                                             int cg0) {
+  if (res_ok) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(residual) + pix * res_ld + cg0);
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) rp.v[g8] = __ldg(src + g8);
+  }
+}
+
 template <bool kTf32>
 __device__ __forceinline__ void epilogue_unit(const uint32_t (&r)[32], uint8_t *sbuf, int lane, int col_in_chunk, int cg0,
                                               const float *s_scale, const float *s_shift, int act, bool fast_relu,
-                                              const void *residual, int res_ld, bool res_ok, size_t pix) {
+                                              const void *residual, int res_ld, bool res_ok, size_t pix,
+                                              const ResPrefetch *pre = nullptr) {
 #pragma unroll
   for (int g8 = 0; g8 < 4; ++g8) {
     const int cg = cg0 + g8 * 8;
@@ -59,8 +75,9 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&r)[32], uint8_t *
         v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
         v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
       } else {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(
-            reinterpret_cast<const __nv_bfloat16 *>(residual) + pix * res_ld + cg));
+        const uint4 raw = pre != nullptr ? pre->v[g8]
+                                         : __ldg(reinterpret_cast<const uint4 *>(
+                                               reinterpret_cast<const __nv_bfloat16 *>(residual) + pix * res_ld + cg));
         const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -101,8 +118,10 @@ __device__ __forceinline__ void staged_epilogue_tile(const CUtensorMap *tmC, uin
   if (cols <= 0) return;
   const int chunks = cols / kChunkCols;
   uint32_t ra[32], rb[32];
+  ResPrefetch pa, pb;
   if (part < chunks) {
     ptx::tmem_ld_32x32(t_row + (uint32_t)(part * kChunkCols), ra);
+    if constexpr (!kTf32) res_prefetch(pa, residual, res_ld, res_ok, pix, n0 + part * kChunkCols);
     ptx::tmem_ld_wait(ra);
   }
   for (int c = part; c < chunks; c += nparts) {
@@ -115,13 +134,18 @@ __device__ __forceinline__ void staged_epilogue_tile(const CUtensorMap *tmC, uin
     const int cn = c + nparts;  // this warp's next chunk
     if constexpr (kUnitsPerChunk == 2) {
       ptx::tmem_ld_32x32(t_row + (uint32_t)(col0 + 32), rb);          // in flight during the first unit's math
+      res_prefetch(pb, residual, res_ld, res_ok, pix, n0 + col0 + 32);
       if (!(dbg & 2))
-        epilogue_unit<kTf32>(ra, sbuf, lane, 0, n0 + col0, s_scale, s_shift, act, fast_relu, residual, res_ld, res_ok, pix);
+        epilogue_unit<kTf32>(ra, sbuf, lane, 0, n0 + col0, s_scale, s_shift, act, fast_relu, residual, res_ld, res_ok, pix,
+                             &pa);
       ptx::tmem_ld_wait(rb);
-      if (cn < chunks) ptx::tmem_ld_32x32(t_row + (uint32_t)(cn * kChunkCols), ra);  // next chunk, in flight
+      if (cn < chunks) {
+        ptx::tmem_ld_32x32(t_row + (uint32_t)(cn * kChunkCols), ra);  // next chunk, in flight
+        res_prefetch(pa, residual, res_ld, res_ok, pix, n0 + cn * kChunkCols);
+      }
       if (!(dbg & 2))
         epilogue_unit<kTf32>(rb, sbuf, lane, 32, n0 + col0 + 32, s_scale, s_shift, act, fast_relu, residual, res_ld, res_ok,
-                             pix);
+                             pix, &pb);
     } else {
       if (cn < chunks) ptx::tmem_ld_32x32(t_row + (uint32_t)(cn * kChunkCols), rb);
       if (!(dbg & 2))
