@@ -9,7 +9,8 @@
 // * B (weights, [Cout][taps*Cin], K-major) is fetched by a 2-D tensor map.
 // * Both land in shared memory in the canonical K-major SWIZZLE_128B layout; one elected thread issues
 //   tcgen05.mma (M = 128, N = block_n, K = 32 bytes per instruction), accumulating fp32 in TMEM.
-// * Persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue;
+// * Persistent CTAs, warp-specialised: warps 0-7 epilogue, warp 8 / 9 TMA producers (activations / weights), warp 10
+//   MMA issuer;
 //   a ring of smem stages (full/empty mbarriers) and two TMEM accumulator stages (tmem_full/empty) so
 //   the epilogue of tile i overlaps the main loop of tile i+1.
 // * Epilogue: tcgen05.ld -> y = act(acc*scale[c] + shift[c]) (+ residual) -> plan dtype and/or fp32.
@@ -22,6 +23,12 @@
 #include "gemm_epilogue.cuh"
 
 namespace lwp {
+
+// Warp roles of conv_gemm_kernel.  The warp scheduler favours higher warp ids, and the three single-lane pipeline roles
+// are latency-critical (their loop length bounds the short-K layers), so they sit ABOVE the eight epilogue warps, whose
+// bulk conversion work would otherwise delay every barrier poll and MMA issue.  Epilogue warp w drains TMEM lane
+// quarter w % 4.
+constexpr int kWarpA = kEpiWarps, kWarpB = kEpiWarps + 1, kWarpMma = kEpiWarps + 2;
 
 struct SmemLayout {
   uint32_t stage_bytes;
@@ -90,7 +97,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int k_iters = p.taps * p.kblocks_per_tap / p.kbps;
   const uint32_t mini_bytes = (uint32_t)(kBlockM + p.block_n) * (uint32_t)p.kb_bytes;   // one [A tile | B tile] pair
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpA && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     if (p.tma_store) ptx::prefetch_tmap(&tmC);
@@ -104,7 +111,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == kWarpMma) ptx::tmem_alloc(tmem_slot, p.tmem_cols);
   for (int i = threadIdx.x; i < p.cout_pad; i += kGemmThreads) {
     s_scale[i] = p.scale[i];
     s_shift[i] = p.shift[i];
@@ -121,7 +128,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // K block (N = 128) the length of these loops IS the speed of the short-K layers.
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
-  if (warp == 0) {
+  if (warp == kWarpA) {
     // ===================== TMA producer: activation tiles =====================
     const bool skip = (p.debug & 1) != 0;
     const int taps_y = p.taps == 1 ? 1 : 3;
@@ -151,7 +158,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == kBProducerWarp) {
+  } else if (warp == kWarpB) {
     // ===================== TMA producer: weight tiles =====================
     const bool skip = (p.debug & 2) != 0;
     int stage = 0;
@@ -179,7 +186,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         kcoord += p.cin;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
     const bool do_mma = (p.debug & 4) == 0;
     const bool thin = p.kb_bytes != kKBlockBytes;
@@ -225,7 +232,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
-  } else if (warp < 2 + kEpiWarps) {
+  } else if (warp < kEpiWarps) {
     // ===================== epilogue (8 warps, two per TMEM lane quarter) =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -243,7 +250,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (p.tma_store) {
         // the two warps of a lane quarter alternate 128-byte chunks; a tile with a single chunk (N = 64 bf16) would leave
         // one of them idle, so there they alternate TILES instead (the store latency of one hides behind the other)
-        int part = (warp - 2) >> 2, nparts = kEpiWarps / 4;
+        int part = warp >> 2, nparts = kEpiWarps / 4;
         int cols = p.n_store - tc.n0;
         if (cols > p.block_n) cols = p.block_n;
         bool mine = true;
@@ -252,12 +259,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           part = 0; nparts = 1;
         }
         if (mine && !(p.debug & 8))
-          staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)(warp - 2) * p.staging_bufs * kStageOutBytes,
+          staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)warp * p.staging_bufs * kStageOutBytes,
                                       p.staging_bufs, sbuf_idx, t_row,
                                       tc.n0, p.block_n, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld, valid, pix,
                                       lane, tc.x0 + (q * 32) % p.tile_w, tc.y0 + (q * 32) / p.tile_w, tc.img, part, nparts);
       } else {
-        for (int c = ((warp - 2) >> 2) * 32; c < p.block_n; c += 32 * (kEpiWarps / 4)) {  // the quarter's two warps alternate
+        for (int c = (warp >> 2) * 32; c < p.block_n; c += 32 * (kEpiWarps / 4)) {  // the quarter's two warps alternate
           uint32_t r[32];
           ptx::tmem_ld_32x32(t_row + (uint32_t)c, r);
           ptx::tmem_ld_wait();
@@ -320,7 +327,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == kWarpMma) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 int conv_gemm_init() {
