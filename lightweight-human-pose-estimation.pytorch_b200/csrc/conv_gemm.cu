@@ -262,7 +262,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)warp * p.staging_bufs * kStageOutBytes,
                                       p.staging_bufs, sbuf_idx, t_row,
                                       tc.n0, p.block_n, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld, valid, pix,
-                                      lane, tc.x0 + (q * 32) % p.tile_w, tc.y0 + (q * 32) / p.tile_w, tc.img, part, nparts);
+                                      lane, tc.x0 + (q * 32) % p.tile_w, tc.y0 + (q * 32) / p.tile_w, tc.img, part, nparts,
+                                      p.debug >> 4);
       } else {
         for (int c = (warp >> 2) * 32; c < p.block_n; c += 32 * (kEpiWarps / 4)) {  // the quarter's two warps alternate
           uint32_t r[32];

@@ -44,7 +44,8 @@ struct GemmParams {
   float *out_f32;          // optional float32 copy, pixel stride out_f32_ld
   int out_f32_ld;
   int *err_flag;           // set non-zero if a pipeline wait timed out
-  int debug;               // timing experiments only (LWP_DEBUG_GEMM): bit 0 skip A loads, 1 skip B loads, 2 skip MMAs, 3 skip epilogue
+  int debug;               // timing experiments only (LWP_DEBUG_GEMM): bit 0 skip A loads, 1 skip B loads, 2 skip MMAs, 3 skip epilogue,
+                           // 4 skip the epilogue's tensor stores, 5 skip the epilogue's math
   // epilogue through shared memory + TMA store (plain single-output layers): each epilogue warp stages its
   // 32 pixel rows x 128 bytes of output and one lane issues a 4-D tensor store of that box
   int tma_store;           // 0: direct register -> global stores

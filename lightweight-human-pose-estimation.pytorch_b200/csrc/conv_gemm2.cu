@@ -102,54 +102,68 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // pipeline roles run warp-uniform with an elected issuing lane (see conv_gemm.cu: the loop length of these
+  // single-lane roles bounds the kernel)
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      for (int pt = cluster_id; pt < num_pt && ok; pt += num_clusters) {
-        const Tile2 tc = decode_tile2(p, pt, rank);
-        for (int tap = 0; tap < p.taps && ok; ++tap) {
-          const int dy = p.taps == 1 ? 0 : (tap / 3 - 1) * p.dil;
-          const int dx = p.taps == 1 ? 0 : (tap % 3 - 1) * p.dil;
+    const int taps_y = p.taps == 1 ? 1 : 3;
+    const int nb = rank * (p.block_n / 2);
+    int stage = 0;
+    uint32_t phase = 0, dst = smem_base;
+    bool ok = true;
+    for (int pt = cluster_id; pt < num_pt && ok; pt += num_clusters) {
+      const Tile2 tc = decode_tile2(p, pt, rank);
+      int kcoord = 0;
+      for (int ty = 0; ty < taps_y && ok; ++ty) {
+        const int cy = tc.y0 + (p.taps == 1 ? 0 : (ty - 1) * p.dil);
+        for (int tx = 0; tx < taps_y && ok; ++tx) {
+          const int cx = tc.x0 + (p.taps == 1 ? 0 : (tx - 1) * p.dil);
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
-            if (!ptx::mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; atomicExch(p.err_flag, 21); break; }
-            uint8_t *sa = smem + (size_t)stage * L.stage_bytes;
-            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2u * L.stage_bytes);
-            ptx::tma_load_4d_pair(sa, &tmA, &full_bar[stage], kb * p.kb_elems, tc.x0 + dx, tc.y0 + dy, tc.img);
-            ptx::tma_load_2d_pair(sa + kATileBytes, &tmB, &full_bar[stage], tap * p.cin + kb * p.kb_elems,
-                                  tc.n0 + rank * (p.block_n / 2));
-            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+            if (!ptx::mbar_wait_u32(empty0 + 8u * stage, phase ^ 1u)) { ok = false; if (lane == 0) atomicExch(p.err_flag, 21); break; }
+            if (ptx::elect_one()) {
+              if (leader) ptx::mbar_arrive_expect_tx_u32(full0 + 8u * stage, 2u * L.stage_bytes);
+              ptx::tma_load_4d_pair_u32(dst, &tmA, full0 + 8u * stage, kb * p.kb_elems, cx, cy, tc.img);
+              ptx::tma_load_2d_pair_u32(dst + kATileBytes, &tmB, full0 + 8u * stage, kcoord + kb * p.kb_elems, tc.n0 + nb);
+            }
+            dst += L.stage_bytes;
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; dst = smem_base; }
           }
+          kcoord += p.cin;
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader) {
+      const uint64_t desc_hi = ptx::umma_desc_k_sw128(0);
+      const uint32_t a_off16 = kATileBytes >> 4, stage16 = L.stage_bytes >> 4, base16 = (smem_base & 0x3FFFFu) >> 4;
+      const uint32_t idesc = p.idesc;
       int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      uint32_t phase = 0, acc_phase = 0, sa16 = base16;
       bool ok = true;
       for (int pt = cluster_id; pt < num_pt && ok; pt += num_clusters) {
-        if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u)) { atomicExch(p.err_flag, 22); break; }
+        if (!ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u)) { if (lane == 0) atomicExch(p.err_flag, 22); break; }
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
         for (int it = 0; it < k_iters; ++it) {
-          if (!ptx::mbar_wait(&full_bar[stage], phase)) { ok = false; atomicExch(p.err_flag, 23); break; }
+          if (!ptx::mbar_wait_u32(full0 + 8u * stage, phase)) { ok = false; if (lane == 0) atomicExch(p.err_flag, 23); break; }
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * L.stage_bytes);
-          const uint64_t da = ptx::umma_desc_k_sw128(sa);
-          const uint64_t db = ptx::umma_desc_k_sw128(sa + kATileBytes);
-#pragma unroll
-          for (int k = 0; k < kKBlockBytes / 32; ++k)
-            ptx::umma_pair<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
-                                  (uint32_t)((it | k) != 0));
-          ptx::umma_commit_pair(&empty_bar[stage]);   // frees this stage in BOTH CTAs
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          if (ptx::elect_one()) {
+            const uint64_t da = desc_hi | (uint64_t)sa16, db = desc_hi | (uint64_t)(sa16 + a_off16);
+            ptx::umma_pair<kTf32>(d_tmem, da, db, idesc, (uint32_t)(it != 0));
+            ptx::umma_pair<kTf32>(d_tmem, da + 2u, db + 2u, idesc, 1u);
+            ptx::umma_pair<kTf32>(d_tmem, da + 4u, db + 4u, idesc, 1u);
+            ptx::umma_pair<kTf32>(d_tmem, da + 6u, db + 6u, idesc, 1u);
+            ptx::umma_commit_pair_u32(empty0 + 8u * stage);   // frees this stage in BOTH CTAs
+          }
+          sa16 += stage16;
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; sa16 = base16; }
         }
         if (!ok) break;
-        ptx::umma_commit_pair(&tfull_bar[acc]);       // accumulators of both CTAs complete
+        if (ptx::elect_one()) ptx::umma_commit_pair(&tfull_bar[acc]);       // accumulators of both CTAs complete
+        __syncwarp();
         if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
       }
     }

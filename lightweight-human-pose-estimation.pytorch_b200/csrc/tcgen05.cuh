@@ -151,6 +151,28 @@ __device__ __forceinline__ void tma_load_4d_pair(void *smem_dst, const void *tma
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// the same with shared-window integer addresses (bar: the executing CTA's address of the barrier; the leader's copy is signalled)
+__device__ __forceinline__ void tma_load_2d_pair_u32(uint32_t smem_dst, const void *tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair_u32(uint32_t smem_dst, const void *tmap, uint32_t bar, int c0, int c1,
+                                                     int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_u32(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
 // arrive on the LEADER CTA's copy of a barrier (from either CTA of the pair)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
