@@ -52,6 +52,7 @@ struct GemmParams {
   int store_bw, store_bh;  // pixel box of one warp's 32 rows (store_bw * store_bh == 32)
   int kbps;                // K blocks per pipeline stage (1 or 2): one barrier round trip then covers 4 or 8 MMAs;
                            // a stage is kbps consecutive [A tile | B tile] pairs (conv_gemm_kernel only)
+  int c3_a_stages, c3_b_stages;   // conv3x3_pair_kernel: activation-strip / weight-tile ring depths
   int staging_bufs;        // 1 or 2 staging buffers per epilogue warp (2: the next chunk is converted while the
                            // tensor store of the previous one still reads its buffer); conv_gemm_kernel only
 };
@@ -63,6 +64,10 @@ int conv_gemm_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, 
                      const GemmParams &p, int grid, cudaStream_t st);
 int conv_gemm_init();
 // CTA-pair (cta_group::2) variant, conv_gemm2.cu
+size_t conv_gemm3_smem_bytes(const GemmParams &p);
+int conv_gemm3_init();
+int conv_gemm3_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+                      const GemmParams &p, int grid, cudaStream_t st);
 size_t conv_gemm2_smem_bytes(const GemmParams &p);
 int conv_gemm2_init();
 int conv_gemm2_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,

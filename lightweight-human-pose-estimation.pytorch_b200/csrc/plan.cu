@@ -49,6 +49,7 @@ struct Op {
   CUtensorMap tmA, tmB, tmC;
   GemmParams gp;
   bool two_cta = false;   // conv_gemm2_kernel: CTA pairs, tcgen05.mma.cta_group::2
+  bool strips = false;    // conv3x3_pair_kernel: CTA pairs + column-strip reuse of the activations (3x3, Cout 128)
   DwpwParams fp;
   int grid = 0;
 };
@@ -274,7 +275,8 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
     // the weight tile is half of the smem traffic there) and lose on the 128-wide 3x3 layers (90 -> 98 us)
     const char *e2 = getenv("LWP_GEMM_2CTA");
     const int mode = e2 ? atoi(e2) : -1;   // -1 default policy, 0 off, 1: 3x3 layers, 2: every eligible layer, 3: also small layers
-    const bool plain = out != nullptr && out_f32 == nullptr && g.n_store % (kKBlockBytes / es) == 0;
+    const bool plain = out != nullptr && out_f32 == nullptr && g.n_store % (kKBlockBytes / es) == 0 &&
+                       getenv("LWP_NO_TMA_STORE") == nullptr;   // the pair kernel only has the TMA-store epilogue
     const bool want = thin64 ? false : mode < 0 ? (taps == 1 && g.block_n == 256 && g.m_tiles >= 2 * num_sms())
                                : (mode > 0 && g.block_n >= 128 && (mode >= 3 || g.m_tiles >= 2 * num_sms()) && (mode >= 2 || taps == 9));
     if (want && plain && conv_gemm2_init() == LWP_OK) {
@@ -291,12 +293,33 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
     }
   }
 
+  // 3x3, Cout 128, plain epilogue: CTA pairs + column strips (conv_gemm3.cu); LWP_CONV3=0 keeps the tap-by-tap kernels
+  {
+    const char *e3 = getenv("LWP_CONV3");
+    const bool plain = out != nullptr && out_f32 == nullptr && g.n_store % (kKBlockBytes / es) == 0 &&
+                       getenv("LWP_NO_TMA_STORE") == nullptr;
+    if ((e3 == nullptr || atoi(e3) != 0) && taps == 9 && cout_pad == 128 && plain && Cin % kb_elems == 0 && dilation <= 2 &&
+        H * W >= 128 && conv_gemm3_init() == LWP_OK) {
+      op.strips = true; op.two_cta = false;
+      g.block_n = 128; g.n_tiles = 1; g.kbps = 1;
+      g.tile_w = 8; g.tile_h = 16;
+      g.tiles_x = ceil_div(g.W, g.tile_w); g.tiles_y = ceil_div(g.H, g.tile_h);
+      g.m_tiles = g.NIMG * g.tiles_x * g.tiles_y;
+      g.idesc = make_umma_idesc(tf32, 2 * kBlockM, 128);
+      g.c3_a_stages = 4; g.c3_b_stages = 8;
+      g.acc_stages = 4; g.tmem_cols = 512;
+      const long long pairs = (g.m_tiles + 1) / 2;
+      const int cap = num_sms() / 2 * 2;
+      op.grid = (int)(2 * pairs < cap ? 2 * pairs : cap);
+    }
+  }
+
   EncodeTiledFn enc = get_encode_fn();
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.NIMG};
     cuuint64_t strides[3] = {(cuuint64_t)in_ld * es, (cuuint64_t)in_ld * es * g.W, (cuuint64_t)in_ld * es * g.W * g.H};
-    cuuint32_t box[4] = {(cuuint32_t)kb_elems, (cuuint32_t)g.tile_w, (cuuint32_t)g.tile_h, 1};
+    cuuint32_t box[4] = {(cuuint32_t)kb_elems, (cuuint32_t)g.tile_w, (cuuint32_t)(op.strips ? g.tile_h + 2 * dilation : g.tile_h), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&op.tmA, dt, 4, const_cast<void *>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      thin64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -307,7 +330,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
     const cuuint64_t ktot = (cuuint64_t)taps * Cin;
     cuuint64_t dims[2] = {ktot, (cuuint64_t)cout_pad};
     cuuint64_t strides[1] = {ktot * es};
-    cuuint32_t box[2] = {(cuuint32_t)kb_elems, (cuuint32_t)(op.two_cta ? g.block_n / 2 : g.block_n)};
+    cuuint32_t box[2] = {(cuuint32_t)kb_elems, (cuuint32_t)(op.two_cta || op.strips ? g.block_n / 2 : g.block_n)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&op.tmB, dt, 2, const_cast<void *>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      thin64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -484,8 +507,9 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const void *x, int first, int las
                                 op.dil, op.act, st);
         break;
       case OP_GEMM:
-        rc = op.two_cta ? conv_gemm2_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st)
-                        : conv_gemm_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st);
+        rc = op.strips    ? conv_gemm3_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st)
+             : op.two_cta ? conv_gemm2_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st)
+                          : conv_gemm_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st);
         break;
       case OP_DWPW:
         rc = dwpw_launch(f32, op.tmA, op.tmB, op.tmC, op.fp, op.grid, st);
