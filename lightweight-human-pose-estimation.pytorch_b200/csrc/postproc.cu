@@ -213,6 +213,7 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
   __shared__ __align__(16) float s_cy[kPkRows + 2][4];
   __shared__ int s_sy[kPkRows + 2];
   __shared__ int s_win[4];  // sx_lo, ncols, sy_lo, nrows
+  __shared__ int s_cmax[kPkMaxCh];  // per channel: max |source value| over the tile's source window (float bits)
   extern __shared__ float pk_smem[];
   float *s_src = pk_smem;                                   // [nrows][n_ch][kPkSrcMax]
   float *s_T = s_src + kPkSrcMax * n_ch * kPkSrcMax;        // [nrows][n_ch][32]
@@ -222,6 +223,11 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
   const int img = blockIdx.y;
   const int ox0 = tx * kPkCols, oy0 = ty * kPkRows;
   constexpr int kInvalid = -(1 << 30);
+  // An up-sampled value is a combination of 16 source values whose weights sum to at most 1.375^2 = 1.890625 in
+  // absolute value (Keys cubic, A = -0.75, any phase), so a channel whose source window stays below 0.1 / 1.890625
+  // cannot reach the 0.1 threshold anywhere in this tile: its two passes are skipped (same candidates, less work).
+  constexpr float kHopeless = 0.0528f;   // a little under 0.052893 (rounding of the fp32 sums)
+  if (tid < kPkMaxCh) s_cmax[tid] = 0;
   // this lane's up-sampled column (lanes 0 and 31 are halo only)
   const int d = ox0 - 1 + lane;
   const bool col_ok = d >= 0 && d < u.W;
@@ -259,8 +265,11 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
     const int drx = dpos % ncols, dry = dpos / ncols;
     const float *src_img = u.src + (size_t)img * u.h * u.w * u.ld;
     for (int idx = tid; idx < nrows * ncols * n_ch; idx += blockDim.x) {
-      s_src[(ry * n_ch + c) * kPkSrcMax + rx] =
+      const float val =
           __ldg(src_img + (size_t)((clampi(sy_lo + ry, 0, u.h - 1) * u.w + clampi(sx_lo + rx, 0, u.w - 1)) * u.ld + c));
+      s_src[(ry * n_ch + c) * kPkSrcMax + rx] = val;
+      const int bits = __float_as_int(fabsf(val));   // non-negative floats order like their bit patterns (NaN: never skipped)
+      if (bits > s_cmax[c]) atomicMax(&s_cmax[c], bits);
       c += dc;
       int carry = 0;
       if (c >= n_ch) { c -= n_ch; carry = 1; }
@@ -273,6 +282,7 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
   const bool border = (sx < 1) || (sx + 2 >= u.w);
   const int rx0 = col_ok ? sx - 1 - sx_lo : 0;
   for (int c = warp; c < n_ch; c += kPkWarps) {
+    if (__int_as_float(s_cmax[c]) < kHopeless) continue;
     for (int ry = 0; ry < nrows; ++ry) {
       const float *p = s_src + ((size_t)ry * n_ch + c) * kPkSrcMax + rx0;
       float v = 0.f;
@@ -291,6 +301,7 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
   // 3. vertical pass streamed down the rows + strict 4-neighbour test on the row in the middle
   const int rowlen = u.W * u.c_layout, body = rowlen - (rowlen & 3);
   for (int c = warp; c < n_ch; c += kPkWarps) {
+    if (__int_as_float(s_cmax[c]) < kHopeless) continue;
     const bool simd_body = d * u.c_layout + c < body;
     float v0 = 0.f, v1 = 0.f;  // rows i-2, i-1
     // the four horizontally-resized source rows of the current output row stay in registers: consecutive output
