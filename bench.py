@@ -386,8 +386,8 @@ def roofline_pass(pipe, x_dev, args):
     gemm_launches = sum(agg[k]["launches"] for k in tc_kinds)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak = pk["bf16"] if args.precision == "bf16" else pk["bf16"] / 2.0
-    traffic, traffic_src = ncu_traffic(("conv_gemm", "dwpw_gemm_kernel"))
-    res = {"roofline": {"kernel": "tcgen05 implicit-GEMM kernels conv_gemm_kernel / conv_gemm2_kernel%s (all %d launches of a "
+    traffic, traffic_src = ncu_traffic(("conv_gemm", "conv3x3_pair", "dwpw_gemm_kernel"))
+    res = {"roofline": {"kernel": "tcgen05 implicit-GEMM kernels conv_gemm_kernel / conv_gemm2_kernel / conv3x3_pair_kernel%s (all %d launches of a "
                                   "step; %.0f %% of the network time)" % (" / dwpw_gemm_kernel" if "dwpw" in agg else "", gemm_launches,
                                                                          100.0 * gemm_ms / max(sum(times), 1e-9)),
                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -399,7 +399,7 @@ def roofline_pass(pipe, x_dev, args):
     if "gemm3x3" in agg:
         d = agg["gemm3x3"]
         tf = d["flops"] / (d["ms"] * 1e-3) / 1e12
-        res["roofline_gemm3x3"] = {"kernel": "conv_gemm_kernel, dense 3x3 layers (%d launches)" % d["launches"],
+        res["roofline_gemm3x3"] = {"kernel": "conv3x3_pair_kernel (CTA pairs + activation strips), dense 3x3 layers (%d launches)" % d["launches"],
                                    "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
                                    "ms_per_step": d["ms"]}
     if "gemm1x1" in agg:

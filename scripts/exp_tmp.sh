@@ -1,2 +1,4 @@
-timeout 600 python -m pytest tests/test_net_gpu.py -m gpu -q -x --timeout 300 2>&1 | tail -5
-for v in "LWP_X=0" "LWP_CONV3=0"; do env $v python scripts/time_layers.py initial_stage.trunk cpm.conv refinement_stages.0.trunk.1 2>&1 | tail -1 | cut -c1-700; done
+LAYERS="initial_stage.trunk.0 refinement_stages.0.trunk.0.trunk.1 model.8.pw model.8.dw postproc"
+python scripts/prof_layers.py $LAYERS > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/prof_layers_f python scripts/prof_layers.py $LAYERS > gpurun_out/ncu_full_f.log 2>&1
+echo "full capture exit=$?"
