@@ -63,18 +63,40 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 struct TileCoord {
   int img, y0, x0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams &p, int t) {
-  TileCoord c;
-  int m_tile = t / p.n_tiles;
-  c.n0 = (t - m_tile * p.n_tiles) * p.block_n;
-  int per_img = p.tiles_x * p.tiles_y;
-  c.img = m_tile / per_img;
-  int rem = m_tile - c.img * per_img;
-  int ty = rem / p.tiles_x;
-  c.y0 = ty * p.tile_h;
-  c.x0 = (rem - ty * p.tiles_x) * p.tile_w;
-  return c;
-}
+// (n tile, tile column, tile row, image) of a tile index, advanced by the grid stride without divisions: on the thin
+// layers a tile is a few hundred cycles of work and three integer divisions per role per tile were a third of it
+struct TileCursor {
+  int n, tx, ty, img;            // position
+  int dn, dtx, dty, dimg;        // decomposition of the stride
+  __device__ __forceinline__ void init(const GemmParams &p, int t, int stride) {
+    decompose(p, t, n, tx, ty, img);
+    decompose(p, stride, dn, dtx, dty, dimg);
+  }
+  static __device__ __forceinline__ void decompose(const GemmParams &p, int t, int &n_, int &tx_, int &ty_, int &img_) {
+    const int m_tile = t / p.n_tiles;
+    n_ = t - m_tile * p.n_tiles;
+    const int per_img = p.tiles_x * p.tiles_y;
+    img_ = m_tile / per_img;
+    const int rem = m_tile - img_ * per_img;
+    ty_ = rem / p.tiles_x;
+    tx_ = rem - ty_ * p.tiles_x;
+  }
+  __device__ __forceinline__ void advance(const GemmParams &p) {   // mixed-radix add with carries
+    n += dn;
+    int c = 0;
+    if (n >= p.n_tiles) { n -= p.n_tiles; c = 1; }
+    tx += dtx + c; c = 0;
+    if (tx >= p.tiles_x) { tx -= p.tiles_x; c = 1; }
+    ty += dty + c; c = 0;
+    if (ty >= p.tiles_y) { ty -= p.tiles_y; c = 1; }
+    img += dimg + c;
+  }
+  __device__ __forceinline__ TileCoord coord(const GemmParams &p) const {
+    TileCoord tc;
+    tc.img = img; tc.y0 = ty * p.tile_h; tc.x0 = tx * p.tile_w; tc.n0 = n * p.block_n;
+    return tc;
+  }
+};
 
 template <bool kTf32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -135,8 +157,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0, dst = smem_base;
     bool ok = true;
-    for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
-      const TileCoord tc = decode_tile(p, t);
+    TileCursor cur;
+    cur.init(p, blockIdx.x, gridDim.x);
+    for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x, cur.advance(p)) {
+      const TileCoord tc = cur.coord(p);
       for (int ty = 0; ty < taps_y && ok; ++ty) {
         const int cy = tc.y0 + (p.taps == 1 ? 0 : (ty - 1) * p.dil);
         for (int tx = 0; tx < taps_y && ok; ++tx) {
@@ -165,8 +189,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t phase = 0, dst = smem_base + a_bytes;
     bool ok = true;
     const uint32_t b_bytes = mini_bytes - a_bytes;
+    int nidx = blockIdx.x % p.n_tiles;
+    const int dnidx = gridDim.x % p.n_tiles;
     for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
-      const int n0 = (t % p.n_tiles) * p.block_n;
+      const int n0 = nidx * p.block_n;
+      nidx += dnidx;
+      if (nidx >= p.n_tiles) nidx -= p.n_tiles;
       int kcoord = 0;
       for (int tap = 0; tap < p.taps && ok; ++tap) {
         for (int kb = 0; kb < p.kblocks_per_tap; kb += p.kbps) {
@@ -239,10 +267,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ty = row / p.tile_w, tx = row - ty * p.tile_w;
     int acc = 0, sbuf_idx = 0, tile_it = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_it) {
+    TileCursor cur;
+    cur.init(p, blockIdx.x, gridDim.x);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_it, cur.advance(p)) {
       if (!ptx::mbar_wait(&tfull_bar[acc], acc_phase)) { atomicExch(p.err_flag, 4); break; }
       ptx::tc_fence_after();
-      const TileCoord tc = decode_tile(p, t);
+      const TileCoord tc = cur.coord(p);
       const int y = tc.y0 + ty, x = tc.x0 + tx;
       const bool valid = y < p.H && x < p.W;
       const size_t pix = ((size_t)tc.img * p.H + y) * (size_t)p.W + x;

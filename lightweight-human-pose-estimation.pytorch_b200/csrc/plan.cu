@@ -31,6 +31,17 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Shared-memory budget of one persistent GEMM CTA.  The whole 227 KB by default; LWP_GEMM_SMEM (bytes) leaves room for
+// a block of another stream's kernel (the post-processing of the previous batch) to co-reside on the SM.
+static int gemm_smem_cap() {
+  static int cap = -1;
+  if (cap < 0) {
+    cap = 232448;
+    if (const char *e = getenv("LWP_GEMM_SMEM")) { int v = atoi(e); if (v >= 96 * 1024 && v <= 232448) cap = v; }
+  }
+  return cap;
+}
+
 enum OpKind { OP_STEM, OP_DW, OP_GEMM, OP_NCHW, OP_DWPW };
 
 struct Op {
@@ -219,7 +230,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   g.out = out; g.out_ld = out_ld; g.out_f32 = out_f32; g.out_f32_ld = out_f32_ld;
   g.err_flag = p->err_flag;
   g.debug = getenv("LWP_DEBUG_GEMM") ? atoi(getenv("LWP_DEBUG_GEMM")) : 0;
-  const int smem_budget = 232448 - 1024 - kStagingBytes - 2 * cout_pad * 4 - 512;
+  const int smem_budget = gemm_smem_cap() - 1024 - kStagingBytes - 2 * cout_pad * 4 - 512;
   const int stage_bytes = (kBlockM + g.block_n) * kb_bytes;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -278,13 +289,13 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
     const bool plain = out != nullptr && out_f32 == nullptr && g.n_store % (kKBlockBytes / es) == 0 &&
                        getenv("LWP_NO_TMA_STORE") == nullptr;   // the pair kernel only has the TMA-store epilogue
     const bool want = thin64 ? false : mode < 0 ? (taps == 1 && g.block_n == 256 && g.m_tiles >= 2 * num_sms())
-                               : (mode > 0 && g.block_n >= 128 && (mode >= 3 || g.m_tiles >= 2 * num_sms()) && (mode >= 2 || taps == 9));
+                               : (mode > 0 && g.block_n >= (mode >= 4 ? 64 : 128) && (mode >= 3 || g.m_tiles >= 2 * num_sms()) && (mode >= 2 || taps == 9));
     if (want && plain && conv_gemm2_init() == LWP_OK) {
       op.two_cta = true;
       g.kbps = 1;   // conv_gemm2_kernel: one K block per stage
       g.idesc = make_umma_idesc(tf32, 2 * kBlockM, g.block_n);
       const int stage2 = kATileBytes + (g.block_n / 2) * kKBlockBytes;
-      int st2 = (200 * 1024 - kStagingBytes) / stage2;
+      int st2 = ((gemm_smem_cap() < 200 * 1024 ? gemm_smem_cap() - 4096 : 200 * 1024) - kStagingBytes) / stage2;
       g.num_stages = st2 > kMaxStages ? kMaxStages : st2;
       const long long pairs = (long long)((g.m_tiles + 1) / 2) * g.n_tiles;
       long long gr = 2 * pairs;
@@ -307,6 +318,8 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
       g.m_tiles = g.NIMG * g.tiles_x * g.tiles_y;
       g.idesc = make_umma_idesc(tf32, 2 * kBlockM, 128);
       g.c3_a_stages = 4; g.c3_b_stages = 8;
+      while (g.c3_b_stages > 3 && conv_gemm3_smem_bytes(g) > (size_t)gemm_smem_cap()) --g.c3_b_stages;
+      while (g.c3_a_stages > 2 && conv_gemm3_smem_bytes(g) > (size_t)gemm_smem_cap()) --g.c3_a_stages;
       g.acc_stages = 4; g.tmem_cols = 512;
       const long long pairs = (g.m_tiles + 1) / 2;
       const int cap = num_sms() / 2 * 2;

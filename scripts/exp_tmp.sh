@@ -1,4 +1,2 @@
-LAYERS="initial_stage.trunk.0 refinement_stages.0.trunk.0.trunk.1 model.8.pw model.8.dw postproc"
-python scripts/prof_layers.py $LAYERS > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/prof_layers_f python scripts/prof_layers.py $LAYERS > gpurun_out/ncu_full_f.log 2>&1
-echo "full capture exit=$?"
+timeout 600 python -m pytest tests/test_net_gpu.py -m gpu -q -x --timeout 300 2>&1 | tail -2
+for v in 0 15; do LWP_DEBUG_GEMM=$v python scripts/time_layers.py model.1.pw model.2.pw model.3.pw model.4.pw cpm.align cpm.trunk.0.pw heads.1 refinement_stages.0.trunk.1.initial 2>&1 | tail -1 | cut -c1-500; done
