@@ -308,15 +308,20 @@ def main():
         pipe(x_host)
     sync_ms = (time.perf_counter() - t0) / 3 * 1000.0
 
+    e2e_f32 = {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": pipe.h2d_bytes,
+               "d2h_bytes_per_step": pipe.d2h_bytes, "mode": "PosePipeline.submit/collect, 2 batches in flight",
+               "input": "float32 NCHW frames [n,3,368,656], already normalised on the host", "sync_call_ms": sync_ms}
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": workload_config(args, world),
-        "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": pipe.h2d_bytes,
-                "d2h_bytes_per_step": pipe.d2h_bytes, "mode": "PosePipeline.submit/collect, 2 batches in flight",
-                "sync_call_ms": sync_ms},
-        "e2e_u8": e2e_u8,
+        # headline end-to-end number: what the reference's entry point is handed -- raw uint8 BGR frames
+        # (demo.py:54 infer_fast(net, img, ...)) -- in pinned host memory, pose tables back in host memory.  The float32
+        # NCHW variant (the tensor the reference builds on the host before its own H2D copy, 4x the bytes: 185 MB per
+        # step, which is PCIe time comparable to the whole step) is reported next to it.
+        "e2e": dict(e2e_u8, mode="PosePipeline.submit/collect, 2 batches in flight") if e2e_u8 is not None else e2e_f32,
+        "e2e_f32": e2e_f32,
         "gpu_launches": pipe.launches_per_step * args.steps,
         "clocks": clocks,
         "poses_per_step_rank0": total_poses, "persons_injected_rank0": int(sum(persons)),
