@@ -216,7 +216,7 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
   __shared__ int s_cmax[kPkMaxCh];  // per channel: max |source value| over the tile's source window (float bits)
   extern __shared__ float pk_smem[];
   float *s_src = pk_smem;                                   // [nrows][n_ch][kPkSrcMax]
-  float *s_T = s_src + kPkSrcMax * n_ch * kPkSrcMax;        // [nrows][n_ch][32]
+  float *s_T = s_src + kPkSrcMax * n_ch * kPkSrcMax + (threadIdx.x >> 5) * (kPkSrcMax * 32);   // this warp's [nrows][32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_x = (u.W + kPkCols - 1) / kPkCols;
   const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
@@ -281,8 +281,10 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
   // 2. horizontal pass: T[ry][c][lane]
   const bool border = (sx < 1) || (sx + 2 >= u.w);
   const int rx0 = col_ok ? sx - 1 - sx_lo : 0;
-  for (int c = warp; c < n_ch; c += kPkWarps) {
+  const int rowlen = u.W * u.c_layout, body = rowlen - (rowlen & 3);
+  for (int c = warp; c < n_ch; c += kPkWarps) {   // a warp takes its channels one at a time: both passes, then the next
     if (__int_as_float(s_cmax[c]) < kHopeless) continue;
+    __syncwarp();   // the previous channel's vertical pass has finished reading s_T
     for (int ry = 0; ry < nrows; ++ry) {
       const float *p = s_src + ((size_t)ry * n_ch + c) * kPkSrcMax + rx0;
       float v = 0.f;
@@ -294,14 +296,10 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
         v = __fadd_rn(v, p2);
         v = __fadd_rn(v, p3);
       }
-      s_T[((size_t)ry * n_ch + c) * 32 + lane] = v;
+      s_T[ry * 32 + lane] = v;
     }
-  }
-  __syncwarp();  // a warp only reads back the T rows of its own channels
-  // 3. vertical pass streamed down the rows + strict 4-neighbour test on the row in the middle
-  const int rowlen = u.W * u.c_layout, body = rowlen - (rowlen & 3);
-  for (int c = warp; c < n_ch; c += kPkWarps) {
-    if (__int_as_float(s_cmax[c]) < kHopeless) continue;
+    __syncwarp();
+    // 3. vertical pass streamed down the rows + strict 4-neighbour test on the row in the middle
     const bool simd_body = d * u.c_layout + c < body;
     float v0 = 0.f, v1 = 0.f;  // rows i-2, i-1
     // the four horizontally-resized source rows of the current output row stay in registers: consecutive output
@@ -313,11 +311,11 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
       float v2 = 0.f;
       if (sy != kInvalid) {
         if (sy != cur_sy) {
-          const float *t = s_T + ((size_t)(sy - 1 - sy_lo) * n_ch + c) * 32 + lane;
+          const float *t = s_T + (sy - 1 - sy_lo) * 32 + lane;
           if (sy == cur_sy + 1) {
-            T[0] = T[1]; T[1] = T[2]; T[2] = T[3]; T[3] = t[3 * n_ch * 32];
+            T[0] = T[1]; T[1] = T[2]; T[2] = T[3]; T[3] = t[3 * 32];
           } else {
-            T[0] = t[0]; T[1] = t[n_ch * 32]; T[2] = t[2 * n_ch * 32]; T[3] = t[3 * n_ch * 32];
+            T[0] = t[0]; T[1] = t[32]; T[2] = t[2 * 32]; T[3] = t[3 * 32];
           }
           cur_sy = sy;
         }
@@ -858,7 +856,7 @@ static int extract_common(bool fused, const float *hm, const UpSrc *up, int n, i
   }
   if (fused) {
     LWP_REQUIRE(n_ch <= kPkMaxCh, "lwp_extract_keypoints_fused: at most %d channels", kPkMaxCh);
-    const size_t pk_smem = (size_t)(kPkSrcMax * n_ch * kPkSrcMax + kPkSrcMax * n_ch * 32) * sizeof(float);
+    const size_t pk_smem = (size_t)(kPkSrcMax * n_ch * kPkSrcMax + kPkWarps * kPkSrcMax * 32) * sizeof(float);
     dim3 grid(ceil_div(W, kPkCols) * ceil_div(H, kPkRows), n);
     peak_candidates_fused_kernel<<<grid, kPkWarps * 32, pk_smem, st>>>(*up, n_ch, cand, cand_count, cap_candidates,
                                                                       overflow);
