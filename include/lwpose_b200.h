@@ -184,6 +184,15 @@ int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, const void *w
                            float *out_f32, int out_f32_ld, int n, int H, int W, int Cin, int Cout, int taps,
                            int dilation, int act);
 
+/* Both 1x1 layers of a stage's heads (models/with_mobilenet.py:33-38,74-79: conv 128->512|128 + ReLU, conv ->19|38,
+   the two heads stacked / block-diagonal) as ONE back-to-back GEMM kernel: the c_mid-channel intermediate never leaves
+   the SM.  bf16 plans only.  in: [n_pixels][in_ld] plan dtype; w1: [c_mid][c_in], w2: [64][c_mid] (K-major, plan
+   dtype); scale/shift: folded bias (+ ReLU after the first layer, none after the second); out_f32: [n_pixels][out_f32_ld]
+   float32 heads (64 columns written); out: optional plan-dtype copy, pixel stride out_ld, or NULL. */
+int lwp_plan_add_heads_fused(lwp_plan *p, const void *in, int in_ld, const void *w1, const float *scale1,
+                             const float *shift1, int c_mid, const void *w2, const float *scale2, const float *shift2,
+                             void *out, int out_ld, float *out_f32, int out_f32_ld, int n_pixels, int c_in);
+
 /*
  * Fused depthwise-separable block (modules/conv.py:13-32 conv_dw / conv_dw_no_bn): depthwise 3x3 stride 1
  * (pad == dilation, 1 or 2) + scale/shift + dw_act, whose result is written straight into the shared-memory A

@@ -39,6 +39,8 @@ SIGNATURES = {
                                       ctypes.POINTER(_c_double), _c_double]),
     "lwp_plan_add_depthwise": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
                                         _c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
+    "lwp_plan_add_heads_fused": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p,
+                                          _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int]),
     "lwp_plan_add_conv_gemm": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                         _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                                         _c_int, _c_int, _c_int, _c_int]),

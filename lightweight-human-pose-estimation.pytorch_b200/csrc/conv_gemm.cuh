@@ -64,6 +64,11 @@ int conv_gemm_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, 
                      const GemmParams &p, int grid, cudaStream_t st);
 int conv_gemm_init();
 // CTA-pair (cta_group::2) variant, conv_gemm2.cu
+// heads_gemm.cu: both 1x1 layers of a stage's heads as one back-to-back GEMM (bf16 plans)
+int heads_fused_launch(const CUtensorMap &tmX, const CUtensorMap &tmW1, const CUtensorMap &tmW2, int n_px, int c_in,
+                       int c_mid, const float *scale1, const float *shift1, const float *scale2, const float *shift2,
+                       float *out_f32, int out_f32_ld, void *out_bf16, int out_ld, int *err_flag, cudaStream_t st);
+size_t heads_fused_smem_bytes(int k1_blocks, int chunks);
 size_t conv_gemm3_smem_bytes(const GemmParams &p);
 int conv_gemm3_init();
 int conv_gemm3_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,

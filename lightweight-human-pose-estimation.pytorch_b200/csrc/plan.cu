@@ -42,7 +42,7 @@ static int gemm_smem_cap() {
   return cap;
 }
 
-enum OpKind { OP_STEM, OP_DW, OP_GEMM, OP_NCHW, OP_DWPW };
+enum OpKind { OP_STEM, OP_DW, OP_GEMM, OP_NCHW, OP_DWPW, OP_HEADS };
 
 struct Op {
   OpKind kind;
@@ -63,6 +63,11 @@ struct Op {
   bool strips = false;    // conv3x3_pair_kernel: CTA pairs + column-strip reuse of the activations (3x3, Cout 128)
   DwpwParams fp;
   int grid = 0;
+  // fused heads (tmA = X, tmB = W1, tmC = W2)
+  int hd_px = 0, hd_cin = 0, hd_cmid = 0, hd_out_ld = 0, hd_f32_ld = 0;
+  const float *hd_scale1 = nullptr, *hd_shift1 = nullptr, *hd_scale2 = nullptr, *hd_shift2 = nullptr;
+  float *hd_out_f32 = nullptr;
+  void *hd_out = nullptr;
 };
 
 }  // namespace lwp
@@ -494,6 +499,54 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
   return LWP_OK;
 }
 
+extern "C" int lwp_plan_add_heads_fused(lwp_plan *p, const void *in, int in_ld, const void *w1, const float *scale1,
+                                        const float *shift1, int c_mid, const void *w2, const float *scale2,
+                                        const float *shift2, void *out, int out_ld, float *out_f32, int out_f32_ld,
+                                        int n_pixels, int c_in) {
+  LWP_REQUIRE(p && in && w1 && scale1 && shift1 && w2 && scale2 && shift2 && out_f32, "lwp_plan_add_heads_fused: null pointer");
+  LWP_REQUIRE(p->dtype == LWP_DTYPE_BF16, "lwp_plan_add_heads_fused: bf16 plans only");
+  LWP_REQUIRE(n_pixels > 0 && c_in > 0 && c_in % 64 == 0 && c_mid > 0 && c_mid % 64 == 0 && in_ld >= c_in && in_ld % 8 == 0,
+              "lwp_plan_add_heads_fused: Cin / Cmid must be multiples of 64");
+  LWP_REQUIRE(out_f32_ld >= 64 && out_f32_ld % 4 == 0 && (uintptr_t)out_f32 % 16 == 0, "lwp_plan_add_heads_fused: bad out_f32");
+  LWP_REQUIRE(!out || (out_ld >= 64 && out_ld % 8 == 0 && (uintptr_t)out % 16 == 0), "lwp_plan_add_heads_fused: bad out");
+  LWP_REQUIRE(((uintptr_t)in % 16) == 0 && ((uintptr_t)w1 % 16) == 0 && ((uintptr_t)w2 % 16) == 0, "lwp_plan_add_heads_fused: unaligned pointer");
+  if (heads_fused_smem_bytes(c_in / 64, c_mid / 64) > 232448) { set_error("lwp_plan_add_heads_fused: tiles do not fit in shared memory"); return LWP_ECAP; }
+  Op op;
+  op.kind = OP_HEADS;
+  op.hd_px = n_pixels; op.hd_cin = c_in; op.hd_cmid = c_mid; op.hd_out_ld = out_ld; op.hd_f32_ld = out_f32_ld;
+  op.hd_scale1 = scale1; op.hd_shift1 = shift1; op.hd_scale2 = scale2; op.hd_shift2 = shift2;
+  op.hd_out_f32 = out_f32; op.hd_out = out;
+  EncodeTiledFn enc = get_encode_fn();
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  cuuint32_t estr[2] = {1, 1};
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)c_in, (cuuint64_t)n_pixels};
+    cuuint64_t strides[1] = {(cuuint64_t)in_ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)kBlockM};
+    CUresult r = enc(&op.tmA, dt, 2, const_cast<void *>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(heads X) failed: %d", (int)r); return LWP_ECUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)c_in, (cuuint64_t)c_mid};
+    cuuint64_t strides[1] = {(cuuint64_t)c_in * 2};
+    cuuint32_t box[2] = {64, 64};
+    CUresult r = enc(&op.tmB, dt, 2, const_cast<void *>(w1), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(heads W1) failed: %d", (int)r); return LWP_ECUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)c_mid, 64};
+    cuuint64_t strides[1] = {(cuuint64_t)c_mid * 2};
+    cuuint32_t box[2] = {64, 64};
+    CUresult r = enc(&op.tmC, dt, 2, const_cast<void *>(w2), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(heads W2) failed: %d", (int)r); return LWP_ECUDA; }
+  }
+  p->ops.push_back(op);
+  return LWP_OK;
+}
+
 extern "C" int lwp_plan_run_range(lwp_plan *p, const void *x, int first, int last, void *stream) {
   LWP_REQUIRE(p != nullptr, "lwp_plan_run: null plan");
   LWP_REQUIRE(first >= 0 && last <= (int)p->ops.size() && first <= last, "lwp_plan_run_range: bad range");
@@ -526,6 +579,11 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const void *x, int first, int las
         break;
       case OP_DWPW:
         rc = dwpw_launch(f32, op.tmA, op.tmB, op.tmC, op.fp, op.grid, st);
+        break;
+      case OP_HEADS:
+        rc = heads_fused_launch(op.tmA, op.tmB, op.tmC, op.hd_px, op.hd_cin, op.hd_cmid, op.hd_scale1, op.hd_shift1,
+                                op.hd_scale2, op.hd_shift2, op.hd_out_f32, op.hd_f32_ld, op.hd_out, op.hd_out_ld, p->err_flag,
+                                st);
         break;
       case OP_NCHW:
         rc = nhwc_to_nchw_launch(op.in_f32 != 0, op.in, op.ld, op.c0, op.C, (float *)op.out, op.n, op.H * op.W, st);

@@ -254,6 +254,32 @@ class Plan:
         self.op_meta.append(dict(kind="dwpw", flops=2.0 * px * d.c * (g.cout + 9), bytes=float(nbytes)))
         return True
 
+    def _heads(self, name, src, src_ld, heads, n, h, w, big, out, out_ptr_off, out_f32):
+        """The two (merged) 1x1 layers of a stage's heads: one back-to-back GEMM kernel on bf16 plans (the intermediate
+        never leaves the SM; LWP_HEADS_FUSION=0 keeps the two-kernel form), two conv GEMMs otherwise."""
+        g0, g1 = heads
+        px = n * h * w
+        fuse = (self.tdtype == torch.bfloat16 and os.environ.get("LWP_HEADS_FUSION", "1") != "0" and g0.cin % 64 == 0
+                and g0.cout_pad % 64 == 0 and g1.cout_pad == 64 and g1.cin == g0.cout_pad)
+        if fuse:
+            out_ptr = (out.data_ptr() + out_ptr_off * 2) if out is not None else None
+            rc = self.lib.lwp_plan_add_heads_fused(
+                self.handle, src.data_ptr(), src_ld, g0.w.data_ptr(), g0.scale.data_ptr(), g0.shift.data_ptr(), g0.cout_pad,
+                g1.w.data_ptr(), g1.scale.data_ptr(), g1.shift.data_ptr(), out_ptr, CONCAT_LD, out_f32.data_ptr(), HEAD_LD,
+                px, g0.cin)
+            if rc != 3:  # LWP_ECAP: tiles too large for shared memory -> two kernels
+                _lib.check(rc, "lwp_plan_add_heads_fused(%s)" % name)
+                self.op_names.append(name + ".fused")
+                flops = px * (2.0 * g0.cin_real * g0.cout + getattr(g1, "flops_per_px", 2.0 * g1.cin_real * g1.cout))
+                nbytes = px * (g0.cin_real * 2 + HEAD_LD * 4 + (64 * 2 if out is not None else 0)) + (g0.w.numel() + g1.w.numel()) * 2
+                self.op_meta.append(dict(kind="gemm1x1", flops=flops, bytes=float(nbytes)))
+                return
+        mid = g0.cout_pad
+        hb = big[: px * mid]
+        self._gemm(name + ".0", src, src_ld, g0, n, h, w, out=hb, out_ld=mid)
+        self._gemm(name + ".1", hb, mid, g1, n, h, w, out=out, out_ld=CONCAT_LD, out_ptr_off=out_ptr_off,
+                   out_f32=out_f32, out_f32_ld=HEAD_LD)
+
     # -- the layer walk -----------------------------------------------------------------------
     def _build(self, P, n_stages_out, num_heatmaps, num_pafs):
         n, H, W = self.n, self.H, self.W
@@ -327,10 +353,8 @@ class Plan:
         for i, g in enumerate(P.init_trunk):
             self._gemm("initial_stage.trunk.%d" % i, srcs[i][0], srcs[i][1], g, n, h, w, out=dsts[i], out_ld=nc)
         more = len(P.refine) > 0
-        self._gemm("initial_stage.heads.0", t0, nc, P.init_heads[0], n, h, w, out=big, out_ld=mid0)
-        self._gemm("initial_stage.heads.1", big, mid0, P.init_heads[1], n, h, w,
-                   out=concat if more else None, out_ld=CONCAT_LD, out_ptr_off=nc,
-                   out_f32=self.heads_f32[0], out_f32_ld=HEAD_LD)
+        self._heads("initial_stage.heads", t0, nc, P.init_heads, n, h, w, big, concat if more else None, nc,
+                    self.heads_f32[0])
         # refinement stages
         for s, (blks, heads) in enumerate(P.refine):
             src, src_ld = concat, CONCAT_LD
@@ -342,13 +366,9 @@ class Plan:
                 self._gemm("refinement_stages.%d.trunk.%d.trunk.1" % (s, k), t0, nc, c1, n, h, w, out=dst, out_ld=nc,
                            residual=i0, res_ld=nc)  # initial_features + trunk_features
                 src, src_ld = dst, nc
-            mid = heads[0].cout_pad
-            hb = big[: px * mid]
-            self._gemm("refinement_stages.%d.heads.0" % s, src, nc, heads[0], n, h, w, out=hb, out_ld=mid)
             more = s + 1 < len(P.refine)
-            self._gemm("refinement_stages.%d.heads.1" % s, hb, mid, heads[1], n, h, w,
-                       out=concat if more else None, out_ld=CONCAT_LD, out_ptr_off=nc,
-                       out_f32=self.heads_f32[s + 1], out_f32_ld=HEAD_LD)
+            self._heads("refinement_stages.%d.heads" % s, src, nc, heads, n, h, w, big, concat if more else None, nc,
+                        self.heads_f32[s + 1])
         self.num_compute_ops = len(self.op_names)
         # NCHW float32 tensors handed back by forward()
         self.outputs = []

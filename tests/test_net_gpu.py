@@ -191,6 +191,43 @@ def test_fused_dwpw_vs_torch(env, precision, shape):
     assert _rel(got, ref) < tol * max(1.0, float(ref.abs().max())), _rel(got, ref)
 
 
+@pytest.mark.parametrize("shape", [
+    # (pixels, Cin, Cmid, copy)
+    (128, 128, 1024, True),      # one exact tile, initial-stage heads
+    (3 * 128 + 57, 128, 1024, False),   # ragged last tile
+    (46 * 82 * 2, 128, 256, True),      # refinement-stage heads, many tiles per CTA
+    (5 * 128, 64, 64, True),            # one K block, one chunk
+])
+def test_fused_heads_vs_torch(env, shape):
+    """Back-to-back GEMM of a stage's heads (bf16 plans): relu(x W1^T + b1) rounded to bf16, then W2^T + b2 in float32."""
+    torch, _lib, engine = env
+    px, cin, cmid, copy = shape
+    g = torch.Generator().manual_seed(px + cmid)
+    x = (torch.randn(px, cin, generator=g) * 0.5).bfloat16()
+    w1 = (torch.randn(cmid, cin, generator=g) * 0.1).bfloat16()
+    w2 = (torch.randn(64, cmid, generator=g) * 0.05).bfloat16()
+    w2[57:] = 0
+    s1, b1 = torch.rand(cmid, generator=g) + 0.5, torch.randn(cmid, generator=g) * 0.1
+    s2, b2 = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+    mid = torch.relu(x.float() @ w1.float().t() * s1 + b1).bfloat16().float()
+    ref = mid @ w2.float().t() * s2 + b2
+    xd, w1d, w2d = x.cuda(), w1.cuda(), w2.cuda()
+    s1d, b1d, s2d, b2d = s1.cuda(), b1.cuda(), s2.cuda(), b2.cuda()
+    out_f32 = torch.full((px, 64), 7.0, dtype=torch.float32, device="cuda")
+    out = torch.full((px, 192), 7.0, dtype=torch.bfloat16, device="cuda") if copy else None
+    p = OnePlan(env, "bf16")
+    _lib.check(p.L.lwp_plan_add_heads_fused(
+        p.h, xd.data_ptr(), cin, w1d.data_ptr(), s1d.data_ptr(), b1d.data_ptr(), cmid, w2d.data_ptr(), s2d.data_ptr(),
+        b2d.data_ptr(), (out.data_ptr() + 128 * 2) if copy else None, 192, out_f32.data_ptr(), 64, px, cin), "add")
+    p.run()
+    p.close()
+    got = out_f32.cpu()
+    assert _rel(got, ref) < 2e-2 * max(1.0, float(ref.abs().max())), _rel(got, ref)
+    if copy:
+        assert torch.equal(out[:, 128:].float().cpu(), got.bfloat16().float())   # bf16 copy of the same values
+        assert float((out[:, :128].float() - 7.0).abs().max()) == 0.0            # nothing else touched
+
+
 @pytest.mark.parametrize("impl", ["gemm", "direct"])
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
 def test_stem_vs_torch(env, precision, impl, monkeypatch):
