@@ -27,10 +27,10 @@
 namespace lwp {
 
 constexpr int kHdChunk = 64;                                  // intermediate columns per chunk = one bf16 K block
-constexpr int kHdWStages = 4;
+constexpr int kHdWStages = 5;
 constexpr int kHdW1Bytes = kHdChunk * kKBlockBytes;           // one K block of a W1 chunk: 64 rows x 128 B
 constexpr int kHdW2Bytes = 64 * kKBlockBytes;                 // W2 chunk: 64 output rows x 64 K
-constexpr int kHdBufs = 3;                                    // acc1 / A2 buffers in flight between the two GEMMs
+constexpr int kHdBufs = 2;                                    // acc1 / A2 buffers in flight between the two GEMMs
 constexpr int kHdAcc2Col = kHdBufs * 64;                      // TMEM: acc1 buffers, then two acc2 buffers
 constexpr int kHdTmemCols = 512;
 constexpr int kHdWarpMma2 = kBProducerWarp + 1;               // warp 11: issuer of the second GEMM
@@ -60,7 +60,7 @@ __host__ __device__ inline HeadsSmem heads_smem(int k1_blocks, int chunks) {
   L.s1_off = L.a2_off + kHdBufs * kATileBytes;
   L.s2_off = L.s1_off + (uint32_t)chunks * kHdChunk * 8;      // scale1 | shift1
   L.bars_off = L.s2_off + 64 * 8;                             // scale2 | shift2
-  L.total = L.bars_off + 32 * 8 + 16;   // 32 barrier slots + the TMEM address
+  L.total = L.bars_off + 40 * 8 + 16;   // 40 barrier slots + the TMEM address
   return L;
 }
 
@@ -73,10 +73,10 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   float *s_scale1 = reinterpret_cast<float *>(smem + L.s1_off), *s_shift1 = s_scale1 + p.chunks * kHdChunk;
   float *s_scale2 = reinterpret_cast<float *>(smem + L.s2_off), *s_shift2 = s_scale2 + 64;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars_off);
-  uint64_t *x_full = bars, *x_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 8;
-  uint64_t *acc1_full = bars + 12, *acc1_empty = bars + 16, *a2_full = bars + 20, *a2_empty = bars + 24;
-  uint64_t *acc2_full = bars + 28, *acc2_empty = bars + 30;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 32);
+  uint64_t *x_full = bars, *x_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 12;   // up to 8 weight stages
+  uint64_t *acc1_full = bars + 20, *acc1_empty = bars + 24, *a2_full = bars + 28, *a2_empty = bars + 32;
+  uint64_t *acc2_full = bars + 36, *acc2_empty = bars + 38;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
