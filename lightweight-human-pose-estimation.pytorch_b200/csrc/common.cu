@@ -25,6 +25,12 @@ int num_sms() {
   return sms;
 }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) on = (getenv("LWP_NO_PDL") != nullptr && atoi(getenv("LWP_NO_PDL")) != 0) ? 0 : 1;
+  return on != 0;
+}
+
 }  // namespace lwp
 
 extern "C" int lwp_version(void) { return 100; }

@@ -315,6 +315,8 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict
     ptx::fence_barrier_init();
   }
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();   // before the first halo load (previous kernel's output) and the first store (its input)
   const int cq = tid % p.cq, pb = tid / p.cq;
   const int xgroups = p.tw / CC;
   const int xg = pb % xgroups, yg = pb / xgroups;
@@ -553,13 +555,13 @@ static int depthwise_tma_launch_t(const CUtensorMap &tm, T *out, const float *w9
 #define LWP_DW_GO(S_, D_)                                                                                             \
   do {                                                                                                              \
     if (pixb == 128) {                                                                                              \
-      if (p.act == LWP_ACT_RELU) depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_RELU, 128><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
-      else if (p.act == LWP_ACT_ELU) depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_ELU, 128><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
-      else depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_NONE, 128><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
+      if (p.act == LWP_ACT_RELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_RELU, 128>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
+      else if (p.act == LWP_ACT_ELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_ELU, 128>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
+      else LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_NONE, 128>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
     } else {                                                                                                        \
-      if (p.act == LWP_ACT_RELU) depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_RELU, 64><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
-      else if (p.act == LWP_ACT_ELU) depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_ELU, 64><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
-      else depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_NONE, 64><<<grid, 256, smem, st>>>(tm, out, w9c, scale, shift, p); \
+      if (p.act == LWP_ACT_RELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_RELU, 64>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
+      else if (p.act == LWP_ACT_ELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_ELU, 64>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
+      else LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_NONE, 64>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
     }                                                                                                               \
   } while (0)
   if (stride == 1 && dil == 1) LWP_DW_GO(1, 1);

@@ -142,6 +142,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();   // the next kernel of the stream may be scheduled as SMs free up ...
+  pdl_wait();      // ... and this one touches activations only after the previous kernel has completed
 
   // The three pipeline roles below run WARP-UNIFORM (all 32 lanes execute the loops, one elected lane issues the
   // asynchronous instruction): every loop variable is then provably uniform, so the compiler keeps stage counters,
@@ -374,9 +376,9 @@ int conv_gemm_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, 
                      const GemmParams &p, int grid, cudaStream_t st) {
   size_t smem = conv_gemm_smem_bytes(p);
   if (tf32)
-    conv_gemm_kernel<true><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmC, p);
+    LWP_CUDA_CHECK(launch_pdl(conv_gemm_kernel<true>, grid, kGemmThreads, smem, st, 1, tmA, tmB, tmC, p));
   else
-    conv_gemm_kernel<false><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmC, p);
+    LWP_CUDA_CHECK(launch_pdl(conv_gemm_kernel<false>, grid, kGemmThreads, smem, st, 1, tmA, tmB, tmC, p));
   LWP_LAUNCH_CHECK();
   return LWP_OK;
 }

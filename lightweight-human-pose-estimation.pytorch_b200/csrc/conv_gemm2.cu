@@ -101,6 +101,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   ptx::cluster_sync();   // both CTAs' barriers are initialised before any remote arrive / TMA signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   // pipeline roles run warp-uniform with an elected issuing lane (see conv_gemm.cu: the loop length of these
   // single-lane roles bounds the kernel)
@@ -210,20 +212,9 @@ int conv_gemm2_init() {
 
 int conv_gemm2_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
                       const GemmParams &p, int grid, cudaStream_t st) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = conv_gemm2_smem_bytes(p);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (tf32) LWP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<true>, tmA, tmB, tmC, p));
-  else LWP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<false>, tmA, tmB, tmC, p));
+  const size_t smem = conv_gemm2_smem_bytes(p);
+  if (tf32) LWP_CUDA_CHECK(launch_pdl(conv_gemm2_kernel<true>, grid, kGemmThreads, smem, st, 2, tmA, tmB, tmC, p));
+  else LWP_CUDA_CHECK(launch_pdl(conv_gemm2_kernel<false>, grid, kGemmThreads, smem, st, 2, tmA, tmB, tmC, p));
   return LWP_OK;
 }
 

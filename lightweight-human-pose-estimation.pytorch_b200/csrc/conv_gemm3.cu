@@ -115,6 +115,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   ptx::cluster_sync();   // both CTAs' barriers are initialised before any remote arrive / TMA signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t afull0 = ptx::smem_u32(a_full), aempty0 = ptx::smem_u32(a_empty);
   const uint32_t bfull0 = ptx::smem_u32(b_full), bempty0 = ptx::smem_u32(b_empty);
@@ -247,21 +249,9 @@ int conv_gemm3_init() {
 
 int conv_gemm3_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
                       const GemmParams &p, int grid, cudaStream_t st) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = conv_gemm3_smem_bytes(p);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (tf32) LWP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<true>, tmA, tmB, tmC, p));
-  else LWP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<false>, tmA, tmB, tmC, p));
+  const size_t smem = conv_gemm3_smem_bytes(p);
+  if (tf32) LWP_CUDA_CHECK(launch_pdl(conv3x3_pair_kernel<true>, grid, kGemmThreads, smem, st, 2, tmA, tmB, tmC, p));
+  else LWP_CUDA_CHECK(launch_pdl(conv3x3_pair_kernel<false>, grid, kGemmThreads, smem, st, 2, tmA, tmB, tmC, p));
   return LWP_OK;
 }
 

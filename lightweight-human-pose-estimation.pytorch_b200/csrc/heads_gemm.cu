@@ -101,6 +101,8 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t wfull0 = ptx::smem_u32(w_full), wempty0 = ptx::smem_u32(w_empty);
 
@@ -307,8 +309,7 @@ int heads_fused_launch(const CUtensorMap &tmX, const CUtensorMap &tmW1, const CU
   const size_t smem = heads_fused_smem_bytes(p.k1_blocks, p.chunks);
   if (smem > 232448) { set_error("heads_fused: %zu bytes of shared memory", smem); return LWP_ECAP; }
   const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
-  heads_fused_kernel<<<grid, kHdThreads, smem, st>>>(tmX, tmW1, tmW2, p);
-  LWP_LAUNCH_CHECK();
+  LWP_CUDA_CHECK(launch_pdl(heads_fused_kernel, grid, kHdThreads, smem, st, 1, tmX, tmW1, tmW2, p));
   return LWP_OK;
 }
 

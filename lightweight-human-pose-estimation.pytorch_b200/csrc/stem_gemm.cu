@@ -96,6 +96,8 @@ stem_gemm_kernel(const StemGemmParams p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();   // (the output buffer may still be read by the previous step's kernels)
   const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(b_tile));
   const float *xf = reinterpret_cast<const float *>(p.x);
   const uint8_t *x8 = reinterpret_cast<const uint8_t *>(p.x);
@@ -235,13 +237,12 @@ int stem_gemm_launch(bool f32, const void *x, bool x_is_u8, const double *mean3,
   int grid = num_sms() * per_sm;
   if (grid > p.tiles) grid = p.tiles;
   if (f32) {
-    if (x_is_u8) stem_gemm_kernel<true, true><<<grid, kStemThreads, smem, st>>>(p);
-    else stem_gemm_kernel<true, false><<<grid, kStemThreads, smem, st>>>(p);
+    if (x_is_u8) LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<true, true>, grid, kStemThreads, smem, st, 1, p));
+    else LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<true, false>, grid, kStemThreads, smem, st, 1, p));
   } else {
-    if (x_is_u8) stem_gemm_kernel<false, true><<<grid, kStemThreads, smem, st>>>(p);
-    else stem_gemm_kernel<false, false><<<grid, kStemThreads, smem, st>>>(p);
+    if (x_is_u8) LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<false, true>, grid, kStemThreads, smem, st, 1, p));
+    else LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<false, false>, grid, kStemThreads, smem, st, 1, p));
   }
-  LWP_LAUNCH_CHECK();
   return LWP_OK;
 }
 
