@@ -10,6 +10,10 @@ namespace lwp {
 constexpr int kEpiWarps = 8;         // two epilogue warps per TMEM lane quarter (alternate 128-byte chunks)
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps + 32;  // warp 0: TMA producer (activations), warp 1: MMA issuer + TMEM owner, 8 epilogue warps, last warp: TMA producer (weights)
 constexpr int kBProducerWarp = 2 + kEpiWarps;
+#ifndef LWP_GEMM_BOUND_THREADS
+#define LWP_GEMM_BOUND_THREADS kGemmThreads
+#endif
+constexpr int kGemmBoundThreads = LWP_GEMM_BOUND_THREADS;   // register cap of the GEMM kernels = 65536 / this (experiments: 512 -> 128 registers)
 constexpr int kBlockM = 128;        // pixels per tile == UMMA M == TMEM lanes
 constexpr int kKBlockBytes = 128;   // one SWIZZLE_128B row of K per pipeline stage
 constexpr int kATileBytes = kBlockM * kKBlockBytes;

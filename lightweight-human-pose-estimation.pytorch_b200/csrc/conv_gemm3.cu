@@ -72,7 +72,7 @@ __device__ __forceinline__ Tile3 decode_tile3(const GemmParams &p, int pt, int r
 }
 
 template <bool kTf32>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmBoundThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
