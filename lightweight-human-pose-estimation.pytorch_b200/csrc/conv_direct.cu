@@ -239,6 +239,7 @@ struct DwTileParams {
   int cb, cq;          // channels per tile, 4-channel groups per pixel (cb/4)
   int tiles_x, tiles_y, cblocks, sp_tiles;   // sp_tiles = n * tiles_x * tiles_y spatial tiles per channel block
   int act, stages;
+  int debug;           // timing experiments only (LWP_DEBUG_DW): bit 0 skip the window loads + FMAs, bit 1 skip the stores
   uint32_t stage_bytes;
 };
 
@@ -246,6 +247,9 @@ __device__ __forceinline__ float2 bf16x2_to_f32x2(uint32_t x) {  // PRMT + LOP3:
   return make_float2(__uint_as_float(__byte_perm(x, 0u, 0x1044)), __uint_as_float(x & 0xffff0000u));
 }
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : __expf(v) - 1.f; }  // ELU(alpha = 1) as in the fused block: abs error ~1e-7
+#ifndef LWP_DW_STCS
+#define LWP_DW_STCS 0
+#endif
 template <typename T> struct SmemVec4;  // 4 channels from shared memory as two packed fp32 pairs; activation + store of 4 channels
 template <> struct SmemVec4<__nv_bfloat16> {
   static __device__ __forceinline__ void load(uint32_t saddr, float2 (&v)[2]) {
@@ -261,7 +265,8 @@ template <> struct SmemVec4<__nv_bfloat16> {
       const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
       lo = __hmax2(lo, zero2); hi = __hmax2(hi, zero2);
     }
-    *reinterpret_cast<uint2 *>(p) = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+    if (LWP_DW_STCS) __stcs(reinterpret_cast<uint2 *>(p), make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi)));
+    else *reinterpret_cast<uint2 *>(p) = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
   }
 };
 template <> struct SmemVec4<float> {
@@ -376,6 +381,7 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int c = 0; c < CC; ++c) acc[r][c][0] = acc[r][c][1] = make_float2(0.f, 0.f);
+    if (!(p.debug & 1))
 #pragma unroll
     for (int iy = 0; iy < NROW; ++iy) {
       const uint32_t rowp = win + (uint32_t)(iy * row_bytes);
@@ -407,7 +413,7 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict
       T *oq = op;
 #pragma unroll
       for (int c = 0; c < CC; ++c) {
-        if (full || (yo0 + r < p.Ho && xo0 + c < p.Wo))
+        if (!(p.debug & 2) && (full || (yo0 + r < p.Ho && xo0 + c < p.Wo)))
           SmemVec4<T>::template store<ACT>(oq, __ffma2_rn(acc[r][c][0], sc[0], sh[0]), __ffma2_rn(acc[r][c][1], sc[1], sh[1]));
         oq += opix;
       }
@@ -580,6 +586,7 @@ int depthwise_tma_launch(bool f32, const CUtensorMap &tm, void *out, const float
   p.n = n; p.H = H; p.W = W; p.C = C; p.Ho = g.Ho; p.Wo = g.Wo; p.tw = g.tw; p.th = g.th; p.iw = g.iw; p.ih = g.ih;
   p.cb = g.cb; p.cq = g.cv; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y; p.cblocks = g.cblocks;
   p.sp_tiles = g.num_tiles; p.act = act; p.stage_bytes = g.stage_bytes; p.stages = 2;
+  p.debug = getenv("LWP_DEBUG_DW") ? atoi(getenv("LWP_DEBUG_DW")) : 0;
   if (f32) return depthwise_tma_launch_t<float>(tm, (float *)out, w9c, scale, shift, p, stride, dil, st);
   return depthwise_tma_launch_t<__nv_bfloat16>(tm, (__nv_bfloat16 *)out, w9c, scale, shift, p, stride, dil, st);
 }

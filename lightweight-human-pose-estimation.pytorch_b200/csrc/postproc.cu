@@ -501,7 +501,7 @@ __device__ __forceinline__ double paf_sample(const float *paf, int W, int ld, co
 // their ratios are exactly the reference's; only work on hopeless pairs is skipped.
 // grid = (blocks per limb, 19 limbs, images).
 template <bool kFused, bool kSmem>   // kSmem (fused only): the limb's two stride-8 PAF channels are staged in shared memory
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ counts, int cap_kpts,
                  const float *__restrict__ pafs, int H, int W, int ld, const UpSrc up, int demo,
                  double min_paf_score, Conn *__restrict__ conn, int *__restrict__ conn_count, int cap_conn) {
@@ -958,8 +958,12 @@ static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *cou
       LWP_CUDA_CHECK(cudaFuncSetAttribute(paf_score_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       ps_attr = true;
     }
+    // staged variant: every block copies the limb's two channels first, so use as few blocks per (limb, image) as still
+    // fill the GPU (batches: one block of 8 warps walks all pairs; a single image: up to 8 blocks per limb)
+    int bs = ceil_div(4 * num_sms(), LWP_NUM_LIMBS * n);
+    bs = bs < 1 ? 1 : (bs > 8 ? 8 : bs);
     if (src_bytes <= 200 * 1024)
-      paf_score_kernel<true, true><<<dim3(bx, LWP_NUM_LIMBS, n), 128, src_bytes, st>>>(
+      paf_score_kernel<true, true><<<dim3(bs, LWP_NUM_LIMBS, n), 256, src_bytes, st>>>(
           kpts, counts, cap_kpts, nullptr, H, W, paf_ld, *up, demo, min_paf_score, w.conn, w.conn_count, cap_connections);
     else
       paf_score_kernel<true, false><<<dim3(bx, LWP_NUM_LIMBS, n), 128, 0, st>>>(
