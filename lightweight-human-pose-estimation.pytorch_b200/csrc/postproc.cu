@@ -706,27 +706,43 @@ pose_assemble_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restric
     __syncwarp();
   };
 
+  // per-image tables read once (lane l holds entry l) instead of one dependent global load per limb
+  const int my_cnt = lane < LWP_NUM_KPT_TYPES ? cnts[lane] : 0;
+  const int my_start = lane < LWP_NUM_KPT_TYPES + 1 ? starts[lane] : 0;
+  const int my_m = lane < LWP_NUM_LIMBS ? match_count[img * LWP_NUM_LIMBS + lane] : 0;
+  const Match *Mimg = match + (size_t)img * LWP_NUM_LIMBS * cap_kpts;
+  // the first 32 accepted connections of the NEXT limb are fetched while the current limb is processed
+  Match pre;
+  pre.ratio = 0.0; pre.ida = pre.idb = 0; pre.sa = pre.sb = 0.f;
+  if (lane < __shfl_sync(0xffffffffu, my_m, 0)) pre = Mimg[lane];
+
   for (int limb = 0; limb < LWP_NUM_LIMBS; ++limb) {
     const int ka = c_kpt_ids[limb][0], kb = c_kpt_ids[limb][1];
-    const int nA = cnts[ka], nB = cnts[kb];
+    const int nA = __shfl_sync(0xffffffffu, my_cnt, ka), nB = __shfl_sync(0xffffffffu, my_cnt, kb);
+    const int m = __shfl_sync(0xffffffffu, my_m, limb);
+    const Match cur = pre;
+    if (limb + 1 < LWP_NUM_LIMBS && lane < __shfl_sync(0xffffffffu, my_m, limb + 1))
+      pre = Mimg[(size_t)(limb + 1) * cap_kpts + lane];
     if (nA == 0 && nB == 0) continue;
     if (nA == 0 || nB == 0) {  // :66-92 singleton poses for key-points no pose holds yet
       const int slot = nA == 0 ? kb : ka, cnt = nA == 0 ? nB : nA;
+      const int start = __shfl_sync(0xffffffffu, my_start, slot);
       const lwp_keypoint *K = kpts + ((size_t)img * LWP_NUM_KPT_TYPES + slot) * cap_kpts;
       for (int i = 0; i < cnt; ++i) {
-        double id = (double)(starts[slot] + i);
+        double id = (double)(start + i);
         bool found = false;
         for (int j = lane; j < np; j += 32) found |= (POSE(j)[slot] == id);
         if (!__any_sync(0xffffffffu, found)) append(slot, id, -1, 0.0, (double)K[i].score, 1.0);
       }
       continue;
     }
-    const int m = match_count[img * LWP_NUM_LIMBS + limb];
     if (m == 0) continue;
-    const Match *Mg = match + ((size_t)img * LWP_NUM_LIMBS + limb) * cap_kpts;
+    const Match *Mg = Mimg + (size_t)limb * cap_kpts;
     const Match *M = Mg;
-    if (kSmem) {  // stage this limb's accepted connections with one coalesced read
-      for (int c = lane; c < m; c += 32) s_match[c] = Mg[c];
+    if (kSmem) {  // this limb's accepted connections: the prefetched 32 + (rarely) the rest
+      __syncwarp();
+      if (lane < m) s_match[lane] = cur;
+      for (int c = 32 + lane; c < m; c += 32) s_match[c] = Mg[c];
       __syncwarp();
       M = s_match;
     }
