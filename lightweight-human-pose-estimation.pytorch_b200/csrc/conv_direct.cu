@@ -239,6 +239,8 @@ struct DwTileParams {
   int cb, cq;          // channels per tile, 4-channel groups per pixel (cb/4)
   int tiles_x, tiles_y, cblocks, sp_tiles;   // sp_tiles = n * tiles_x * tiles_y spatial tiles per channel block
   int act, stages;
+  int tma_out;         // 1: outputs staged in smem and written by one TMA tensor store per tile (2 staging buffers)
+  uint32_t stg_bytes;  // tw * th * cb * sizeof(T)
   int debug;           // timing experiments only (LWP_DEBUG_DW): bit 0 skip the window loads + FMAs, bit 1 skip the stores
   uint32_t stage_bytes;
 };
@@ -304,7 +306,8 @@ struct DwTileCursor {  // (image, tile row, tile column) of a spatial tile index
 
 template <typename T, int S, int D, int ACT, int PIXB>   // PIXB: bytes of one pixel of the smem tile (cb * sizeof(T): 64 or 128)
 __global__ void __launch_bounds__(256, 2)
-depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict__ out,
+depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                        T *__restrict__ out,
                         const float *__restrict__ w9c, const float *__restrict__ scale,
                         const float *__restrict__ shift, const DwTileParams p) {
   constexpr int R = 2, CC = 4;                            // outputs per thread: R rows x CC columns (x 4 channels)
@@ -316,6 +319,7 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict
   const int tid = threadIdx.x;
   if (tid == 0) {
     ptx::prefetch_tmap(&tm_in);
+    if (p.tma_out) ptx::prefetch_tmap(&tm_out);
     for (int s = 0; s < p.stages; ++s) ptx::mbar_init(&bars[s], 1);
     ptx::fence_barrier_init();
   }
@@ -366,7 +370,7 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict
   const size_t opix = (size_t)p.C;                        // elements between horizontally adjacent output pixels
   const size_t orow = (size_t)p.Wo * p.C;
 
-  int buf = 0;
+  int buf = 0, it = 0;
   uint32_t phase = 0;
   for (int j = j0; j < p.sp_tiles; j += jstride) {
     if (tid == 0) {  // refill the buffer every thread left at the end of the previous iteration
@@ -406,6 +410,32 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict
       }
     }
     const int yo0 = cur.ty * p.th + yg * R, xo0 = cur.tx * p.tw + xg * CC;
+    if (p.tma_out) {
+      // outputs -> staging tile [th][tw][cb] in shared memory -> one TMA tensor store of the tile (rows / columns past the
+      // image are clipped by the hardware).  Two staging buffers: the store of tile i-1 may still read the other one.
+      uint8_t *stg = bufs + (size_t)p.stages * p.stage_bytes + (size_t)(it & 1) * p.stg_bytes;
+      __syncthreads();   // thread 0 has waited for the store that last read this staging buffer (two tiles ago)
+      T *sp = reinterpret_cast<T *>(stg + ((yg * R) * p.tw + xg * CC) * PIXB) + cq * 4;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < CC; ++c)
+          SmemVec4<T>::template store<ACT>(sp + (r * p.tw + c) * (PIXB / (int)sizeof(T)), __ffma2_rn(acc[r][c][0], sc[0], sh[0]),
+                                           __ffma2_rn(acc[r][c][1], sc[1], sh[1]));
+      ptx::fence_proxy_async();
+      __syncthreads();   // also: everyone is done with input buffer `buf`
+      if (tid == 0) {
+        if (!(p.debug & 2)) {
+          ptx::tma_store_4d(&tm_out, stg, cblk * p.cb, cur.tx * p.tw, cur.ty * p.th, cur.img);
+          ptx::bulk_commit();
+        }
+        ptx::bulk_wait_read<1>();   // the previous tile's store has finished reading the other staging buffer
+      }
+      cur.advance(step, p.tiles_x, p.tiles_y);
+      ++it;
+      if (++buf == p.stages) { buf = 0; phase ^= 1u; }
+      continue;
+    }
     T *op = out + (((size_t)cur.img * p.Ho + yo0) * p.Wo + xo0) * p.C + c0;
     const bool full = yo0 + R <= p.Ho && xo0 + CC <= p.Wo;
 #pragma unroll
@@ -423,6 +453,7 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, T *__restrict
     __syncthreads();  // everyone is done with buffer `buf` before it is refilled at the top of the next iteration
     if (++buf == p.stages) { buf = 0; phase ^= 1u; }
   }
+  if (p.tma_out && tid == 0) ptx::bulk_wait<0>();   // all tensor stores have landed
 }
 
 // NHWC (T or float, pixel stride ld, channels [c0, c0 + c)) -> NCHW float32 [n][c][H][W]
@@ -541,17 +572,19 @@ int depthwise_tma_init() {
 }
 
 template <typename T>
-static int depthwise_tma_launch_t(const CUtensorMap &tm, T *out, const float *w9c, const float *scale,
+static int depthwise_tma_launch_t(const CUtensorMap &tm, const CUtensorMap &tm_out, T *out, const float *w9c, const float *scale,
                                   const float *shift, DwTileParams p, int stride, int dil, cudaStream_t st) {
   // two CTAs per SM with a ring of up to 4 halo boxes each; big (stride-2) boxes: one CTA per SM
   int per_sm = 2;
-  int stages = (int)((100 * 1024) / p.stage_bytes);
-  if (stages < 2) { per_sm = 1; stages = (int)((200 * 1024) / p.stage_bytes); }
+  p.stg_bytes = (uint32_t)(p.tw * p.th * p.cb * (int)sizeof(T));
+  const size_t stg = p.tma_out ? 2 * (size_t)p.stg_bytes : 0;
+  int stages = (int)((100 * 1024 - stg) / p.stage_bytes);
+  if (stages < 2) { per_sm = 1; stages = (int)((200 * 1024 - stg) / p.stage_bytes); }
   if (stages > kDwMaxStages) stages = kDwMaxStages;
   if (stages < 2) { set_error("depthwise: halo box of %u bytes does not fit twice in shared memory", p.stage_bytes); return LWP_ECAP; }
   if (const char *e = getenv("LWP_DW_STAGES")) { int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
   p.stages = stages;
-  const size_t smem = 128 + 128 + (size_t)stages * p.stage_bytes;
+  const size_t smem = 128 + 128 + (size_t)stages * p.stage_bytes + stg;
   int per_cblk = num_sms() * per_sm / p.cblocks;
   if (per_cblk < 1) per_cblk = 1;
   if (per_cblk > p.sp_tiles) per_cblk = p.sp_tiles;
@@ -561,13 +594,13 @@ static int depthwise_tma_launch_t(const CUtensorMap &tm, T *out, const float *w9
 #define LWP_DW_GO(S_, D_)                                                                                             \
   do {                                                                                                              \
     if (pixb == 128) {                                                                                              \
-      if (p.act == LWP_ACT_RELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_RELU, 128>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
-      else if (p.act == LWP_ACT_ELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_ELU, 128>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
-      else LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_NONE, 128>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
+      if (p.act == LWP_ACT_RELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_RELU, 128>, grid, 256, smem, st, 1, tm, tm_out, out, w9c, scale, shift, p)); \
+      else if (p.act == LWP_ACT_ELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_ELU, 128>, grid, 256, smem, st, 1, tm, tm_out, out, w9c, scale, shift, p)); \
+      else LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_NONE, 128>, grid, 256, smem, st, 1, tm, tm_out, out, w9c, scale, shift, p)); \
     } else {                                                                                                        \
-      if (p.act == LWP_ACT_RELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_RELU, 64>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
-      else if (p.act == LWP_ACT_ELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_ELU, 64>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
-      else LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_NONE, 64>, grid, 256, smem, st, 1, tm, out, w9c, scale, shift, p)); \
+      if (p.act == LWP_ACT_RELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_RELU, 64>, grid, 256, smem, st, 1, tm, tm_out, out, w9c, scale, shift, p)); \
+      else if (p.act == LWP_ACT_ELU) LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_ELU, 64>, grid, 256, smem, st, 1, tm, tm_out, out, w9c, scale, shift, p)); \
+      else LWP_CUDA_CHECK(launch_pdl(depthwise3x3_tma_kernel<T, S_, D_, LWP_ACT_NONE, 64>, grid, 256, smem, st, 1, tm, tm_out, out, w9c, scale, shift, p)); \
     }                                                                                                               \
   } while (0)
   if (stride == 1 && dil == 1) LWP_DW_GO(1, 1);
@@ -579,7 +612,7 @@ static int depthwise_tma_launch_t(const CUtensorMap &tm, T *out, const float *w9
   return LWP_OK;
 }
 
-int depthwise_tma_launch(bool f32, const CUtensorMap &tm, void *out, const float *w9c, const float *scale,
+int depthwise_tma_launch(bool f32, const CUtensorMap &tm, const CUtensorMap *tm_out, void *out, const float *w9c, const float *scale,
                          const float *shift, int n, int H, int W, int C, int stride, int dil, int act,
                          const DwTileGeom &g, cudaStream_t st) {
   DwTileParams p;
@@ -587,8 +620,10 @@ int depthwise_tma_launch(bool f32, const CUtensorMap &tm, void *out, const float
   p.cb = g.cb; p.cq = g.cv; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y; p.cblocks = g.cblocks;
   p.sp_tiles = g.num_tiles; p.act = act; p.stage_bytes = g.stage_bytes; p.stages = 2;
   p.debug = getenv("LWP_DEBUG_DW") ? atoi(getenv("LWP_DEBUG_DW")) : 0;
-  if (f32) return depthwise_tma_launch_t<float>(tm, (float *)out, w9c, scale, shift, p, stride, dil, st);
-  return depthwise_tma_launch_t<__nv_bfloat16>(tm, (__nv_bfloat16 *)out, w9c, scale, shift, p, stride, dil, st);
+  p.tma_out = tm_out != nullptr ? 1 : 0;
+  const CUtensorMap &tmo = tm_out != nullptr ? *tm_out : tm;
+  if (f32) return depthwise_tma_launch_t<float>(tm, tmo, (float *)out, w9c, scale, shift, p, stride, dil, st);
+  return depthwise_tma_launch_t<__nv_bfloat16>(tm, tmo, (__nv_bfloat16 *)out, w9c, scale, shift, p, stride, dil, st);
 }
 
 int nhwc_to_nchw_launch(bool in_f32, const void *in, int ld, int c0, int c, float *out, int n, int HW,

@@ -19,7 +19,7 @@ struct DwTileGeom {
 };
 int depthwise_tma_geometry(bool f32, int n, int H, int W, int C, int stride, int dil, DwTileGeom *g);
 int depthwise_tma_init();
-int depthwise_tma_launch(bool f32, const CUtensorMap &tm, void *out, const float *w9c, const float *scale,
+int depthwise_tma_launch(bool f32, const CUtensorMap &tm, const CUtensorMap *tm_out /* NULL: register stores */, void *out, const float *w9c, const float *scale,
                          const float *shift, int n, int H, int W, int C, int stride, int dil, int act,
                          const DwTileGeom &g, cudaStream_t st);
 int nhwc_to_nchw_launch(bool in_f32, const void *in, int ld, int c0, int c, float *out, int n, int HW,

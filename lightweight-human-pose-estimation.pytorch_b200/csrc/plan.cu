@@ -55,7 +55,7 @@ struct Op {
   bool stem_u8 = false;          // stem reads a uint8 HWC frame and normalises it on the fly
   double mean[3] = {0, 0, 0}, img_scale = 1.0;
   DwTileGeom dwg;
-  bool dw_tma = false;
+  bool dw_tma = false, dw_tma_out = false;   // (tmB = output map of the depthwise kernel)
   // gemm (tmA is also the input map of the TMA depthwise kernel)
   CUtensorMap tmA, tmB, tmC;
   GemmParams gp;
@@ -168,6 +168,17 @@ extern "C" int lwp_plan_add_depthwise(lwp_plan *p, const void *in, void *out, co
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(depthwise) failed: %d", (int)r); return LWP_ECUDA; }
     op.dw_tma = true;
+    // output tensor map: one TMA store per tile (LWP_DW_TMA_STORE=0: register stores)
+    op.dw_tma_out = false;
+    if (getenv("LWP_DW_TMA_STORE") == nullptr || atoi(getenv("LWP_DW_TMA_STORE")) != 0) {
+      cuuint64_t odims[4] = {(cuuint64_t)C, (cuuint64_t)op.dwg.Wo, (cuuint64_t)op.dwg.Ho, (cuuint64_t)n};
+      cuuint64_t ostr[3] = {(cuuint64_t)C * es, (cuuint64_t)C * es * op.dwg.Wo, (cuuint64_t)C * es * op.dwg.Wo * op.dwg.Ho};
+      cuuint32_t obox[4] = {(cuuint32_t)op.dwg.cb, (cuuint32_t)op.dwg.tw, (cuuint32_t)op.dwg.th, 1};
+      CUresult ro = get_encode_fn()(&op.tmB, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, odims,
+                                    ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      op.dw_tma_out = ro == CUDA_SUCCESS && ((uintptr_t)out % 16) == 0;
+    }
   }
   p->ops.push_back(op);
   return LWP_OK;
@@ -566,7 +577,7 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const void *x, int first, int las
         break;
       case OP_DW:
         if (op.dw_tma)
-          rc = depthwise_tma_launch(f32, op.tmA, op.out, op.w, op.scale, op.shift, op.n, op.H, op.W, op.C, op.stride,
+          rc = depthwise_tma_launch(f32, op.tmA, op.dw_tma_out ? &op.tmB : nullptr, op.out, op.w, op.scale, op.shift, op.n, op.H, op.W, op.C, op.stride,
                                     op.dil, op.act, op.dwg, st);
         else
           rc = depthwise_launch(f32, op.in, op.out, op.w, op.scale, op.shift, op.n, op.H, op.W, op.C, op.stride,
