@@ -171,6 +171,10 @@ stem_gemm_kernel(const StemGemmParams p) {
   uint32_t phases = 0u;   // bit s: parity the next wait on bars[s] expects
   for (int s = 0; t < p.tiles; t += gridDim.x, s ^= 1) {
     const int tn = t + gridDim.x;
+    if constexpr (!kTf32) {   // the bulk store of the previous tile has finished reading its staging rows (= stage s ^ 1)
+      if (lane == 0) ptx::bulk_wait_read<0>();
+      __syncwarp();
+    }
     if (tn < p.tiles) {   // next tile's A rows while this tile's MMA runs; stage s^1 and its accumulator were released by
       build(tn, s ^ 1);   // the previous iteration (its MMA was waited for, its accumulator drained)
       ptx::fence_proxy_async();
@@ -193,18 +197,36 @@ stem_gemm_kernel(const StemGemmParams p) {
         float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + pix * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) op[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-      } else {
-        uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * 32);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 pk;
-          __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(y[8 * j + 2 * q], y[8 * j + 2 * q + 1]);
-          op[j] = pk;
-        }
       }
     }
+    if constexpr (!kTf32) {
+      // bf16: the warp's 32 pixels are 2 KB of contiguous output.  They are staged in the warp's own rows of the A tile
+      // the MMA has just finished reading (only this warp rewrites those rows, in build() two tiles later) and leave
+      // as ONE bulk copy instead of 4 x 32 scattered 16-byte stores.
+      uint8_t *stg = a_tiles + s * kATileBytes + warp * 4096;
+      float y[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) y[c] = fmaxf(fmaf(__uint_as_float(r[c]), s_scale[c], s_shift[c]), 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(y[8 * j + 2 * q], y[8 * j + 2 * q + 1]);
+        *reinterpret_cast<uint4 *>(stg + lane * 64 + j * 16) = pk;
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      const long long pix0 = (long long)t * kBlockM + warp * 32;
+      if (lane == 0 && pix0 < p.total) {
+        const long long left = p.total - pix0;
+        ptx::bulk_store_1d(reinterpret_cast<__nv_bfloat16 *>(p.out) + pix0 * 32, stg, (uint32_t)(left < 32 ? left : 32) * 64u);
+        ptx::bulk_commit();
+      }
+    }
+  }
+  if constexpr (!kTf32) {
+    if (lane == 0) ptx::bulk_wait<0>();
   }
   ptx::tc_fence_before();
   __syncthreads();
