@@ -11,8 +11,8 @@ import bench  # noqa: E402
 
 
 def main():
-    names = sys.argv[1:] or ["model.1.pw", "model.8.dw", "model.8.pw", "initial_stage.trunk.0", "initial_stage.heads.0",
-                             "refinement_stages.0.trunk.0.trunk.1", "postproc"]
+    names = sys.argv[1:] or ["model.0", "model.1.pw", "model.8.dw", "model.8.pw", "initial_stage.trunk.0",
+                             "initial_stage.heads.fused", "refinement_stages.0.trunk.0.trunk.1", "postproc"]
     import lwpose_b200  # noqa: F401
     from lwpose_b200 import synth
     from lwpose_b200.pipeline import PosePipeline
