@@ -65,6 +65,9 @@ def _rel(a, b):
     (2, 23, 41, 128, 128, 9, 1, 1, False),    # 3x3 ragged
     (1, 46, 82, 128, 128, 9, 2, 1, True),     # 3x3 dilation 2 + residual
     (3, 32, 57, 128, 128, 9, 1, 1, False),    # config-1 grid
+    (5, 17, 9, 128, 128, 9, 2, 1, True),      # strip kernel: odd tile count (one CTA of the last pair idles), narrow map
+    (1, 8, 8, 128, 128, 9, 1, 1, False),      # fewer than 128 pixels: tap-by-tap kernel
+    (2, 20, 24, 64, 128, 9, 1, 0, False),     # 3x3 with one K block per tap, no activation
 ])
 def test_conv_gemm_vs_torch(env, precision, shape):
     torch, _lib, engine = env
