@@ -658,15 +658,22 @@ limb_match_kernel(const Conn *__restrict__ conn, const int *__restrict__ conn_co
       if (ok) {
         if (lane == b) {
           usedA[c.i] = 1; usedB[c.j] = 1;
-          Match mt;
-          mt.ratio = c.ratio; mt.ida = a0 + c.i; mt.idb = b0 + c.j;
-          mt.sa = A[c.i].score; mt.sb = B[c.j].score;
-          out[accepted] = mt;
+          cs[accepted] = c;   // accepted connections are compacted in place (accepted <= the index just read)
         }
         ++accepted;
       }
       __syncwarp();
     }
+  }
+  __syncwarp();
+  // the key-point scores are fetched for all accepted connections at once (a dependent global load inside the greedy
+  // loop would serialise one memory round trip per connection)
+  for (int t = lane; t < accepted; t += 32) {
+    const Conn c = cs[t];
+    Match mt;
+    mt.ratio = c.ratio; mt.ida = a0 + c.i; mt.idb = b0 + c.j;
+    mt.sa = A[c.i].score; mt.sb = B[c.j].score;
+    out[t] = mt;
   }
   if (lane == 0) match_count[slot] = accepted;
 }
