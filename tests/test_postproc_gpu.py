@@ -165,6 +165,34 @@ def test_fused_postproc_bit_exact_vs_reference_golden(torch_cuda, case, demo):
     assert np.array_equal(poses.view(np.int64), g[tag + "_poses"].view(np.int64))
 
 
+@pytest.mark.parametrize("demo", [True, False])
+def test_config3_batch256_bit_exact_vs_oracle(torch_cuda, demo):
+    """BASELINE.json configs[2] at full size: 256 synthetic frames of 19 heat-maps / 38 PAFs at 46x82 with 1..30
+    persons (+ noise), up-sampled x4, through the fused batched path -- key-points and pose entries of EVERY frame
+    bit-identical to the oracle."""
+    from lwpose_b200 import postproc, synth
+    from oracle import postproc as orc
+    hm, paf, persons = synth.synthetic_pose_maps(256, 46, 82, seed=0, noise=0.02, max_persons=30)
+    assert min(persons) == 1 and max(persons) == 30
+    kpts_h, counts_h, start_h, poses_h, n_h = _fused_postproc(torch_cuda, hm, paf, demo, cap_kpts=256, cap_cand=8192,
+                                                              cap_poses=512, cap_conn=8192)
+    n_poses = 0
+    for b in range(hm.shape[0]):
+        heat = orc.resize_cubic(np.ascontiguousarray(hm[b].transpose(1, 2, 0)), fx=4, fy=4)
+        pafs = orc.resize_cubic(np.ascontiguousarray(paf[b].transpose(1, 2, 0)), fx=4, fy=4)
+        total, ref_by_type = 0, []
+        for k in range(18):
+            total += orc.extract_keypoints(heat[:, :, k], ref_by_type, total)
+        ref_poses, _ = orc.group_keypoints(ref_by_type, pafs, demo=demo)
+        got = postproc.keypoint_lists(kpts_h, counts_h, start_h, b)
+        assert np.array_equal(gc.pack_keypoints(got), gc.pack_keypoints(ref_by_type)), b
+        gp = np.asarray(postproc.pose_entries_array(poses_h, n_h, b), np.float64).reshape(-1, 20)
+        rp = np.asarray(ref_poses, np.float64).reshape(-1, 20)
+        assert gp.shape == rp.shape and np.array_equal(gp.view(np.int64), rp.view(np.int64)), b
+        n_poses += gp.shape[0]
+    assert n_poses >= sum(persons) // 2   # the synthetic persons are actually found
+
+
 @pytest.mark.parametrize("shape,ratio", [((3, 13, 21), 4), ((2, 46, 82), 4), ((2, 9, 40), 8), ((1, 33, 7), 3)])
 def test_fused_equals_materialised_on_noise(torch_cuda, shape, ratio):
     """Random maps with odd sizes / other ratios: fused and materialising paths give identical tables."""
