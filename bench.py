@@ -37,6 +37,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-u8", action="store_true", help="skip the uint8-frame end-to-end run")
+    ap.add_argument("--no-other-precision", action="store_true", help="skip the device-resident run on the other precision")
     ap.add_argument("--chunk", type=int, default=0, help="frames per pipeline chunk (0 = whole batch)")
     ap.add_argument("--no-overlap-postproc", action="store_true", help="post-processing on the network's stream")
     ap.add_argument("--unfused-postproc", action="store_true", help="materialise the up-sampled maps like the reference")
@@ -302,6 +303,28 @@ def main():
                   "h2d_bytes_per_step": pipe8.h2d_bytes, "d2h_bytes_per_step": pipe8.d2h_bytes,
                   "input": "uint8 BGR frames [n,368,656,3], normalisation fused into the stem"}
         del pipe8
+    # the other arithmetic of BASELINE.json configs[1] ("fp32 and bf16"): the same device-resident measurement on the
+    # other precision's plan (fp32 storage + TF32 tensor-core products when the headline is bf16, and vice versa)
+    other = None
+    if not args.no_other_precision:
+        oprec = "tf32" if args.precision == "bf16" else "bf16"
+        pipe_o = PosePipeline(net, args.batch, HEIGHT, WIDTH, precision=oprec, demo=True,
+                              heads_hook=lambda heads, lo: heads.add_(inject[lo:lo + heads.shape[0]]),
+                              fused=not args.unfused_postproc, chunk=args.chunk or None,
+                              overlap_postproc=not args.no_overlap_postproc)
+        for _ in range(3):
+            pipe_o.run_device(x_dev)
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for _ in range(args.steps):
+            pipe_o.run_device(x_dev)
+        pipe_o.join()
+        o1.record()
+        barrier()
+        o_ms = parallel.max_over_ranks(o0.elapsed_time(o1), device=dev) / args.steps
+        other = {"dtype": oprec, "value": world * args.batch / (o_ms / 1000.0), "unit": "frames/s", "ms_per_step": o_ms}
+        del pipe_o
     # latency of one synchronous call (H2D -> kernels -> D2H, nothing overlapped)
     t0 = time.perf_counter()
     for _ in range(3):
@@ -322,6 +345,7 @@ def main():
         # step, which is PCIe time comparable to the whole step) is reported next to it.
         "e2e": dict(e2e_u8, mode="PosePipeline.submit/collect, 2 batches in flight") if e2e_u8 is not None else e2e_f32,
         "e2e_f32": e2e_f32,
+        "other_precision": other,
         "gpu_launches": pipe.launches_per_step * args.steps,
         "clocks": clocks,
         "poses_per_step_rank0": total_poses, "persons_injected_rank0": int(sum(persons)),

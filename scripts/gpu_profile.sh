@@ -2,7 +2,7 @@
 # plain run, then (same command line) the ncu launch list, then one `--set full` capture of selected layers of a step.
 # Keep captures small: gpurun only merges gpurun_out/ back when it is < 64 MiB.
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-roofline --no-u8"
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-roofline --no-u8 --no-other-precision"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "launch list exit=$?"
