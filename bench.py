@@ -41,7 +41,13 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=0, help="frames per pipeline chunk (0 = whole batch)")
     ap.add_argument("--no-overlap-postproc", action="store_true", help="post-processing on the network's stream")
     ap.add_argument("--unfused-postproc", action="store_true", help="materialise the up-sampled maps like the reference")
+    ap.add_argument("--steady-seconds", type=float, default=2.0, help="length of the extra steady-state run (0 = skip)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config0 / config3 / config4 extra keys")
+    ap.add_argument("--config3-batch", type=int, default=256, help="GLOBAL batch of configs[3] (strong scaling over the ranks)")
     return ap.parse_args()
+
+
+NET_TOL = {"bf16": 3e-3, "tf32": 1e-3}   # max abs error of the heads vs the CPU fp32 oracle (outputs are O(0.1))
 
 
 def peaks():
@@ -109,23 +115,23 @@ class ClockSampler:
         return out
 
 
-def make_net(seed=0):
+def make_net(seed=0, refine=REFINE):
     import torch
     import lwpose_b200  # noqa: F401
     from lwpose_b200 import synth
     from lwpose_b200.models.with_mobilenet import PoseEstimationWithMobileNet
     torch.manual_seed(seed)
-    net = PoseEstimationWithMobileNet(num_refinement_stages=REFINE).eval()
+    net = PoseEstimationWithMobileNet(num_refinement_stages=refine).eval()
     synth.randomize_bn_(net, seed=7)
     return net
 
 
-def person_maps(batch, rank, max_persons):
-    """[batch, 46, 82, 64] float32: synthetic person heat-maps / PAFs in head-buffer layout."""
+def person_maps(batch, rank, max_persons, height=HEIGHT, width=WIDTH):
+    """[batch, h/8, w/8, 64] float32: synthetic person heat-maps / PAFs in head-buffer layout."""
     import numpy as np
     from lwpose_b200 import synth
-    hm, paf, counts = synth.synthetic_pose_maps(batch, HEIGHT // 8, WIDTH // 8, seed=100 + rank, max_persons=max_persons)
-    m = np.zeros((batch, HEIGHT // 8, WIDTH // 8, 64), np.float32)
+    hm, paf, counts = synth.synthetic_pose_maps(batch, height // 8, width // 8, seed=100 + rank, max_persons=max_persons)
+    m = np.zeros((batch, height // 8, width // 8, 64), np.float32)
     m[..., :19] = hm.transpose(0, 2, 3, 1)
     m[..., 19:57] = paf.transpose(0, 2, 3, 1)
     return m, counts
@@ -134,14 +140,19 @@ def person_maps(batch, rank, max_persons):
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's CPU path (reference itself is not on the GPU box)
 # ----------------------------------------------------------------------------------------------
-def cpu_frame(state_dict, x1, inject1):
-    """One frame through the CPU path: torch-CPU forward, cubic x4, 18 x extract, group (demo=True)."""
+def cpu_frame(state_dict, x1, inject1, keep=None):
+    """One frame through the CPU path: torch-CPU forward, cubic x4, 18 x extract, group (demo=True).
+    keep: optional list that receives the frame's raw heads [h, w, 57] (network output before the person maps)."""
     import numpy as np
     from oracle import net as onet
     from oracle import postproc as orc
     outs = onet.forward(state_dict, x1)
-    hm = outs[-2][0].numpy().transpose(1, 2, 0) + inject1[..., :19]
-    paf = outs[-1][0].numpy().transpose(1, 2, 0) + inject1[..., 19:57]
+    hm0 = outs[-2][0].numpy().transpose(1, 2, 0)
+    paf0 = outs[-1][0].numpy().transpose(1, 2, 0)
+    if keep is not None:
+        keep.append(np.concatenate([hm0, paf0], 2))
+    hm = hm0 + inject1[..., :19] if inject1 is not None else hm0
+    paf = paf0 + inject1[..., 19:57] if inject1 is not None else paf0
     heat = orc.resize_cubic(np.ascontiguousarray(hm), fx=4, fy=4)
     pafs = orc.resize_cubic(np.ascontiguousarray(paf), fx=4, fy=4)
     total, by_type = 0, []
@@ -151,15 +162,28 @@ def cpu_frame(state_dict, x1, inject1):
     return len(poses)
 
 
-def cpu_time_frames(state_dict, x, inject, frames, warm=1):
+def cpu_time_frames(state_dict, x, inject, frames, warm=1, keep=None):
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
     for i in range(warm):
         cpu_frame(state_dict, x[i:i + 1], inject[i])
     t0 = time.perf_counter()
     for i in range(frames):
-        cpu_frame(state_dict, x[i % x.shape[0]:i % x.shape[0] + 1], inject[i % inject.shape[0]])
+        cpu_frame(state_dict, x[i % x.shape[0]:i % x.shape[0] + 1], inject[i % inject.shape[0]], keep)
     return time.perf_counter() - t0
+
+
+def raw_heads(pipe, x_dev, frames):
+    """The network's own head output (no person maps) of the first `frames` frames, float32 [frames, h, w, 57] on the host."""
+    import torch
+    hook, pipe.heads_hook = pipe.heads_hook, None
+    try:
+        pipe.run_device(x_dev)
+        pipe.join()
+        torch.cuda.synchronize()
+        return pipe.heads[:frames, :, :, :57].cpu().numpy()
+    finally:
+        pipe.heads_hook = hook
 
 
 def run_reference(args):
@@ -220,8 +244,10 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     import lwpose_b200  # noqa: F401
-    from lwpose_b200 import parallel, synth
+    from lwpose_b200 import _lib, parallel, synth
     from lwpose_b200.pipeline import PosePipeline
+    _lib.load()
+    _lib.refuse_debug_env()   # no timed run with a work-skipping LWP_DEBUG_* switch in the environment
 
     net = make_net().to(dev)
     inject_h, persons = person_maps(args.batch, rank, args.max_persons)
@@ -256,6 +282,28 @@ def main():
     if pipe.error_flag() != 0:
         raise RuntimeError("GEMM pipeline wait timed out (error flag %d)" % pipe.error_flag())
     value = world * args.batch / (ms / 1000.0)
+
+    # ---- steady state: the same loop for >= --steady-seconds (power-cap / clock behaviour of a long run) ----------
+    steady = None
+    if args.steady_seconds > 0:
+        n_steady = max(args.steps, int(args.steady_seconds * 1000.0 / ms) + 1)
+        sampler2 = ClockSampler(local_rank, period_s=0.02) if rank == 0 else None
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(n_steady):
+            pipe.run_device(x_dev)
+        pipe.join()
+        q1.record()
+        barrier()
+        st_ms = parallel.max_over_ranks(q0.elapsed_time(q1), device=dev) / n_steady
+        steady = {"value": world * args.batch / (st_ms / 1000.0), "unit": "frames/s", "ms_per_step": st_ms,
+                  "steps": n_steady, "seconds": st_ms * n_steady / 1000.0,
+                  "clocks": sampler2.stop() if sampler2 else None}
+    cpu_n = max(1, min(args.cpu_frames, args.batch))
+    gpu_heads = {}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gpu_heads[args.precision] = raw_heads(pipe, x_dev, cpu_n)
 
     # ---- end to end through the public API: pinned host frames in, host pose tables out --------------
     # streaming use of PosePipeline (submit / collect, 2 batches in flight): every step's H2D copy and
@@ -324,6 +372,10 @@ def main():
         barrier()
         o_ms = parallel.max_over_ranks(o0.elapsed_time(o1), device=dev) / args.steps
         other = {"dtype": oprec, "value": world * args.batch / (o_ms / 1000.0), "unit": "frames/s", "ms_per_step": o_ms}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            gpu_heads[oprec] = raw_heads(pipe_o, x_dev, cpu_n)
+        if rank == 0 and not args.no_roofline:
+            other["roofline"] = roofline_pass(pipe_o, x_dev, args, precision=oprec, brief=True)
         del pipe_o
     # latency of one synchronous call (H2D -> kernels -> D2H, nothing overlapped)
     t0 = time.perf_counter()
@@ -345,6 +397,7 @@ def main():
         # step, which is PCIe time comparable to the whole step) is reported next to it.
         "e2e": dict(e2e_u8, mode="PosePipeline.submit/collect, 2 batches in flight") if e2e_u8 is not None else e2e_f32,
         "e2e_f32": e2e_f32,
+        "steady_state": steady,
         "other_precision": other,
         "gpu_launches": pipe.launches_per_step * args.steps,
         "clocks": clocks,
@@ -352,14 +405,147 @@ def main():
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # before the roofline pass re-runs single layers
-        out["cpu_baseline"], out["postproc_parity"] = cpu_baseline(net, pipe, x_host, inject_h, res, args)
+        out["cpu_baseline"], out["postproc_parity"], out["net_parity"] = cpu_baseline(net, pipe, x_host, inject_h, res,
+                                                                                      args, gpu_heads)
     if rank == 0 and not args.no_roofline:
         out.update(roofline_pass(pipe, x_dev, args))
+    del pipe
+    if not args.no_configs:
+        out.update(extra_configs(args, net, dev, rank, world, barrier))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
+
+
+def extra_configs(args, net, dev, rank, world, barrier):
+    """The other configurations BASELINE.json names, as extra keys of the same JSON line (the headline stays configs[1])."""
+    out = {}
+    out["config3"] = config3(args, dev, rank, world, barrier)
+    if rank == 0:
+        out["config0_latency"] = config0_latency(args, net, dev)
+    return out
+
+
+def config3(args, dev, rank, world, barrier):
+    """configs[3]: 3 refinement stages, GLOBAL batch 256 at 368x656 split over the ranks (strong scaling: 256 / N
+    frames per GPU), network + grouping, device-resident like `value`."""
+    import numpy as np
+    import torch
+    from lwpose_b200 import parallel, synth
+    from lwpose_b200.pipeline import PosePipeline
+    lo, hi = parallel.shard_range(args.config3_batch, rank, world)
+    per = hi - lo
+    net3 = make_net(refine=3).to(dev)
+    inj_h, _ = person_maps(per, rank, args.max_persons)
+    inject = torch.from_numpy(inj_h).to(dev)
+    base = synth.synthetic_net_input(min(per, 32), HEIGHT, WIDTH, seed=11 + rank).to(dev)
+    x_dev = base.repeat((per + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:per].contiguous()
+    pipe = PosePipeline(net3, per, HEIGHT, WIDTH, precision=args.precision, demo=True,
+                        heads_hook=lambda heads, l: heads.add_(inject[l:l + heads.shape[0]]))
+    for _ in range(3):
+        pipe.run_device(x_dev)
+    barrier()
+    steps = max(3, min(args.steps, 10))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        pipe.run_device(x_dev)
+    pipe.join()
+    b.record()
+    barrier()
+    ms = parallel.max_over_ranks(a.elapsed_time(b), device=dev) / steps
+    res = {"workload": "configs[3]: R=3 network, global batch %d @368x656 split %d per GPU over %d GPU(s), + person maps, "
+                       "cubic x4, extract, group" % (args.config3_batch, per, world),
+           "value": args.config3_batch / (ms / 1000.0), "unit": "frames/s", "ms_per_step": ms, "steps": steps,
+           "scaling": "strong", "dtype": args.precision, "global_batch": args.config3_batch, "frames_per_gpu": per,
+           "poses_rank0": int(pipe.n_poses.sum().item())}
+    if rank == 0 and not args.no_roofline:
+        rf = roofline_pass(pipe, x_dev, args, brief=True)
+        res["roofline_gemm3x3"] = rf.get("roofline_gemm3x3")
+        res["roofline"] = rf.get("roofline")
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import net as onet
+        sd = {k: v.detach().cpu() for k, v in net3.state_dict().items()}
+        gh = raw_heads(pipe, x_dev, 2)
+        ref = onet.forward(sd, x_dev[:2].cpu())
+        rh = np.concatenate([ref[-2].numpy(), ref[-1].numpy()], 1).transpose(0, 2, 3, 1)
+        err = float(np.abs(gh - rh).max())
+        res["net_parity"] = {"max_abs_err": err, "tol": NET_TOL[args.precision], "frames": 2}
+        if not err < NET_TOL[args.precision]:
+            raise RuntimeError("config3 net_parity FAILED: %g" % err)
+    del pipe
+    return res
+
+
+def config0_latency(args, net, dev):
+    """configs[0]: ONE 1x3x256x456 frame end to end -- the only thing the reference itself ever runs (demo.py:91-100).
+    (a) the drop-in call pattern infer_fast + 18 x extract_keypoints + group_keypoints on a 720p frame, (b) the
+    batch-1 PosePipeline replaying one CUDA graph per pass, (c) the CPU port of the reference on the same frame."""
+    import cv2
+    import numpy as np
+    import torch
+    from lwpose_b200 import demo, synth, val
+    from lwpose_b200.pipeline import PosePipeline
+    H0, W0 = 256, 456
+    img = np.random.default_rng(0).integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+    scale = H0 / img.shape[0]
+    scaled = cv2.resize(img, (0, 0), fx=scale, fy=scale, interpolation=cv2.INTER_CUBIC)
+    # pad with the mean: the stem normalises (128 - 128) / 256 = 0, the reference's pad value in the normalised image
+    padded_u8, pad = val.pad_width(scaled, 8, (128, 128, 128), [H0, max(scaled.shape[1], H0)])
+    assert padded_u8.shape == (H0, W0, 3), padded_u8.shape
+    hm, paf, _ = synth.synthetic_pose_maps(1, H0 // 8, W0 // 8, seed=5, persons=5)
+    inj_h = np.zeros((1, H0 // 8, W0 // 8, 64), np.float32)
+    inj_h[..., :19] = hm.transpose(0, 2, 3, 1)
+    inj_h[..., 19:57] = paf.transpose(0, 2, 3, 1)
+    inject = torch.from_numpy(inj_h).to(dev)
+    out = {"workload": "configs[0]: one 720x1280 BGR frame -> 1x3x256x456, R=1 network, 5 synthetic persons added to the "
+                       "heads, cubic x4, extract, group (demo=True)", "dtype": args.precision, "unit": "ms per frame"}
+    # (b) batch-1 pipeline, one CUDA graph per pass; frame already resized + padded on the host (uint8)
+    x8 = torch.from_numpy(np.ascontiguousarray(padded_u8[None])).pin_memory()
+    for graph in (True, False):
+        pipe = PosePipeline(net, 1, H0, W0, precision=args.precision, demo=True, input_format="u8_nhwc", depth=1,
+                            graph=graph, heads_hook=lambda heads, l: heads.add_(inject[l:l + heads.shape[0]]))
+        for _ in range(5):
+            r = pipe(x8)
+        ts = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            r = pipe(x8)
+            ts.append((time.perf_counter() - t0) * 1000.0)
+        ts.sort()
+        key = "pipeline_graph" if graph else "pipeline_stream_launches"
+        out[key] = {"median_ms": ts[len(ts) // 2], "p90_ms": ts[int(len(ts) * 0.9)], "frames_per_s": 1000.0 / ts[len(ts) // 2],
+                    "poses": r.check().total_poses(), "h2d_bytes": pipe.h2d_bytes, "d2h_bytes": pipe.d2h_bytes}
+        del pipe
+    # (a) the reference's own call pattern through the drop-in functions (host cv2 resize, maps back on the host,
+    # 18 + 1 synchronous post-processing calls)
+    net.precision = args.precision
+    for _ in range(2):
+        demo.run_frame(net, img, H0)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        demo.run_frame(net, img, H0)
+    out["dropin_run_frame_ms"] = (time.perf_counter() - t0) / 10 * 1000.0
+    # (c) CPU port of the reference on the same frame (host resize + normalise + pad + fp32 forward + post-processing)
+    if not args.no_cpu_baseline:
+        sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+
+        def cpu_once():
+            sc = cv2.resize(img, (0, 0), fx=scale, fy=scale, interpolation=cv2.INTER_CUBIC)
+            pd, _ = val.pad_width(val.normalize(sc, (128, 128, 128), 1 / 256), 8, (0, 0, 0), [H0, max(sc.shape[1], H0)])
+            x = torch.from_numpy(pd).permute(2, 0, 1).unsqueeze(0).float()
+            return cpu_frame(sd, x, inj_h[0])
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu_once()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            n_cpu = cpu_once()
+        out["cpu_port_ms"] = (time.perf_counter() - t0) / 5 * 1000.0
+        out["cpu_port_poses"] = n_cpu
+        out["cpu_cores"] = torch.get_num_threads()
+    return out
 
 
 def ncu_traffic(prefixes):
@@ -378,7 +564,7 @@ def ncu_traffic(prefixes):
         os.path.relpath(files[-1], ROOT).replace("dram_traffic_bytes.json", "ncu_full_layers.csv"), len(vals))
 
 
-def roofline_pass(pipe, x_dev, args):
+def roofline_pass(pipe, x_dev, args, precision=None, brief=False):
     """Per-kernel device time (CUDA events on the launching stream, op by op, after the timed region) ->
     achieved TFLOP/s of the tcgen05 GEMM kernel and GB/s of the depthwise kernel vs the measured peaks.
     Times are summed over the chunks of one step."""
@@ -414,14 +600,15 @@ def roofline_pass(pipe, x_dev, args):
     gemm_flops = sum(agg[k]["flops"] for k in tc_kinds)
     gemm_launches = sum(agg[k]["launches"] for k in tc_kinds)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    peak = pk["bf16"] if args.precision == "bf16" else pk["bf16"] / 2.0
+    precision = precision or args.precision
+    peak = pk["bf16"] if precision == "bf16" else pk["bf16"] / 2.0
     traffic, traffic_src = ncu_traffic(("conv_gemm", "conv3x3_pair", "dwpw_gemm_kernel"))
     res = {"roofline": {"kernel": "tcgen05 implicit-GEMM kernels conv_gemm_kernel / conv_gemm2_kernel / conv3x3_pair_kernel%s (all %d launches of a "
                                   "step; %.0f %% of the network time)" % (" / dwpw_gemm_kernel" if "dwpw" in agg else "", gemm_launches,
                                                                          100.0 * gemm_ms / max(sum(times), 1e-9)),
                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                        "peak_source": pk["source"] + (" bf16 sustained" if args.precision == "bf16"
+                        "peak_source": pk["source"] + (" bf16 sustained" if precision == "bf16"
                                                        else " bf16 sustained / 2 (tf32 nominal ratio)"),
                         "algorithmic_flops_per_launch": gemm_flops / max(gemm_launches, 1),
                         "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "ms_per_step": gemm_ms}}
@@ -456,6 +643,9 @@ def roofline_pass(pipe, x_dev, args):
                                      "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                                      "traffic": traffic_d, "traffic_source": src_d, "ms_per_step": d["ms"]}
     res["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in agg.items()}
+    if brief:   # the other precision of configs[1]: the three roofline objects only
+        return {k: {kk: vv for kk, vv in v.items() if kk in ("bound", "achieved", "peak", "unit", "frac", "ms_per_step")}
+                for k, v in res.items() if k.startswith("roofline")}
     res["kernel_ms_per_step"].update(postproc_stage_ms(pipe, x_dev, reps))
     res["layer_ms"] = {n: round(t, 4) for n, t in zip(plan0.op_names[:nops], times)}
     return res
@@ -482,19 +672,31 @@ def postproc_stage_ms(pipe, x_dev, reps):
     return out
 
 
-def cpu_baseline(net, pipe, x_host, inject_h, res, args):
-    """The oracle port of the reference's CPU path timed on this box's host cores on a bounded sample,
-    plus a bit-exactness check of the GPU post-processing against the oracle on the GPU's own maps."""
+def cpu_baseline(net, pipe, x_host, inject_h, res, args, gpu_heads):
+    """The oracle port of the reference's CPU path timed on this box's host cores on a bounded sample; the heads the
+    GPU network produced for those very frames compared with the CPU fp32 forward (net_parity: the run FAILS above the
+    stated tolerance -- a wrong network cannot print a number); and a bit-exactness check of the GPU post-processing
+    against the oracle on the GPU's own maps."""
     import numpy as np
     import torch
     from lwpose_b200 import postproc
     from oracle import postproc as orc
     sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
     frames = max(1, min(args.cpu_frames, args.batch))
-    dt = cpu_time_frames(sd, x_host[:frames], inject_h[:frames], frames)
+    cpu_heads = []
+    dt = cpu_time_frames(sd, x_host[:frames], inject_h[:frames], frames, keep=cpu_heads)
     base = {"value": frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": "%d of the %d frames of one step, batch-1 loop: torch CPU fp32 forward + C oracle cubic x4 / "
                       "extract / group" % (frames, args.batch)}
+    cpu_heads = np.stack(cpu_heads)
+    net_parity = {}
+    for prec, gh in gpu_heads.items():
+        err = float(np.abs(gh[:frames] - cpu_heads).max())
+        net_parity[prec] = {"max_abs_err": err, "tol": NET_TOL[prec], "frames": frames,
+                            "ref_max_abs": float(np.abs(cpu_heads).max()),
+                            "what": "last-stage heat-maps + PAFs [frames,46,82,57] of the timed batch, GPU %s vs torch CPU fp32 oracle" % prec}
+        if not err < NET_TOL[prec]:
+            raise RuntimeError("net_parity FAILED: %s heads differ from the CPU fp32 oracle by %g (tol %g)" % (prec, err, NET_TOL[prec]))
     # parity: oracle post-processing on the maps the GPU actually produced (heads + injected persons)
     heads = pipe.heads.cpu().numpy()
     checked = 0
@@ -509,9 +711,9 @@ def cpu_baseline(net, pipe, x_host, inject_h, res, args):
         rp = np.asarray(ref_poses, np.float64).reshape(-1, 20)
         gp = np.asarray(got_poses, np.float64).reshape(-1, 20)
         if rp.shape != gp.shape or not np.array_equal(rp.view(np.int64), gp.view(np.int64)):
-            return base, "MISMATCH on frame %d" % b
+            raise RuntimeError("postproc_parity FAILED: pose table of frame %d differs from the oracle" % b)
         checked += 1
-    return base, "bit-exact pose tables vs oracle on %d frames" % checked
+    return base, "bit-exact pose tables vs oracle on %d frames" % checked, net_parity
 
 
 if __name__ == "__main__":

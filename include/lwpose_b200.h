@@ -45,6 +45,9 @@ extern "C" {
 
 int lwp_version(void);
 const char *lwp_last_error(void);
+/* 1 if the library was built with -DLWP_TIMING_EXPERIMENTS (kernels honour the LWP_DEBUG_* work-skipping switches and
+ * results may be wrong by design); 0 for a release build, where those code paths do not exist. */
+int lwp_timing_experiments(void);
 /* 0 if device `dev` can run this library (compute capability 10.x). */
 int lwp_check_device(int dev);
 

@@ -15,6 +15,7 @@ _c_double = ctypes.c_double
 SIGNATURES = {
     "lwp_version": (_c_int, []),
     "lwp_last_error": (ctypes.c_char_p, []),
+    "lwp_timing_experiments": (_c_int, []),
     "lwp_check_device": (_c_int, [_c_int]),
     "lwp_upsample_cubic": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_int,
                                     _c_double, _c_double, _c_void_p]),
@@ -74,8 +75,24 @@ def load():
             fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
+        refuse_debug_env(L)
         _lib = L
     return _lib
+
+
+def refuse_debug_env(L=None):
+    """The LWP_DEBUG_* switches make kernels skip loads / MMAs / epilogues (timing experiments: results are wrong by
+    design).  A release library ignores them, but a run that has them set is refused anyway, so that no timed or
+    product run can ever be taken with one of them in the environment; only a library built with
+    -DLWP_TIMING_EXPERIMENTS (lwp_timing_experiments() == 1) together with LWP_ALLOW_TIMING_EXPERIMENTS=1 accepts them."""
+    bad = sorted(k for k, v in os.environ.items() if k.startswith("LWP_DEBUG_") and v not in ("", "0"))
+    if not bad:
+        return
+    L = L if L is not None else _lib
+    experiments = L is not None and L.lwp_timing_experiments() == 1 and os.environ.get("LWP_ALLOW_TIMING_EXPERIMENTS") == "1"
+    if not experiments:
+        raise LwpError("refusing to run with %s set: these switches skip work inside the kernels (timing experiments "
+                       "only; needs a -DLWP_TIMING_EXPERIMENTS build and LWP_ALLOW_TIMING_EXPERIMENTS=1)" % ", ".join(bad))
 
 
 def check(rc, what):

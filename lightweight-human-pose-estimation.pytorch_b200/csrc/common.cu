@@ -15,14 +15,14 @@ void set_error(const char *fmt, ...) {
 }
 
 int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        sms <= 0)
-      sms = 148;
+  static int sms[kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  int &s = sms[dev % kMaxDevices];
+  if (s == 0) {
+    if (cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || s <= 0) s = 148;
   }
-  return sms;
+  return s;
 }
 
 bool pdl_enabled() {
@@ -33,7 +33,15 @@ bool pdl_enabled() {
 
 }  // namespace lwp
 
-extern "C" int lwp_version(void) { return 100; }
+extern "C" int lwp_version(void) { return 200; }
+
+extern "C" int lwp_timing_experiments(void) {
+#ifdef LWP_TIMING_EXPERIMENTS
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 extern "C" const char *lwp_last_error(void) { return lwp::g_err; }
 

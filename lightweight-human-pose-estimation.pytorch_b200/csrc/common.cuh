@@ -38,7 +38,32 @@ void set_error(const char *fmt, ...);
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int num_sms();
+int num_sms();   // SM count of the CURRENT device (cached per device ordinal)
+
+// One-time set-up that is per DEVICE (cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is): a process that drives
+// several GPUs must repeat it on each of them.
+constexpr int kMaxDevices = 64;
+struct DeviceOnce {
+  bool done[kMaxDevices] = {};
+  // true while the current device still needs the set-up; *slot = index to mark in `done` afterwards
+  bool pending(int *slot) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+    *slot = d % kMaxDevices;
+    return !done[*slot];
+  }
+};
+
+// Timing-experiment switches (LWP_DEBUG_GEMM / _DW / _HEADS / _DWPW skip loads, MMAs or epilogues: results are wrong
+// by design).  They only exist in a library built with -DLWP_TIMING_EXPERIMENTS; the release build compiles the
+// branches out (LWP_DBG(x) is the constant 0) and lwp_timing_experiments() reports 0.
+#ifdef LWP_TIMING_EXPERIMENTS
+#define LWP_DBG(x) (x)
+static inline int debug_env(const char *name) { const char *e = getenv(name); return e ? atoi(e) : 0; }
+#else
+#define LWP_DBG(x) 0
+static inline int debug_env(const char *) { return 0; }
+#endif
 
 // Programmatic dependent launch: a kernel launched through launch_pdl may begin (prologue: barrier init, TMEM
 // allocation, tensor-map prefetch, constant loads) while the previous kernel of the stream is still draining; it must

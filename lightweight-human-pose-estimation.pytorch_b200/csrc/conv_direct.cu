@@ -385,7 +385,7 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int c = 0; c < CC; ++c) acc[r][c][0] = acc[r][c][1] = make_float2(0.f, 0.f);
-    if (!(p.debug & 1))
+    if (!(LWP_DBG(p.debug) & 1))
 #pragma unroll
     for (int iy = 0; iy < NROW; ++iy) {
       const uint32_t rowp = win + (uint32_t)(iy * row_bytes);
@@ -425,7 +425,7 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       ptx::fence_proxy_async();
       __syncthreads();   // also: everyone is done with input buffer `buf`
       if (tid == 0) {
-        if (!(p.debug & 2)) {
+        if (!(LWP_DBG(p.debug) & 2)) {
           ptx::tma_store_4d(&tm_out, stg, cblk * p.cb, cur.tx * p.tw, cur.ty * p.th, cur.img);
           ptx::bulk_commit();
         }
@@ -443,7 +443,7 @@ depthwise3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       T *oq = op;
 #pragma unroll
       for (int c = 0; c < CC; ++c) {
-        if (!(p.debug & 2) && (full || (yo0 + r < p.Ho && xo0 + c < p.Wo)))
+        if (!(LWP_DBG(p.debug) & 2) && (full || (yo0 + r < p.Ho && xo0 + c < p.Wo)))
           SmemVec4<T>::template store<ACT>(oq, __ffma2_rn(acc[r][c][0], sc[0], sh[0]), __ffma2_rn(acc[r][c][1], sc[1], sh[1]));
         oq += opix;
       }
@@ -556,8 +556,9 @@ int depthwise_tma_geometry(bool f32, int n, int H, int W, int C, int stride, int
 }
 
 int depthwise_tma_init() {
-  static bool done = false;
-  if (done) return LWP_OK;
+  static DeviceOnce once;
+  int slot;
+  if (!once.pending(&slot)) return LWP_OK;
 #define LWP_DW_ATTR1(T, S, D, A) \
   LWP_CUDA_CHECK(cudaFuncSetAttribute(depthwise3x3_tma_kernel<T, S, D, A, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024)); \
   LWP_CUDA_CHECK(cudaFuncSetAttribute(depthwise3x3_tma_kernel<T, S, D, A, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024))
@@ -567,7 +568,7 @@ int depthwise_tma_init() {
   LWP_DW_ATTR(__nv_bfloat16, 1, 1); LWP_DW_ATTR(__nv_bfloat16, 2, 1); LWP_DW_ATTR(__nv_bfloat16, 1, 2);
 #undef LWP_DW_ATTR
 #undef LWP_DW_ATTR1
-  done = true;
+  once.done[slot] = true;
   return LWP_OK;
 }
 
@@ -619,7 +620,7 @@ int depthwise_tma_launch(bool f32, const CUtensorMap &tm, const CUtensorMap *tm_
   p.n = n; p.H = H; p.W = W; p.C = C; p.Ho = g.Ho; p.Wo = g.Wo; p.tw = g.tw; p.th = g.th; p.iw = g.iw; p.ih = g.ih;
   p.cb = g.cb; p.cq = g.cv; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y; p.cblocks = g.cblocks;
   p.sp_tiles = g.num_tiles; p.act = act; p.stage_bytes = g.stage_bytes; p.stages = 2;
-  p.debug = getenv("LWP_DEBUG_DW") ? atoi(getenv("LWP_DEBUG_DW")) : 0;
+  p.debug = debug_env("LWP_DEBUG_DW");
   p.tma_out = tm_out != nullptr ? 1 : 0;
   const CUtensorMap &tmo = tm_out != nullptr ? *tm_out : tm;
   if (f32) return depthwise_tma_launch_t<float>(tm, tmo, (float *)out, w9c, scale, shift, p, stride, dil, st);

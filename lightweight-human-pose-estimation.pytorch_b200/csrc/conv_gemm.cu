@@ -154,7 +154,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
   if (warp == kWarpA) {
     // ===================== TMA producer: activation tiles =====================
-    const bool skip = (p.debug & 1) != 0;
+    const bool skip = (LWP_DBG(p.debug) & 1) != 0;
     const int taps_y = p.taps == 1 ? 1 : 3;
     int stage = 0;
     uint32_t phase = 0, dst = smem_base;
@@ -186,7 +186,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == kWarpB) {
     // ===================== TMA producer: weight tiles =====================
-    const bool skip = (p.debug & 2) != 0;
+    const bool skip = (LWP_DBG(p.debug) & 2) != 0;
     int stage = 0;
     uint32_t phase = 0, dst = smem_base + a_bytes;
     bool ok = true;
@@ -218,7 +218,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
-    const bool do_mma = (p.debug & 4) == 0;
+    const bool do_mma = (LWP_DBG(p.debug) & 4) == 0;
     const bool thin = p.kb_bytes != kKBlockBytes;
     // descriptor without the start address; the address field is added per stage / per 32-byte K step (+2)
     const uint64_t desc_hi = thin ? ptx::umma_desc_k_sw64(0) : ptx::umma_desc_k_sw128(0);
@@ -290,12 +290,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mine = (tile_it % nparts) == part;
           part = 0; nparts = 1;
         }
-        if (mine && !(p.debug & 8))
+        if (mine && !(LWP_DBG(p.debug) & 8))
           staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)warp * p.staging_bufs * kStageOutBytes,
                                       p.staging_bufs, sbuf_idx, t_row,
                                       tc.n0, p.block_n, p.n_store, s_scale, s_shift, p.act, p.residual, p.res_ld, valid, pix,
                                       lane, tc.x0 + (q * 32) % p.tile_w, tc.y0 + (q * 32) / p.tile_w, tc.img, part, nparts,
-                                      p.debug >> 4);
+                                      LWP_DBG(p.debug) >> 4);
       } else {
         for (int c = (warp >> 2) * 32; c < p.block_n; c += 32 * (kEpiWarps / 4)) {  // the quarter's two warps alternate
           uint32_t r[32];
@@ -364,11 +364,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 int conv_gemm_init() {
-  static bool done = false;
-  if (done) return LWP_OK;
+  static DeviceOnce once;
+  int slot;
+  if (!once.pending(&slot)) return LWP_OK;
   LWP_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   LWP_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  done = true;
+  once.done[slot] = true;
   return LWP_OK;
 }
 

@@ -202,11 +202,12 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 int conv_gemm2_init() {
-  static bool done = false;
-  if (done) return LWP_OK;
+  static DeviceOnce once;
+  int slot;
+  if (!once.pending(&slot)) return LWP_OK;
   LWP_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   LWP_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  done = true;
+  once.done[slot] = true;
   return LWP_OK;
 }
 

@@ -239,11 +239,12 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 int conv_gemm3_init() {
-  static bool done = false;
-  if (done) return LWP_OK;
+  static DeviceOnce once;
+  int slot;
+  if (!once.pending(&slot)) return LWP_OK;
   LWP_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   LWP_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  done = true;
+  once.done[slot] = true;
   return LWP_OK;
 }
 

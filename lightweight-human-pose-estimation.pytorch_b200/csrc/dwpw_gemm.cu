@@ -244,7 +244,7 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
           for (int h = 0; h < p.n_mma; ++h) {
             if (!ptx::mbar_wait(&b_full[bs], bph)) { ok = false; atomicExch(p.err_flag, 14); break; }
             ptx::tc_fence_after();
-            if (!(p.debug & 4)) {
+            if (!(LWP_DBG(p.debug) & 4)) {
               const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem + L.b_off + (size_t)bs * p.b_stage_bytes));
 #pragma unroll
               for (int k = 0; k < kKBlockBytes / 32; ++k)
@@ -280,11 +280,11 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
       const bool valid = y < p.H && x < p.W;
       const size_t pix = ((size_t)img * p.H + y) * (size_t)p.W + x;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.cout_pad);
-      if (!(p.debug & 2))
+      if (!(LWP_DBG(p.debug) & 2))
         staged_epilogue_tile<kTf32>(&tmC, smem + L.staging_off + (size_t)(warp - 2) * p.staging_bufs * kStageOutBytes,
                                     p.staging_bufs, sbuf_idx, t_row, 0, p.cout_pad, p.n_store, s_scale, s_shift, p.act,
                                     p.residual, p.res_ld, valid, pix, lane, x0 + (q * 32) % p.tile_w,
-                                    y0 + (q * 32) / p.tile_w, img, (warp - 2) >> 2, kDwpwEpiWarps / 4, p.debug >> 3);
+                                    y0 + (q * 32) / p.tile_w, img, (warp - 2) >> 2, kDwpwEpiWarps / 4, LWP_DBG(p.debug) >> 3);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
@@ -313,7 +313,7 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         if (!ptx::mbar_wait(&in_full[is], iph) || !ptx::mbar_wait(&a_empty[as], aph ^ 1u)) {
           ok = false; atomicExch(p.err_flag, 16); break;
         }
-        if (active && !(p.debug & 1)) {
+        if (active && !(LWP_DBG(p.debug) & 1)) {
           const uint8_t *sbuf = smem + L.in_off + is * (int)p.in_stage_bytes;
           uint8_t *abuf = smem + L.a_off + as * kATileBytes;
           const int c0 = kb * p.kb_ch + cv * 8;
@@ -359,13 +359,14 @@ dwpw_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
 }
 
 int dwpw_init() {
-  static bool done = false;
-  if (done) return LWP_OK;
+  static DeviceOnce once;
+  int slot;
+  if (!once.pending(&slot)) return LWP_OK;
 #define LWP_DWPW_ATTR(TF, D) \
   LWP_CUDA_CHECK(cudaFuncSetAttribute(dwpw_gemm_kernel<TF, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))
   LWP_DWPW_ATTR(false, 1); LWP_DWPW_ATTR(false, 2); LWP_DWPW_ATTR(true, 1); LWP_DWPW_ATTR(true, 2);
 #undef LWP_DWPW_ATTR
-  done = true;
+  once.done[slot] = true;
   return LWP_OK;
 }
 

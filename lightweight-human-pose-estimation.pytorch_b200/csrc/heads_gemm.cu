@@ -131,7 +131,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int c = 0; c < p.chunks; ++c) {
         if (!ptx::mbar_wait_u32(wempty0 + 8u * stage, phase ^ 1u)) { ok = false; if (lane == 0) atomicExch(p.err_flag, 42); break; }
         if (ptx::elect_one()) {
-          if (p.debug & 8) { ptx::mbar_arrive_u32(wfull0 + 8u * stage); } else {
+          if (LWP_DBG(p.debug) & 8) { ptx::mbar_arrive_u32(wfull0 + 8u * stage); } else {
           ptx::mbar_arrive_expect_tx_u32(wfull0 + 8u * stage, L.w_stage_bytes);
           for (int kb = 0; kb < p.k1_blocks; ++kb)
             ptx::tma_load_2d_u32(dst + (uint32_t)kb * kHdW1Bytes, &tmW1, wfull0 + 8u * stage, kb * 64, c * kHdChunk);
@@ -163,7 +163,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (ptx::elect_one()) {
           const uint32_t d1 = tmem_base + b * 64u;
           const uint32_t wb16 = w16 + (uint32_t)ws * wst16;
-          for (int kb = 0; kb < p.k1_blocks && !(p.debug & 1); ++kb) {
+          for (int kb = 0; kb < p.k1_blocks && !(LWP_DBG(p.debug) & 1); ++kb) {
             const uint64_t da = desc_hi | (uint64_t)(xa16 + (uint32_t)kb * (kATileBytes >> 4));
             const uint64_t db = desc_hi | (uint64_t)(wb16 + (uint32_t)kb * (kHdW1Bytes >> 4));
             ptx::umma<false>(d1, da, db, idesc, kb == 0 ? 0u : 1u);
@@ -200,7 +200,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (ptx::elect_one()) {
           const uint64_t da = desc_hi | (uint64_t)(a216 + b * (kATileBytes >> 4));
           const uint64_t db = desc_hi | (uint64_t)(w216 + (uint32_t)ws * wst16);
-          if (!(p.debug & 2)) {
+          if (!(LWP_DBG(p.debug) & 2)) {
           ptx::umma<false>(d2, da, db, idesc, c == 0 ? 0u : 1u);
           ptx::umma<false>(d2, da + 2u, db + 2u, idesc, 1u);
           ptx::umma<false>(d2, da + 4u, db + 4u, idesc, 1u);
@@ -236,7 +236,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (lane == 0) ptx::mbar_arrive(&acc1_empty[b]);   // the accumulator is in registers: GEMM1 may reuse it
         const int cg0 = c * kHdChunk + half * 32;
         uint8_t *arow = a2_row + b * kATileBytes;
-        if (!(p.debug & 4))
+        if (!(LWP_DBG(p.debug) & 4))
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           const int cg = cg0 + g8 * 8;
@@ -301,10 +301,11 @@ size_t heads_fused_smem_bytes(int k1_blocks, int chunks) { return (size_t)heads_
 int heads_fused_launch(const CUtensorMap &tmX, const CUtensorMap &tmW1, const CUtensorMap &tmW2, int n_px, int c_in,
                        int c_mid, const float *scale1, const float *shift1, const float *scale2, const float *shift2,
                        float *out_f32, int out_f32_ld, void *out_bf16, int out_ld, int *err_flag, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  int attr_slot;
+  if (attr.pending(&attr_slot)) {
     LWP_CUDA_CHECK(cudaFuncSetAttribute(heads_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr = true;
+    attr.done[attr_slot] = true;
   }
   HeadsParams p;
   p.n_px = n_px; p.m_tiles = ceil_div(n_px, kBlockM);
@@ -313,7 +314,7 @@ int heads_fused_launch(const CUtensorMap &tmX, const CUtensorMap &tmW1, const CU
   p.scale1 = scale1; p.shift1 = shift1; p.scale2 = scale2; p.shift2 = shift2;
   p.out_f32 = out_f32; p.out_f32_ld = out_f32_ld; p.out_bf16 = out_bf16; p.out_ld = out_ld;
   p.err_flag = err_flag;
-  p.debug = getenv("LWP_DEBUG_HEADS") ? atoi(getenv("LWP_DEBUG_HEADS")) : 0;
+  p.debug = debug_env("LWP_DEBUG_HEADS");
   const size_t smem = heads_fused_smem_bytes(p.k1_blocks, p.chunks);
   if (smem > 232448) { set_error("heads_fused: %zu bytes of shared memory", smem); return LWP_ECAP; }
   const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();

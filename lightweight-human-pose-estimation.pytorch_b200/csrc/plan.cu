@@ -245,7 +245,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   g.residual = residual; g.res_ld = res_ld;
   g.out = out; g.out_ld = out_ld; g.out_f32 = out_f32; g.out_f32_ld = out_f32_ld;
   g.err_flag = p->err_flag;
-  g.debug = getenv("LWP_DEBUG_GEMM") ? atoi(getenv("LWP_DEBUG_GEMM")) : 0;
+  g.debug = debug_env("LWP_DEBUG_GEMM");
   const int smem_budget = gemm_smem_cap() - 1024 - kStagingBytes - 2 * cout_pad * 4 - 512;
   const int stage_bytes = (kBlockM + g.block_n) * kb_bytes;
   int stages = smem_budget / stage_bytes;
@@ -443,7 +443,7 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
     f.dw_consts = d;
   }
   f.residual = residual; f.res_ld = res_ld; f.err_flag = p->err_flag;
-  f.debug = getenv("LWP_DEBUG_DWPW") ? atoi(getenv("LWP_DEBUG_DWPW")) : 0;
+  f.debug = debug_env("LWP_DEBUG_DWPW");
   // tile: rectangle of 128 pixels, width a multiple of 4 (a depthwise thread owns 4 consecutive columns)
   long long best = -1;
   for (int th = 1; th <= 32; th <<= 1) {

@@ -870,12 +870,13 @@ static int extract_common(bool fused, const float *hm, const UpSrc *up, int n, i
   unsigned long long *cand = (unsigned long long *)((char *)workspace + align_up(slots * sizeof(int), 256));
   LWP_CUDA_CHECK(cudaMemsetAsync(cand_count, 0, slots * sizeof(int), st));
   LWP_CUDA_CHECK(cudaMemsetAsync(overflow, 0, (size_t)n * sizeof(int), st));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_slot;
+  if (attr_set.pending(&attr_set_slot)) {
     LWP_CUDA_CHECK(cudaFuncSetAttribute(peak_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     LWP_CUDA_CHECK(cudaFuncSetAttribute(peak_candidates_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         100 * 1024));
-    attr_set = true;
+    attr_set.done[attr_set_slot] = true;
   }
   if (fused) {
     LWP_REQUIRE(n_ch <= kPkMaxCh, "lwp_extract_keypoints_fused: at most %d channels", kPkMaxCh);
@@ -976,10 +977,11 @@ static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *cou
   memset(&u0, 0, sizeof(u0));
   if (fused) {
     const size_t src_bytes = (size_t)up->h * up->w * sizeof(float2);   // the limb's two PAF channels of one image
-    static bool ps_attr = false;
-    if (!ps_attr) {
+    static DeviceOnce ps_attr;
+    int ps_attr_slot;
+    if (ps_attr.pending(&ps_attr_slot)) {
       LWP_CUDA_CHECK(cudaFuncSetAttribute(paf_score_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      ps_attr = true;
+      ps_attr.done[ps_attr_slot] = true;
     }
     // staged variant: every block copies the limb's two channels first, so use as few blocks per (limb, image) as still
     // fill the GPU (batches: one block of 8 warps walks all pairs; a single image: up to 8 blocks per limb)
@@ -997,21 +999,23 @@ static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *cou
                                                                                cap_connections);
   }
   LWP_LAUNCH_CHECK();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  int attr_set_slot;
+  if (attr_set.pending(&attr_set_slot)) {
     LWP_CUDA_CHECK(cudaFuncSetAttribute(limb_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_set.done[attr_set_slot] = true;
   }
   limb_match_kernel<<<dim3(LWP_NUM_LIMBS, n), 256, smem, st>>>(w.conn, w.conn_count, cap_connections, kpts, counts,
                                                               kpt_start, cap_kpts, w.match, w.match_count, overflow);
   LWP_LAUNCH_CHECK();
   const size_t pa_smem = (size_t)cap_poses * LWP_POSE_ENTRY * sizeof(double) + (size_t)cap_kpts * sizeof(Match);
   if (pa_smem <= 160 * 1024) {
-    static bool pa_attr = false;
-    if (!pa_attr) {
+    static DeviceOnce pa_attr;
+    int pa_attr_slot;
+    if (pa_attr.pending(&pa_attr_slot)) {
       LWP_CUDA_CHECK(cudaFuncSetAttribute(pose_assemble_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           160 * 1024));
-      pa_attr = true;
+      pa_attr.done[pa_attr_slot] = true;
     }
     pose_assemble_kernel<true><<<n, 32, pa_smem, st>>>(kpts, counts, kpt_start, cap_kpts, w.match, w.match_count,
                                                        w.poses, pose_entries, n_poses, cap_poses, overflow);

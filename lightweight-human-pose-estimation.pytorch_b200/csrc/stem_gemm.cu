@@ -246,13 +246,14 @@ int stem_gemm_launch(bool f32, const void *x, bool x_is_u8, const double *mean3,
   p.img_scale = img_scale;
   p.err_flag = err_flag;
   const size_t smem = 1024 + kStemStages * kATileBytes + kStemN * kKBlockBytes + 2 * kStemN * sizeof(float) + 64;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  int attr_slot;
+  if (attr.pending(&attr_slot)) {
     LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    attr.done[attr_slot] = true;
   }
   int per_sm = 5;   // 5 x (38 KB smem, 64 TMEM columns, 128 threads) per SM
   if (const char *e = getenv("LWP_STEM_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }

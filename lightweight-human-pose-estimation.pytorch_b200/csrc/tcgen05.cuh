@@ -43,12 +43,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a mis-programmed pipeline must never hang the GPU.  Returns false after ~2 s.
+// Bounded wait: a mis-programmed pipeline must never hang the GPU -- and must never return wrong results silently
+// either: after ~10 s of spinning (20e9 clocks; a healthy wait is microseconds, even under ncu replay or
+// compute-sanitizer) the kernel TRAPS, so the next CUDA call of the host fails ("unspecified launch failure")
+// instead of the pipeline carrying on with incomplete tiles.  The bool result is kept for the callers' control flow.
+constexpr long long kMbarTimeoutClocks = 20000000000ll;
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return true;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) return false;
+    if (clock64() - t0 > kMbarTimeoutClocks) { __trap(); return false; }
   }
   return true;
 }
@@ -76,7 +80,7 @@ __device__ __forceinline__ bool mbar_wait_u32(uint32_t bar, uint32_t parity) {  
   if (mbar_try_wait_u32(bar, parity)) return true;
   long long t0 = clock64();
   while (!mbar_try_wait_u32(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) return false;
+    if (clock64() - t0 > kMbarTimeoutClocks) { __trap(); return false; }
   }
   return true;
 }

@@ -13,6 +13,7 @@ its forward (:114-123):
                                                    producers write straight into a 192-wide buffer
 PyTorch is used for device memory and one-off weight re-layout only.
 """
+import collections
 import os
 
 import torch
@@ -408,15 +409,31 @@ class Plan:
 
 
 class NetEngine:
+    MAX_CACHED_PLANS = 12   # LRU bound: val.infer over variable-width images creates one plan per (scale, shape)
+
     def __init__(self, net):
         _lib.require_cuda()
         self.net = net
         p = next(net.parameters())
         if not p.is_cuda:
             raise _lib.LwpError("module parameters are on the CPU; call net.cuda() (there is no CPU path)")
+        # the buffer plan hard-codes the reference's default widths (CONCAT_LD = 128 + 64, HEAD_LD = 64): refuse
+        # anything else loudly instead of writing heads into a neighbouring pixel's row
+        if net.num_channels != 128 or net.num_heatmaps + net.num_pafs > HEAD_LD:
+            raise ValueError("the sm_100a engine supports num_channels=128 and num_heatmaps+num_pafs<=%d "
+                             "(got num_channels=%d, %d+%d)" % (HEAD_LD, net.num_channels, net.num_heatmaps, net.num_pafs))
         self.device = p.device
         self._packed = {}
-        self._plans = {}
+        self._plans = collections.OrderedDict()
+
+    def new_plan(self, precision, n, H, W, input_u8=None):
+        """A private, uncached plan (own activation buffers): every PosePipeline chunk takes one, so two pipelines
+        (or a pipeline and net.forward) of the same shape never share buffers across streams; it lives as long as
+        its owner."""
+        net = self.net
+        with torch.cuda.device(self.device):
+            return Plan(self.packed(precision), precision, n, H, W, 1 + len(net.refinement_stages),
+                        net.num_heatmaps, net.num_pafs, self.device, input_u8=input_u8)
 
     def packed(self, precision):
         if precision not in _PREC:
@@ -427,16 +444,23 @@ class NetEngine:
         return self._packed[precision]
 
     def plan(self, precision, n, H, W, slot=0, input_u8=None):
-        """Launch plan (with its own activation buffers) for one shape; `slot` distinguishes independent
-        instances of the same shape that run concurrently on different streams; input_u8 = (mean3, scale) makes
-        the stem take raw uint8 [n,H,W,3] frames."""
+        """Cached launch plan (with its own activation buffers) for one shape, shared by net.forward / infer_fast /
+        val.infer (synchronous, one stream); input_u8 = (mean3, scale) makes the stem take raw uint8 [n,H,W,3]
+        frames.  At most MAX_CACHED_PLANS shapes stay alive (least recently used goes first)."""
         key = (precision, n, H, W, slot, None if input_u8 is None else (tuple(input_u8[0]), float(input_u8[1])))
-        if key not in self._plans:
-            net = self.net
-            with torch.cuda.device(self.device):
-                self._plans[key] = Plan(self.packed(precision), precision, n, H, W, 1 + len(net.refinement_stages),
-                                        net.num_heatmaps, net.num_pafs, self.device, input_u8=input_u8)
-        return self._plans[key]
+        if key in self._plans:
+            self._plans.move_to_end(key)
+            return self._plans[key]
+        net = self.net
+        with torch.cuda.device(self.device):
+            while len(self._plans) >= self.MAX_CACHED_PLANS:
+                # least recently used plan: its kernels may still be in flight, so drain the device before its
+                # buffers and tensor maps go away (a pipeline that still holds the plan keeps it alive regardless)
+                torch.cuda.synchronize(self.device)
+                self._plans.popitem(last=False)
+        plan = self.new_plan(precision, n, H, W, input_u8=input_u8)
+        self._plans[key] = plan
+        return plan
 
     def forward(self, x, precision="tf32"):
         if x.dim() != 4 or x.shape[1] != 3:

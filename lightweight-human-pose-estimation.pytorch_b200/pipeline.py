@@ -50,7 +50,7 @@ class _Chunk:
         self.pipe, self.lo, self.n = pipe, lo, n
         dev = pipe.device
         eng = pipe.net.engine()
-        self.plan = eng.plan(pipe.precision, n, pipe.H, pipe.W, slot=slot, input_u8=pipe.input_u8)
+        self.plan = eng.new_plan(pipe.precision, n, pipe.H, pipe.W, input_u8=pipe.input_u8)   # private buffers
         ck, cc, cp, cn = pipe.caps
         L = pipe.L
         if not pipe.fused:
@@ -80,6 +80,9 @@ class _Chunk:
         heads = self.heads
         if pipe.heads_hook is not None:
             pipe.heads_hook(heads, self.lo)
+        if pipe.graph:   # one stream, no events: the whole pass is (or is being captured into) one CUDA graph
+            self.enqueue_postproc(heads)
+            return
         if not pipe.overlap_postproc:
             self.enqueue_postproc(heads)
             self.pp_done.record(cur)
@@ -154,7 +157,7 @@ class PosePipeline:
     def __init__(self, net, batch, height, width, precision="bf16", upsample_ratio=4, demo=True,
                  min_paf_score=0.05, cap_kpts=128, cap_candidates=2048, cap_poses=256, cap_connections=2048,
                  heads_hook=None, fused=True, chunk=None, depth=2, overlap_postproc=True, input_format="f32_nchw",
-                 img_mean=(128, 128, 128), img_scale=1 / 256):
+                 img_mean=(128, 128, 128), img_scale=1 / 256, graph=False):
         _lib.require_cuda()
         self.net, self.precision = net, precision
         self.n, self.H, self.W = batch, height, width
@@ -167,12 +170,20 @@ class PosePipeline:
         self.fused = bool(fused) and upsample_ratio >= 3
         # post-processing of batch i on a second stream, overlapping the network of batch i+1
         self.overlap_postproc = bool(overlap_postproc)
+        # graph=True: the ~60 launches of one pass (network, post-processing, result read-back) are captured once per
+        # input buffer into a CUDA graph and replayed -- for small batches (the reference's batch-1 demo loop) the
+        # launches, not the kernels, are the cost.  Everything then runs on one stream.
+        self.graph = bool(graph)
+        if self.graph:
+            self.overlap_postproc = False
+        self._graphs = {}
         # "f32_nchw": normalised float32 [n,3,H,W] like the reference's tensor_img; "u8_nhwc": raw BGR frames uint8
         # [n,H,W,3] already at the network size -- (img - mean) * scale (val.normalize) is fused into the stem kernel
         if input_format not in ("f32_nchw", "u8_nhwc"):
             raise ValueError("input_format must be 'f32_nchw' or 'u8_nhwc'")
         self.input_u8 = (tuple(img_mean), float(img_scale)) if input_format == "u8_nhwc" else None
-        self.device = net.engine().device
+        self._engine = net.engine()      # the packed weights this pipeline's plans were recorded with
+        self.device = self._engine.device
         self.h, self.w = height // 8, width // 8
         self.Hu, self.Wu = self.h * upsample_ratio, self.w * upsample_ratio
         self.L = _lib.load()
@@ -201,8 +212,26 @@ class PosePipeline:
         """Make the current stream wait for every enqueued post-processing (call before timing / reading results
         produced by run_device)."""
         cur = torch.cuda.current_stream()
+        if self.graph:
+            cur.wait_stream(self.stream)
+            return
         for c in self.chunks:
             cur.wait_event(c.pp_done)
+
+    def _graphed(self, key, fn):
+        """Run fn() on self.stream (the current stream): eagerly the first time (one-time kernel attribute set-up
+        must not happen under capture), captured into a CUDA graph the second time, replayed from then on."""
+        state = self._graphs.get(key)
+        if state is None:
+            fn()
+            self._graphs[key] = False
+            return
+        if state is False:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
+                fn()
+            self._graphs[key] = state = g
+        state.replay()
 
     @property
     def n_poses(self):
@@ -217,16 +246,32 @@ class PosePipeline:
     def launches_per_step(self):
         return sum(c.plan.num_compute_ops + (0 if self.fused else 2) + 3 + 3 for c in self.chunks)
 
+    def _check_engine(self):
+        """net.cuda() / load_state_dict() / refresh() drop the engine whose packed weights this pipeline's plans hold:
+        running on would silently use the old weights."""
+        if self.net._engine is not self._engine:
+            raise RuntimeError("the network's parameters changed after this PosePipeline was built (load_state / .cuda() / "
+                               "refresh()): build a new PosePipeline")
+
     def run_device(self, x_dev):
         """Hot path on a device-resident batch (no host traffic): network on the current stream, post-processing
         on the post-processing stream (successive calls overlap); results stay on the device
         (self.pose_entries / self.n_poses / chunk.kb).  Call join() (or synchronise the device) before reading."""
+        self._check_engine()
         with torch.cuda.device(self.device):
+            if self.graph:
+                cur = torch.cuda.current_stream()
+                self.stream.wait_stream(cur)
+                with torch.cuda.stream(self.stream):
+                    self._graphed(("dev", x_dev.data_ptr()),
+                                  lambda: [c.enqueue(x_dev[c.lo:c.lo + c.n]) for c in self.chunks])
+                return
             for c in self.chunks:
                 c.enqueue(x_dev[c.lo:c.lo + c.n])
 
     def submit(self, frames):
         """Enqueue one batch: frames float32 [n,3,H,W], pinned host memory (asynchronous copy) or device."""
+        self._check_engine()
         if len(self._pending) == len(self.slots):
             raise RuntimeError("pipeline full: collect() a result first (depth=%d)" % len(self.slots))
         slot = self.slots[self._next]
@@ -241,6 +286,30 @@ class PosePipeline:
                     slot.x_dev.copy_(frames, non_blocking=True)
                     slot.copied.record(self.copy_stream)
                 x = slot.x_dev
+            def read_back(stream_waits):
+                for c in self.chunks:
+                    sl = slice(c.lo, c.lo + c.n)
+                    if stream_waits is not None:
+                        stream_waits.wait_event(c.pp_done)
+                    slot.h_pose_entries[sl].copy_(c.pose_entries, non_blocking=True)
+                    slot.h_n_poses[sl].copy_(c.n_poses, non_blocking=True)
+                    slot.h_kpts[sl].copy_(c.kb.kpts, non_blocking=True)
+                    slot.h_counts[sl].copy_(c.kb.counts, non_blocking=True)
+                    slot.h_kpt_start[sl].copy_(c.kb.kpt_start, non_blocking=True)
+                    slot.h_overflow[sl].copy_(c.kb.overflow, non_blocking=True)
+
+            if self.graph:
+                def whole_pass():
+                    for c in self.chunks:
+                        c.enqueue(x[c.lo:c.lo + c.n])
+                    read_back(None)
+                with torch.cuda.stream(self.stream):
+                    self.stream.wait_event(slot.copied)
+                    self._graphed(("slot", self.slots.index(slot), x.data_ptr()), whole_pass)
+                    slot.consumed.record(self.stream)
+                    slot.done.record(self.stream)
+                self._pending.append(slot)
+                return
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(slot.copied)
                 for c in self.chunks:
@@ -248,15 +317,7 @@ class PosePipeline:
                 slot.consumed.record(self.stream)       # the network has read this slot's input buffer
             tail = self.pp_stream if self.overlap_postproc else self.stream
             with torch.cuda.stream(tail):
-                for c in self.chunks:
-                    sl = slice(c.lo, c.lo + c.n)
-                    tail.wait_event(c.pp_done)
-                    slot.h_pose_entries[sl].copy_(c.pose_entries, non_blocking=True)
-                    slot.h_n_poses[sl].copy_(c.n_poses, non_blocking=True)
-                    slot.h_kpts[sl].copy_(c.kb.kpts, non_blocking=True)
-                    slot.h_counts[sl].copy_(c.kb.counts, non_blocking=True)
-                    slot.h_kpt_start[sl].copy_(c.kb.kpt_start, non_blocking=True)
-                    slot.h_overflow[sl].copy_(c.kb.overflow, non_blocking=True)
+                read_back(tail)
                 slot.done.record(tail)
         self._pending.append(slot)
 

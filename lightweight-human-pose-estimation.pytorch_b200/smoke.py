@@ -19,7 +19,7 @@ def run(verbose=True):
     x = synth.synthetic_net_input(2, 64, 96, seed=3)
     ref = onet.forward(net.state_dict(), x)
     net = net.cuda()
-    for precision, tol in (("tf32", 3e-3), ("bf16", 3e-2)):
+    for precision, tol in (("tf32", 1e-3), ("bf16", 3e-3)):
         net.precision = precision
         outs = net(x.cuda())
         torch.cuda.synchronize()
@@ -28,6 +28,22 @@ def run(verbose=True):
         assert err < tol, "network %s max abs err %g >= %g" % (precision, err, tol)
         if verbose:
             print("smoke: network %s max abs err vs oracle %.3g (tol %g)" % (precision, err, tol))
+
+    # one batch on the benchmark's 46x82 grid (12 frames x 368x656, bf16): large enough for the plan to pick the
+    # production kernels -- CTA-pair 1x1 GEMMs (conv_gemm2_kernel), the 3x3 strip kernel (conv3x3_pair_kernel), fused
+    # heads, TMA depthwise -- so that they appear in the driver's launch list; two frames checked against the oracle
+    xb = synth.synthetic_net_input(12, 368, 656, seed=4)
+    net.precision = "bf16"
+    outs = net(xb.cuda())
+    torch.cuda.synchronize()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    err = 0.0
+    for b in (0, 11):
+        refb = onet.forward(sd, xb[b:b + 1])
+        err = max(err, max(float((o[b:b + 1].cpu() - r).abs().max()) for o, r in zip(outs, refb)))
+    assert err < 3e-3, "network bf16 @12x368x656 max abs err %g >= 3e-3" % err
+    if verbose:
+        print("smoke: network bf16 12x3x368x656 max abs err vs oracle %.3g (tol 3e-3)" % err)
 
     # post-processing: synthetic 2- and 3-person maps through the fused pipeline stages, bit-exact vs oracle
     hm, paf, _ = synth.synthetic_pose_maps(2, 32, 57, seed=5, noise=0.02, persons=None, max_persons=3)

@@ -140,7 +140,11 @@ def _gloo_worker(rank, world, port, q):
     poses = torch.full((hi - lo, 4, 20), float(rank), dtype=torch.float64)
     gn, gp = parallel.gather_pose_tables(n_poses, poses)
     slow = parallel.max_over_ranks(1.0 + rank)
-    q.put((rank, gn.tolist(), gp[:, 0, 0].tolist(), slow))
+    # unequal shards (7 frames over 2 ranks: 4 + 3): padded for the collective, trimmed afterwards
+    lo, hi = parallel.shard_range(7, rank, world)
+    un, up = parallel.gather_pose_tables(torch.arange(lo, hi, dtype=torch.int32),
+                                         torch.full((hi - lo, 4, 20), float(rank), dtype=torch.float64), total=7)
+    q.put((rank, gn.tolist(), gp[:, 0, 0].tolist(), slow, un.tolist(), up[:, 0, 0].tolist()))
     dist.destroy_process_group()
 
 
@@ -156,7 +160,23 @@ def test_gather_and_timing_over_gloo_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, gn, gp, slow in outs:
+    for rank, gn, gp, slow, un, up in outs:
         assert gn == [0, 1, 2, 3, 4, 5]
         assert gp == [0.0, 0.0, 0.0, 1.0, 1.0, 1.0]
         assert slow == 2.0
+        assert un == [0, 1, 2, 3, 4, 5, 6] and up == [0.0] * 4 + [1.0] * 3
+
+
+def test_debug_switches_are_refused(monkeypatch):
+    """A run with a work-skipping LWP_DEBUG_* switch in the environment is refused (release builds do not even
+    contain those code paths: lwp_timing_experiments() == 0)."""
+    import lwpose_b200  # noqa: F401
+    from lwpose_b200 import _lib
+    L = _lib.load()
+    assert L.lwp_timing_experiments() == 0
+    _lib.refuse_debug_env()
+    monkeypatch.setenv("LWP_DEBUG_GEMM", "4")
+    with pytest.raises(_lib.LwpError):
+        _lib.refuse_debug_env()
+    monkeypatch.setenv("LWP_DEBUG_GEMM", "0")
+    _lib.refuse_debug_env()

@@ -4,7 +4,8 @@ reference of the same op, then the whole network against the golden outputs of t
 Stated tolerances (max abs error, outputs are O(0.1..1)):
   tf32 plans ("fp32 mode": fp32 storage, TF32 tensor-core products, fp32 accumulate)  2e-3 per layer test
   bf16 plans (bf16 storage + products, fp32 accumulate)                              3e-2 per layer test
-  whole network vs reference CPU fp32 golden: tf32 3e-3, bf16 3e-2 (numerics)
+  whole network vs reference CPU fp32 golden: tf32 1e-3, bf16 3e-3 on outputs of magnitude 0.05-0.2 (measured:
+  2.5e-4 / 5.7e-4; SURVEY.md section 7 derives 3e-4 / 3e-3 from the operand rounding), scaled by the head gain
 """
 import numpy as np
 import pytest
@@ -14,6 +15,7 @@ import golden_cases as gc
 pytestmark = pytest.mark.gpu
 
 TOL = {"tf32": 2e-3, "bf16": 3e-2}
+NET_TOL = {"tf32": 1e-3, "bf16": 3e-3}   # whole network, max abs error of the NCHW float32 outputs
 
 
 @pytest.fixture(scope="module")
@@ -287,7 +289,7 @@ def test_network_vs_reference_golden(env, case, precision):
     torch.cuda.synchronize()
     assert net.engine().plan(precision, B, H, W).error_flag() == 0
     assert len(outs) == 2 * (1 + R)
-    tol = (3e-3 if precision == "tf32" else 3e-2) * gain
+    tol = NET_TOL[precision] * gain
     for i, y in enumerate(outs):
         ref = torch.from_numpy(g["net_%s_out%d" % (name, i)])
         assert tuple(y.shape) == tuple(ref.shape) and y.dtype == torch.float32
@@ -329,7 +331,7 @@ def test_fused_dwpw_network(env, precision, monkeypatch):
     plan = net.engine().plan(precision, B, H, W)
     assert plan.error_flag() == 0
     assert any(nm.endswith(".dwpw") for nm in plan.op_names)
-    tol = 3e-3 if precision == "tf32" else 3e-2
+    tol = NET_TOL[precision] * gain
     for i, y in enumerate(outs):
         ref = torch.from_numpy(g["net_%s_out%d" % (name, i)])
         assert _rel(y.cpu(), ref) < tol, i
@@ -350,7 +352,38 @@ def test_cta_pair_gemm_network(env, precision, monkeypatch):
     outs = net(x)
     torch.cuda.synchronize()
     assert net.engine().plan(precision, B, H, W).error_flag() == 0
-    tol = 3e-3 if precision == "tf32" else 3e-2
+    tol = NET_TOL[precision] * gain
     for i, y in enumerate(outs):
         ref = torch.from_numpy(g["net_%s_out%d" % (name, i)])
         assert _rel(y.cpu(), ref) < tol, i
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_network_full_config1_vs_oracle(env, precision):
+    """BASELINE.json configs[1] at FULL size -- the benchmarked shape: 64 x 3 x 368 x 656 through every production
+    kernel (CTA-pair 1x1 GEMMs, 3x3 strip kernel, fused heads, TMA depthwise), all stage outputs of 4 sampled frames
+    against the torch CPU fp32 oracle forward of those frames."""
+    torch, _lib, engine = env
+    from lwpose_b200 import synth
+    from oracle import net as onet
+    B, H, W = 64, 368, 656
+    net = _build_net(torch, "cfg1", 1, 1.0)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    net.precision = precision
+    x = synth.synthetic_net_input(B, H, W, seed=1)
+    outs = [o.cpu() for o in net(x.cuda())]
+    torch.cuda.synchronize()
+    plan = net.engine().plan(precision, B, H, W)
+    assert plan.error_flag() == 0
+    names = set(plan.op_names)
+    assert "initial_stage.heads.fused" in names or precision == "tf32"
+    worst = 0.0
+    for b in (0, 21, 42, 63):
+        ref = onet.forward(sd, x[b:b + 1])
+        for o, r in zip(outs, ref):
+            assert tuple(o[b:b + 1].shape) == tuple(r.shape)
+            worst = max(worst, _rel(o[b:b + 1], r))
+    assert worst < NET_TOL[precision], worst
+    del net
+    torch.cuda.empty_cache()
