@@ -595,7 +595,8 @@ def roofline_pass(pipe, x_dev, args, precision=None, brief=False):
         a["ms"] += t
         for c in pipe.chunks:
             a["flops"] += c.plan.op_meta[i]["flops"]; a["bytes"] += c.plan.op_meta[i]["bytes"]; a["launches"] += 1
-    tc_kinds = [k for k in agg if k.startswith("gemm") or k == "dwpw"]   # the two tcgen05 kernels
+    tc_kinds = [k for k in agg if k.startswith("gemm") or k == "dwpw"]   # the tcgen05 implicit-GEMM kernels (the fused
+    # depthwise+1x1 blocks of the thin layers are HBM-bound: they get their own object below)
     gemm_ms = sum(agg[k]["ms"] for k in tc_kinds)
     gemm_flops = sum(agg[k]["flops"] for k in tc_kinds)
     gemm_launches = sum(agg[k]["launches"] for k in tc_kinds)
@@ -635,6 +636,13 @@ def roofline_pass(pipe, x_dev, args, precision=None, brief=False):
         res["roofline_dwpw_hbm"] = {"kernel": "dwpw_gemm_kernel as an HBM-bound fused block (%d launches)" % d["launches"],
                                     "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
                                     "frac": gbs / pk["hbm"], "ms_per_step": d["ms"]}
+    if "sepconv" in agg:
+        d = agg["sepconv"]
+        gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        res["roofline_sepconv"] = {"kernel": "sepconv_kernel: weight-resident fused depthwise 3x3 + 1x1 blocks of the thin layers (%d launches); "
+                                             "bytes = block input + block output (+ weights)" % d["launches"],
+                                   "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                                   "tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12, "ms_per_step": d["ms"]}
     if "depthwise" in agg:
         d = agg["depthwise"]
         gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9

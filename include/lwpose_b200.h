@@ -207,6 +207,19 @@ int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w, const floa
                       int dw_act, int dilation, const void *w, const float *scale, const float *shift, int act,
                       const void *residual, int res_ld, void *out, int out_ld, int n, int H, int W, int Cin, int Cout);
 
+/*
+ * Weight-resident fused depthwise-separable block for the THIN layers (modules/conv.py:13-32 conv_dw / conv_dw_no_bn as
+ * used by models/with_mobilenet.py:94-99 and :12-16): depthwise 3x3, pad 1, stride 1 or 2, + scale/shift + dw_act,
+ * written straight into the shared-memory A operand of the 1x1 convolution's tcgen05 GEMM (+ scale/shift + act
+ * (+ residual)); the whole 1x1 weight matrix stays in shared memory for the CTA's life.  Same argument meaning as
+ * lwp_plan_add_dwpw (stride instead of dilation); out is [n][(H-1)/stride+1][(W-1)/stride+1] pixels.
+ * Cin a multiple of the 128-byte K block, Cout <= 256.  Returns LWP_ECAP when the weights + rings do not fit in
+ * shared memory (the caller then records the two-kernel form).
+ */
+int lwp_plan_add_sepconv(lwp_plan *p, const void *in, const float *dw_w, const float *dw_scale, const float *dw_shift,
+                         int dw_act, int stride, const void *w, const float *scale, const float *shift, int act,
+                         const void *residual, int res_ld, void *out, int out_ld, int n, int H, int W, int Cin, int Cout);
+
 /* NHWC (plan dtype or float32) -> NCHW float32, for the tensors `forward` returns at the module boundary. */
 int lwp_plan_add_nhwc_to_nchw(lwp_plan *p, const void *in, int in_ld, int in_is_f32, int c0, int c, float *out, int n,
                               int H, int W);

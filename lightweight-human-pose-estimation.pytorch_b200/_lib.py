@@ -48,6 +48,9 @@ SIGNATURES = {
     "lwp_plan_add_dwpw": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
                                    _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int,
                                    _c_int, _c_int, _c_int]),
+    "lwp_plan_add_sepconv": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
+                                      _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int,
+                                      _c_int, _c_int, _c_int]),
     "lwp_plan_add_nhwc_to_nchw": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_int,
                                            _c_int, _c_int]),
     "lwp_plan_run": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),

@@ -6,6 +6,7 @@
 #include "conv_direct.cuh"
 #include "conv_gemm.cuh"
 #include "dwpw_gemm.cuh"
+#include "sepconv_gemm.cuh"
 #include "tcgen05.cuh"
 
 #include <cuda.h>
@@ -42,7 +43,7 @@ static int gemm_smem_cap() {
   return cap;
 }
 
-enum OpKind { OP_STEM, OP_DW, OP_GEMM, OP_NCHW, OP_DWPW, OP_HEADS };
+enum OpKind { OP_STEM, OP_DW, OP_GEMM, OP_NCHW, OP_DWPW, OP_HEADS, OP_SEP };
 
 struct Op {
   OpKind kind;
@@ -62,6 +63,7 @@ struct Op {
   bool two_cta = false;   // conv_gemm2_kernel: CTA pairs, tcgen05.mma.cta_group::2
   bool strips = false;    // conv3x3_pair_kernel: CTA pairs + column-strip reuse of the activations (3x3, Cout 128)
   DwpwParams fp;
+  SepParams sp;
   int grid = 0;
   // fused heads (tmA = X, tmB = W1, tmC = W2)
   int hd_px = 0, hd_cin = 0, hd_cmid = 0, hd_out_ld = 0, hd_f32_ld = 0;
@@ -510,6 +512,128 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
   return LWP_OK;
 }
 
+// dw constants re-laid-out per K block: [kblocks][9 taps | scale | shift][kb_ch] fp32, zero beyond Cin
+static int build_dw_consts(lwp_plan *p, const float *dw_w, const float *dw_scale, const float *dw_shift, int Cin, int kb_ch,
+                           int kblocks, const float **out) {
+  const size_t blob = (size_t)kblocks * 11 * kb_ch * sizeof(float);
+  float *d = nullptr;
+  LWP_CUDA_CHECK(cudaMalloc(&d, blob));
+  p->owned.push_back(d);
+  LWP_CUDA_CHECK(cudaMemset(d, 0, blob));
+  for (int kb = 0; kb < kblocks; ++kb) {
+    const int c0 = kb * kb_ch, nc = Cin - c0 < kb_ch ? Cin - c0 : kb_ch;
+    float *dst = d + (size_t)kb * 11 * kb_ch;
+    LWP_CUDA_CHECK(cudaMemcpy2D(dst, kb_ch * sizeof(float), dw_w + c0, (size_t)Cin * sizeof(float), nc * sizeof(float), 9,
+                                cudaMemcpyDeviceToDevice));
+    LWP_CUDA_CHECK(cudaMemcpy(dst + 9 * kb_ch, dw_scale + c0, nc * sizeof(float), cudaMemcpyDeviceToDevice));
+    LWP_CUDA_CHECK(cudaMemcpy(dst + 10 * kb_ch, dw_shift + c0, nc * sizeof(float), cudaMemcpyDeviceToDevice));
+  }
+  *out = d;
+  return LWP_OK;
+}
+
+extern "C" int lwp_plan_add_sepconv(lwp_plan *p, const void *in, const float *dw_w, const float *dw_scale,
+                                    const float *dw_shift, int dw_act, int stride, const void *w, const float *scale,
+                                    const float *shift, int act, const void *residual, int res_ld, void *out, int out_ld,
+                                    int n, int H, int W, int Cin, int Cout) {
+  LWP_REQUIRE(p && in && dw_w && dw_scale && dw_shift && w && scale && shift && out, "lwp_plan_add_sepconv: null pointer");
+  LWP_REQUIRE(n > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "lwp_plan_add_sepconv: bad shape");
+  LWP_REQUIRE(stride == 1 || stride == 2, "lwp_plan_add_sepconv: stride must be 1 or 2");
+  const bool tf32 = p->dtype == LWP_DTYPE_TF32;
+  const int es = tf32 ? 4 : 2;
+  const int kb_ch = kKBlockBytes / es;
+  const int cout_pad = (Cout + 63) / 64 * 64;
+  LWP_REQUIRE(Cin % kb_ch == 0, "lwp_plan_add_sepconv: Cin must be a multiple of %d", kb_ch);
+  LWP_REQUIRE(out_ld % 8 == 0 && out_ld >= Cout && ((uintptr_t)out % 16) == 0 && ((uintptr_t)in % 16) == 0 &&
+                  ((uintptr_t)w % 16) == 0,
+              "lwp_plan_add_sepconv: bad out_ld / alignment");
+  LWP_REQUIRE(!residual || (res_ld % 8 == 0 && (uintptr_t)residual % 16 == 0), "lwp_plan_add_sepconv: bad res_ld");
+  if (cout_pad > 256) { set_error("lwp_plan_add_sepconv: Cout %d needs more than one 256-column MMA", Cout); return LWP_ECAP; }
+  int rc = sepconv_init();
+  if (rc != LWP_OK) return rc;
+  Op op;
+  op.kind = OP_SEP;
+  SepParams &f = op.sp;
+  f.H = H; f.W = W; f.NIMG = n; f.stride = stride;
+  f.Ho = (H - 1) / stride + 1; f.Wo = (W - 1) / stride + 1;
+  f.cin = Cin; f.kb_ch = kb_ch; f.kblocks = Cin / kb_ch;
+  f.cout_pad = cout_pad;
+  int n_store = cout_pad;
+  if (out_ld < n_store) n_store = out_ld / 8 * 8;
+  if (residual) { int lim = (Cout + 7) / 8 * 8; if (lim < n_store) n_store = lim; }
+  LWP_REQUIRE(n_store % 64 == 0, "lwp_plan_add_sepconv: stored width %d is not a multiple of 64 columns", n_store);
+  f.n_store = n_store;
+  f.slice_bytes = n_store / 4 * es;   // one compute warp stages 32 rows x a quarter of the columns
+  if (f.slice_bytes > 128) { set_error("lwp_plan_add_sepconv: %d-byte output slices (fp32, N = 256)", f.slice_bytes); return LWP_ECAP; }
+  f.idesc = make_umma_idesc(tf32, kBlockM, cout_pad);
+  f.acc_stages = 512 / cout_pad > 4 ? 4 : 512 / cout_pad;
+  f.dw_act = dw_act; f.act = act; f.scale = scale; f.shift = shift;
+  f.residual = residual; f.res_ld = res_ld; f.err_flag = p->err_flag;
+  // output tile: 128 pixels, width a multiple of 4 and at most 32 (one epilogue warp = a bw x bh box of 32 rows), height
+  // a multiple of 2; cheapest = fewest (halo + output) pixels over the map
+  long long best = -1;
+  for (int tw = 4; tw <= 32; tw <<= 1) {
+    const int th = 128 / tw;
+    const int iw = (tw - 1) * stride + 3, ih = (th - 1) * stride + 3;
+    if (iw > 256 || ih > 256) continue;
+    long long cost = (long long)ceil_div(f.Ho, th) * ceil_div(f.Wo, tw) * ((long long)iw * ih + 2 * 128);
+    if (best < 0 || cost < best) { best = cost; f.tile_h = th; f.tile_w = tw; f.iw = iw; f.ih = ih; }
+  }
+  LWP_REQUIRE(best >= 0, "lwp_plan_add_sepconv: no tile shape fits");
+  if (const char *e = getenv("LWP_SEP_TW")) { int tw = atoi(e); if (tw == 4 || tw == 8 || tw == 16 || tw == 32) { f.tile_w = tw; f.tile_h = 128 / tw; f.iw = (tw - 1) * stride + 3; f.ih = (f.tile_h - 1) * stride + 3; } }
+  f.tiles_x = ceil_div(f.Wo, f.tile_w); f.tiles_y = ceil_div(f.Ho, f.tile_h);
+  f.m_tiles = n * f.tiles_x * f.tiles_y;
+  f.in_stage_bytes = (uint32_t)(f.iw * f.ih * kKBlockBytes);
+  // rings: as deep as shared memory allows (the depthwise groups work on 2 / 4 items at once), halo boxes first
+  // (in_stages must be a multiple of the number of depthwise groups: a group refills the stages it reads)
+  // ring depths are multiples of the number of depthwise groups: a stage is then always used by the same group, which
+  // therefore sees every phase of its barriers (a group skipping a phase of a shared stage would pass a parity wait early)
+  const int groups = tf32 ? 2 : 1;
+  f.in_stages = 2; f.a_stages = 2;
+  if (sepconv_smem_bytes(f) > (size_t)gemm_smem_cap()) { set_error("lwp_plan_add_sepconv: weights + rings do not fit in shared memory"); return LWP_ECAP; }
+  for (int round = 0; round < 8; ++round) {
+    SepParams t = f;
+    if (t.in_stages <= t.a_stages && t.in_stages + groups <= 8) t.in_stages += groups; else if (t.a_stages + groups <= 8) t.a_stages += groups; else break;
+    if (sepconv_smem_bytes(t) <= (size_t)gemm_smem_cap()) f = t; else break;
+  }
+  rc = build_dw_consts(p, dw_w, dw_scale, dw_shift, Cin, kb_ch, f.kblocks, &f.dw_consts);
+  if (rc != LWP_OK) return rc;
+  op.grid = f.m_tiles < num_sms() ? f.m_tiles : num_sms();
+
+  EncodeTiledFn enc = get_encode_fn();
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * es, (cuuint64_t)Cin * es * W, (cuuint64_t)Cin * es * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)kb_ch, (cuuint32_t)f.iw, (cuuint32_t)f.ih, 1};
+    CUresult r = enc(&op.tmA, dt, 4, const_cast<void *>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(sepconv in) failed: %d", (int)r); return LWP_ECUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin * es};
+    cuuint32_t box[2] = {(cuuint32_t)kb_ch, (cuuint32_t)cout_pad};
+    CUresult r = enc(&op.tmB, dt, 2, const_cast<void *>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(sepconv B) failed: %d", (int)r); return LWP_ECUDA; }
+  }
+  {
+    const int bw = f.tile_w < 32 ? f.tile_w : 32, bh = 32 / bw;
+    cuuint64_t dims[4] = {(cuuint64_t)n_store, (cuuint64_t)f.Wo, (cuuint64_t)f.Ho, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)out_ld * es, (cuuint64_t)out_ld * es * f.Wo, (cuuint64_t)out_ld * es * f.Wo * f.Ho};
+    cuuint32_t box[4] = {(cuuint32_t)(n_store / 4), (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const CUtensorMapSwizzle sw = f.slice_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : f.slice_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = enc(&op.tmC, dt, 4, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(sepconv C) failed: %d", (int)r); return LWP_ECUDA; }
+  }
+  p->ops.push_back(op);
+  return LWP_OK;
+}
+
 extern "C" int lwp_plan_add_heads_fused(lwp_plan *p, const void *in, int in_ld, const void *w1, const float *scale1,
                                         const float *shift1, int c_mid, const void *w2, const float *scale2,
                                         const float *shift2, void *out, int out_ld, float *out_f32, int out_f32_ld,
@@ -590,6 +714,9 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const void *x, int first, int las
         break;
       case OP_DWPW:
         rc = dwpw_launch(f32, op.tmA, op.tmB, op.tmC, op.fp, op.grid, st);
+        break;
+      case OP_SEP:
+        rc = sepconv_launch(f32, op.tmA, op.tmB, op.tmC, op.sp, op.grid, st);
         break;
       case OP_HEADS:
         rc = heads_fused_launch(op.tmA, op.tmB, op.tmC, op.hd_px, op.hd_cin, op.hd_cmid, op.hd_scale1, op.hd_shift1,

@@ -57,6 +57,19 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
   return true;
 }
 
+// Wait of a throughput-oriented warp (one of many compute warps): back off with nanosleep between polls, so a waiting
+// warp does not burn issue slots the working warps need (a quarter of all issued instructions of the first fused
+// depthwise + 1x1 kernel were polls of waiting warps).  Same bounded-spin trap as mbar_wait.
+__device__ __forceinline__ bool mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(96);
+    if (clock64() - t0 > kMbarTimeoutClocks) { __trap(); return false; }
+  }
+  return true;
+}
+
 // The same operations taking shared-window addresses (uint32_t) directly: the hot pipeline loops keep barrier and
 // tile addresses as integers in the uniform datapath instead of converting generic pointers at every use.
 __device__ __forceinline__ void mbar_arrive_expect_tx_u32(uint32_t bar, uint32_t bytes) {
@@ -348,6 +361,14 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
                  "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
                  "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {   // 16-register form of the tied wait
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :
                : "memory");
 }

@@ -178,6 +178,14 @@ class Plan:
         fuse = os.environ.get("LWP_DWPW_FUSION", "0")
         self.fuse_dwpw = fuse not in ("", "0")
         self.fuse_only = None if fuse in ("", "0", "1", "all") else set(fuse.split(","))
+        # weight-resident fused block for the thin layers (sepconv_gemm.cu).  Measured (round 2, 64 x 368x656 bf16): it takes
+        # the depthwise intermediate out of HBM (ncu: 451 MB instead of 741 MB of DRAM traffic on model.3) but is
+        # instruction-issue-bound on the CUDA cores -- 208 us vs 178 us for TMA depthwise + tcgen05 GEMM on model.3, 95 vs 93 us
+        # on the Cpm trunk blocks -- so it is OPT-IN: LWP_SEPCONV=1 uses it wherever it fits, a comma-separated list of op
+        # names restricts it (DESIGN.md section 3.2d has the ncu evidence)
+        sep = os.environ.get("LWP_SEPCONV", "0")
+        self.use_sepconv = sep not in ("", "0")
+        self.sepconv_only = None if sep in ("", "0", "1", "all") else set(sep.split(","))
         self.bufs = []
         self.op_names = []
         self.op_meta = []  # per op: kind, algorithmic flops and bytes (real channel counts, no padding)
@@ -255,6 +263,32 @@ class Plan:
         self.op_meta.append(dict(kind="dwpw", flops=2.0 * px * d.c * (g.cout + 9), bytes=float(nbytes)))
         return True
 
+    def _sepconv(self, name, src, d, g, n, H, W, out, out_ld, residual=None, res_ld=0):
+        """Record the weight-resident fused depthwise + 1x1 block (thin layers); returns False (nothing recorded) when
+        the layer is not eligible or its weights + rings do not fit in shared memory."""
+        kb_ch = 64 if self.tdtype == torch.bfloat16 else 32
+        if not self.use_sepconv or (self.sepconv_only is not None and name not in self.sepconv_only):
+            return False
+        if not (d.dilation == 1 and d.stride in (1, 2) and g.taps == 1 and d.c == g.cin and d.c % kb_ch == 0
+                and g.cout_pad <= 256):
+            return False
+        es = 2 if self.tdtype == torch.bfloat16 else 4
+        rc = self.lib.lwp_plan_add_sepconv(
+            self.handle, src.data_ptr(), d.w.data_ptr(), d.scale.data_ptr(), d.shift.data_ptr(), d.act, d.stride,
+            g.w.data_ptr(), g.scale.data_ptr(), g.shift.data_ptr(), g.act,
+            residual.data_ptr() if residual is not None else None, res_ld, out.data_ptr(), out_ld, n, H, W, d.c, g.cout)
+        if rc == 3:  # LWP_ECAP: two-kernel form
+            return False
+        _lib.check(rc, "lwp_plan_add_sepconv(%s)" % name)
+        self.op_names.append(name)
+        ho, wo = (H - 1) // d.stride + 1, (W - 1) // d.stride + 1
+        px = n * ho * wo
+        nbytes = (n * H * W * d.c + px * g.cout) * es + d.c * g.cout * es + 9 * d.c * 4
+        if residual is not None:
+            nbytes += px * g.cout * es
+        self.op_meta.append(dict(kind="sepconv", flops=2.0 * px * d.c * (g.cout + 9), bytes=float(nbytes)))
+        return True
+
     def _heads(self, name, src, src_ld, heads, n, h, w, big, out, out_ptr_off, out_f32):
         """The two (merged) 1x1 layers of a stage's heads: one back-to-back GEMM kernel on bf16 plans (the intermediate
         never leaves the SM; LWP_HEADS_FUSION=0 keeps the two-kernel form), two conv GEMMs otherwise."""
@@ -314,6 +348,8 @@ class Plan:
             if self._fusable(dw, pw, "model.%d.dwpw" % (i + 1)) and self._dwpw("model.%d.dwpw" % (i + 1), pp[cur], dw, pw, n, hh, ww, pp[cur ^ 1],
                                                     pw.cout_pad):
                 cur ^= 1
+            elif self._sepconv("model.%d.sep" % (i + 1), pp[cur], dw, pw, n, hh, ww, pp[cur ^ 1], pw.cout_pad):
+                cur ^= 1
             else:
                 self._dw("model.%d.dw" % (i + 1), pp[cur], pp[cur ^ 1], dw, n, hh, ww)
                 self._gemm("model.%d.pw" % (i + 1), pp[cur ^ 1], c, pw, n, ho, wo, out=pp[cur], out_ld=pw.cout_pad)
@@ -339,6 +375,8 @@ class Plan:
             dst = t1 if src is t0 else t0
             if self._fusable(dw, pw, "cpm.trunk.%d.dwpw" % i) and self._dwpw("cpm.trunk.%d.dwpw" % i, src, dw, pw, n, h, w, dst, nc,
                                                     residual=res, res_ld=nc):
+                pass
+            elif self._sepconv("cpm.trunk.%d.sep" % i, src, dw, pw, n, h, w, dst, nc, residual=res, res_ld=nc):
                 pass
             else:
                 mid = t1 if src is t0 else t0
