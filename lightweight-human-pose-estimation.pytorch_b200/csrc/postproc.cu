@@ -678,137 +678,190 @@ limb_match_kernel(const Conn *__restrict__ conn, const int *__restrict__ conn_co
   if (lane == 0) match_count[slot] = accepted;
 }
 
-// One warp per image walks the 19 limbs in table order and builds the pose entries exactly like the
-// reference's sequential code; lanes parallelise the "for every pose" scans.
+// Pose assembly (modules/keypoints.py:63-92,159-200), one block per image.  The reference walks the accepted connections
+// of a limb one after the other and scans every pose for each of them; limbs must stay in table order, but WITHIN a limb
+// the connections are independent: greedy matching is one-to-one, so the key-point ids on either side of a limb's
+// connections are pairwise distinct, a pose holds one id per slot and therefore matches at most one connection, and a
+// pose appended for an unmatched connection (its slot ka holds that connection's own id) can never match a later one.
+// So every limb is a constant number of block-wide steps: (1) an id -> connection lookup table, (2) all poses updated in
+// parallel through it, (3) unmatched connections appended in connection order by a prefix sum -- the same pose table,
+// bit for bit (every pose still receives its single update `score += (score_b + ratio)` with the same operands), in a
+// few microseconds instead of ~100 for the one-warp sequential walk.  Quirks kept: limb 0 replaces the list, limbs
+// 17 / 18 only fill a missing end and touch neither score nor count, singleton poses for one-sided limbs.
+constexpr int kPaThreads = 128;
+
+// exclusive prefix over the block of one flag per thread; *total = number of flags set (uniform); two barriers inside
+__device__ __forceinline__ int block_excl_scan_flag(bool flag, int *s_warp /* kPaThreads / 32 + 1 ints */, int *total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) s_warp[w] = __popc(m);
+  __syncthreads();
+  int base = 0, sum = 0;
+#pragma unroll
+  for (int i = 0; i < kPaThreads / 32; ++i) {
+    const int v = s_warp[i];
+    if (i < w) base += v;
+    sum += v;
+  }
+  __syncthreads();   // s_warp may be rewritten by the next call
+  *total = sum;
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
 template <bool kSmem>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kPaThreads)
 pose_assemble_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ counts,
                      const int *__restrict__ kpt_start, int cap_kpts, const Match *__restrict__ match,
                      const int *__restrict__ match_count, double *__restrict__ scratch,
                      double *__restrict__ pose_entries, int *__restrict__ n_poses, int cap_poses,
                      int *__restrict__ overflow) {
-  const int img = blockIdx.x, lane = threadIdx.x;
+  const int img = blockIdx.x, tid = threadIdx.x;
   extern __shared__ __align__(16) unsigned char pa_smem[];
-  // working set in shared memory (latency ~30 cycles instead of an L2 round trip per dependent step)
+  // layout: [poses (kSmem only)] [matches of the current limb: cap_kpts] [lutA, lutB, found: 3 x cap_kpts ints]
   double *poses = kSmem ? reinterpret_cast<double *>(pa_smem) : scratch + (size_t)img * cap_poses * LWP_POSE_ENTRY;
   Match *s_match = reinterpret_cast<Match *>(pa_smem + (kSmem ? (size_t)cap_poses * LWP_POSE_ENTRY * sizeof(double) : 0));
+  int *lutA = reinterpret_cast<int *>(s_match + cap_kpts), *lutB = lutA + cap_kpts, *found = lutB + cap_kpts;
+  __shared__ int s_cnt[LWP_NUM_KPT_TYPES], s_start[LWP_NUM_KPT_TYPES + 1], s_m[LWP_NUM_LIMBS], s_warp[kPaThreads / 32 + 1];
 #define POSE(jj) (poses + (size_t)(jj) * LWP_POSE_ENTRY)
-  int np = 0;
+  if (tid < LWP_NUM_KPT_TYPES) s_cnt[tid] = counts[img * LWP_NUM_KPT_TYPES + tid];
+  if (tid < LWP_NUM_KPT_TYPES + 1) s_start[tid] = kpt_start[img * (LWP_NUM_KPT_TYPES + 1) + tid];
+  if (tid < LWP_NUM_LIMBS) s_m[tid] = match_count[img * LWP_NUM_LIMBS + tid];
+  __syncthreads();
+  int np = 0;          // uniform over the block
   bool ovf = false;
-  const int *cnts = counts + img * LWP_NUM_KPT_TYPES;
-  const int *starts = kpt_start + img * (LWP_NUM_KPT_TYPES + 1);
-
-  // append a pose holding up to two key-points; all lanes call it, lanes 0..19 write one field each
-  auto append = [&](int slot_a, double id_a, int slot_b, double id_b, double score, double count) {
-    if (np >= cap_poses) { ovf = true; return; }
-    if (lane < LWP_POSE_ENTRY) {
-      double v = -1.0;
-      if (lane == slot_a) v = id_a;
-      if (lane == slot_b) v = id_b;
-      if (lane == 18) v = score;
-      if (lane == 19) v = count;
-      POSE(np)[lane] = v;
-    }
-    ++np;
-    __syncwarp();
-  };
-
-  // per-image tables read once (lane l holds entry l) instead of one dependent global load per limb
-  const int my_cnt = lane < LWP_NUM_KPT_TYPES ? cnts[lane] : 0;
-  const int my_start = lane < LWP_NUM_KPT_TYPES + 1 ? starts[lane] : 0;
-  const int my_m = lane < LWP_NUM_LIMBS ? match_count[img * LWP_NUM_LIMBS + lane] : 0;
   const Match *Mimg = match + (size_t)img * LWP_NUM_LIMBS * cap_kpts;
-  // the first 32 accepted connections of the NEXT limb are fetched while the current limb is processed
-  Match pre;
-  pre.ratio = 0.0; pre.ida = pre.idb = 0; pre.sa = pre.sb = 0.f;
-  if (lane < __shfl_sync(0xffffffffu, my_m, 0)) pre = Mimg[lane];
+
+  // write one pose holding up to two key-points (one thread writes all 20 fields)
+  auto write_pose = [&](int pos, int slot_a, double id_a, int slot_b, double id_b, double score, double count) {
+    double *p = POSE(pos);
+#pragma unroll
+    for (int q = 0; q < LWP_NUM_KPT_TYPES; ++q) p[q] = -1.0;
+    p[slot_a] = id_a;
+    if (slot_b >= 0) p[slot_b] = id_b;
+    p[18] = score;
+    p[19] = count;
+  };
 
   for (int limb = 0; limb < LWP_NUM_LIMBS; ++limb) {
     const int ka = c_kpt_ids[limb][0], kb = c_kpt_ids[limb][1];
-    const int nA = __shfl_sync(0xffffffffu, my_cnt, ka), nB = __shfl_sync(0xffffffffu, my_cnt, kb);
-    const int m = __shfl_sync(0xffffffffu, my_m, limb);
-    const Match cur = pre;
-    if (limb + 1 < LWP_NUM_LIMBS && lane < __shfl_sync(0xffffffffu, my_m, limb + 1))
-      pre = Mimg[(size_t)(limb + 1) * cap_kpts + lane];
+    const int nA = s_cnt[ka], nB = s_cnt[kb];
     if (nA == 0 && nB == 0) continue;
-    if (nA == 0 || nB == 0) {  // :66-92 singleton poses for key-points no pose holds yet
-      const int slot = nA == 0 ? kb : ka, cnt = nA == 0 ? nB : nA;
-      const int start = __shfl_sync(0xffffffffu, my_start, slot);
+    if (nA == 0 || nB == 0) {  // :66-92 singleton poses, in key-point order, for key-points no pose holds yet
+      const int slot = nA == 0 ? kb : ka, cnt = nA == 0 ? nB : nA, start = s_start[slot];
       const lwp_keypoint *K = kpts + ((size_t)img * LWP_NUM_KPT_TYPES + slot) * cap_kpts;
-      for (int i = 0; i < cnt; ++i) {
-        double id = (double)(start + i);
-        bool found = false;
-        for (int j = lane; j < np; j += 32) found |= (POSE(j)[slot] == id);
-        if (!__any_sync(0xffffffffu, found)) append(slot, id, -1, 0.0, (double)K[i].score, 1.0);
+      for (int i = tid; i < cnt; i += kPaThreads) found[i] = 0;
+      __syncthreads();
+      for (int j = tid; j < np; j += kPaThreads) {
+        const double v = POSE(j)[slot];
+        if (v != -1.0) {
+          const int idx = (int)v - start;
+          if (idx >= 0 && idx < cnt) found[idx] = 1;
+        }
       }
+      __syncthreads();
+      for (int base = 0; base < cnt; base += kPaThreads) {   // ordered append of the key-points not found
+        const int i = base + tid;
+        const bool add = i < cnt && !found[i];
+        int total;
+        const int pos = np + block_excl_scan_flag(add, s_warp, &total);
+        if (add) {
+          if (pos < cap_poses) write_pose(pos, slot, (double)(start + i), -1, 0.0, (double)K[i].score, 1.0);
+        }
+        np += total;
+      }
+      if (np > cap_poses) { ovf = true; np = cap_poses; }
+      __syncthreads();
       continue;
     }
+    const int m = s_m[limb];
     if (m == 0) continue;
     const Match *Mg = Mimg + (size_t)limb * cap_kpts;
-    const Match *M = Mg;
-    if (kSmem) {  // this limb's accepted connections: the prefetched 32 + (rarely) the rest
-      __syncwarp();
-      if (lane < m) s_match[lane] = cur;
-      for (int c = 32 + lane; c < m; c += 32) s_match[c] = Mg[c];
-      __syncwarp();
-      M = s_match;
+    const int startA = s_start[ka], startB = s_start[kb];
+    for (int c = tid; c < m; c += kPaThreads) s_match[c] = Mg[c];
+    if (limb == 0) {  // :159-165 replaces the list with one pose per accepted connection
+      __syncthreads();
+      np = m < cap_poses ? m : cap_poses;
+      if (m > cap_poses) ovf = true;
+      for (int c = tid; c < np; c += kPaThreads) {
+        const Match mt = s_match[c];
+        write_pose(c, ka, (double)mt.ida, kb, (double)mt.idb, __dadd_rn(__dadd_rn((double)mt.sa, (double)mt.sb), mt.ratio), 2.0);
+      }
+      __syncthreads();
+      continue;
     }
-    if (limb == 0) {  // :159-165 replaces the list
-      np = 0;
-      for (int c = 0; c < m; ++c) {
-        Match mt = M[c];
-        append(ka, (double)mt.ida, kb, (double)mt.idb,
-               __dadd_rn(__dadd_rn((double)mt.sa, (double)mt.sb), mt.ratio), 2.0);
-      }
-    } else if (limb == 17 || limb == 18) {  // :166-175
-      for (int c = 0; c < m; ++c) {
-        Match mt = M[c];
-        double ia = (double)mt.ida, ib = (double)mt.idb;
-        for (int j = lane; j < np; j += 32) {
-          double *p = POSE(j);
-          if (p[ka] == ia && p[kb] == -1.0) p[kb] = ib;
-          else if (p[kb] == ib && p[ka] == -1.0) p[ka] = ia;
+    // id -> connection tables (ids of one key-point type are consecutive: local index = id - start of the type)
+    for (int i = tid; i < nA; i += kPaThreads) lutA[i] = -1;
+    for (int i = tid; i < nB; i += kPaThreads) lutB[i] = -1;
+    for (int c = tid; c < m; c += kPaThreads) found[c] = 0;
+    __syncthreads();
+    for (int c = tid; c < m; c += kPaThreads) {
+      lutA[s_match[c].ida - startA] = c;
+      lutB[s_match[c].idb - startB] = c;
+    }
+    __syncthreads();
+    if (limb == 17 || limb == 18) {  // :166-175 fill a missing end only; no score / count change, no new pose
+      for (int j = tid; j < np; j += kPaThreads) {
+        double *p = POSE(j);
+        const double va = p[ka], vb = p[kb];
+        if (va != -1.0 && vb == -1.0) {
+          const int c = lutA[(int)va - startA];
+          if (c >= 0) p[kb] = (double)s_match[c].idb;
+        } else if (va == -1.0 && vb != -1.0) {
+          const int c = lutB[(int)vb - startB];
+          if (c >= 0) p[ka] = (double)s_match[c].ida;
         }
-        __syncwarp();
       }
-    } else {  // :176-193
-      for (int c = 0; c < m; ++c) {
-        Match mt = M[c];
-        double ia = (double)mt.ida, ib = (double)mt.idb;
-        bool found = false;
-        for (int j = lane; j < np; j += 32) {
-          double *p = POSE(j);
-          if (p[ka] == ia) {
-            p[kb] = ib;
-            p[19] = __dadd_rn(p[19], 1.0);
-            p[18] = __dadd_rn(p[18], __dadd_rn((double)mt.sb, mt.ratio));
-            found = true;
-          }
+      __syncthreads();
+      continue;
+    }
+    // :176-193 every pose whose slot ka holds a connection's a gets its b, count += 1, score += (score_b + ratio)
+    for (int j = tid; j < np; j += kPaThreads) {
+      double *p = POSE(j);
+      const double va = p[ka];
+      if (va != -1.0) {
+        const int c = lutA[(int)va - startA];
+        if (c >= 0) {
+          const Match mt = s_match[c];
+          p[kb] = (double)mt.idb;
+          p[19] = __dadd_rn(p[19], 1.0);
+          p[18] = __dadd_rn(p[18], __dadd_rn((double)mt.sb, mt.ratio));
+          found[c] = 1;
         }
-        __syncwarp();
-        if (!__any_sync(0xffffffffu, found))
-          append(ka, ia, kb, ib, __dadd_rn(__dadd_rn((double)mt.sa, (double)mt.sb), mt.ratio), 2.0);
       }
     }
+    __syncthreads();
+    for (int base = 0; base < m; base += kPaThreads) {   // connections no pose matched: new poses, in connection order
+      const int c = base + tid;
+      const bool add = c < m && !found[c];
+      int total;
+      const int pos = np + block_excl_scan_flag(add, s_warp, &total);
+      if (add && pos < cap_poses) {
+        const Match mt = s_match[c];
+        write_pose(pos, ka, (double)mt.ida, kb, (double)mt.idb, __dadd_rn(__dadd_rn((double)mt.sa, (double)mt.sb), mt.ratio), 2.0);
+      }
+      np += total;
+    }
+    if (np > cap_poses) { ovf = true; np = cap_poses; }
+    __syncthreads();
   }
-  __syncwarp();
+  __syncthreads();
   // :195-200 final filter, order preserved
   double *outp = pose_entries + (size_t)img * cap_poses * LWP_POSE_ENTRY;
   int kept = 0;
-  for (int base = 0; base < np; base += 32) {
-    int j = base + lane;
+  for (int base = 0; base < np; base += kPaThreads) {
+    const int j = base + tid;
     bool keep = false;
     if (j < np) {
-      double cnt = POSE(j)[19], sc = POSE(j)[18];
+      const double cnt = POSE(j)[19], sc = POSE(j)[18];
       keep = !(cnt < 3.0 || __ddiv_rn(sc, cnt) < 0.2);
     }
-    unsigned mk = __ballot_sync(0xffffffffu, keep);
-    int pos = kept + __popc(mk & ((1u << lane) - 1));
+    int total;
+    const int pos = kept + block_excl_scan_flag(keep, s_warp, &total);
     if (keep)
       for (int q = 0; q < LWP_POSE_ENTRY; ++q) outp[(size_t)pos * LWP_POSE_ENTRY + q] = POSE(j)[q];
-    kept += __popc(mk);
+    kept += total;
   }
-  if (lane == 0) {
+  if (tid == 0) {
     n_poses[img] = kept;
     if (ovf) overflow[img] = 1;
   }
@@ -1008,7 +1061,8 @@ static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *cou
   limb_match_kernel<<<dim3(LWP_NUM_LIMBS, n), 256, smem, st>>>(w.conn, w.conn_count, cap_connections, kpts, counts,
                                                               kpt_start, cap_kpts, w.match, w.match_count, overflow);
   LWP_LAUNCH_CHECK();
-  const size_t pa_smem = (size_t)cap_poses * LWP_POSE_ENTRY * sizeof(double) + (size_t)cap_kpts * sizeof(Match);
+  const size_t pa_tables = (size_t)cap_kpts * (sizeof(Match) + 3 * sizeof(int));   // current limb's matches + lutA / lutB / found
+  const size_t pa_smem = (size_t)cap_poses * LWP_POSE_ENTRY * sizeof(double) + pa_tables;
   if (pa_smem <= 160 * 1024) {
     static DeviceOnce pa_attr;
     int pa_attr_slot;
@@ -1017,10 +1071,17 @@ static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *cou
                                           160 * 1024));
       pa_attr.done[pa_attr_slot] = true;
     }
-    pose_assemble_kernel<true><<<n, 32, pa_smem, st>>>(kpts, counts, kpt_start, cap_kpts, w.match, w.match_count,
+    pose_assemble_kernel<true><<<n, kPaThreads, pa_smem, st>>>(kpts, counts, kpt_start, cap_kpts, w.match, w.match_count,
                                                        w.poses, pose_entries, n_poses, cap_poses, overflow);
   } else {
-    pose_assemble_kernel<false><<<n, 32, (size_t)cap_kpts * sizeof(Match), st>>>(
+    if (pa_tables > 200 * 1024) { set_error("lwp_group_keypoints: cap_kpts %d too large", cap_kpts); return LWP_ECAP; }
+    static DeviceOnce pb_attr;
+    int pb_attr_slot;
+    if (pb_attr.pending(&pb_attr_slot)) {
+      LWP_CUDA_CHECK(cudaFuncSetAttribute(pose_assemble_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      pb_attr.done[pb_attr_slot] = true;
+    }
+    pose_assemble_kernel<false><<<n, kPaThreads, pa_tables, st>>>(
         kpts, counts, kpt_start, cap_kpts, w.match, w.match_count, w.poses, pose_entries, n_poses, cap_poses, overflow);
   }
   LWP_LAUNCH_CHECK();
