@@ -132,6 +132,19 @@ int lwp_group_keypoints_fused(const lwp_keypoint *kpts, const int32_t *counts, c
                               int32_t *n_poses, int cap_poses, int cap_connections, void *workspace,
                               size_t workspace_bytes, int32_t *overflow, void *stream);
 
+/*
+ * Replaces the result post-conversion of demo.py:101-115 for n images at once: key-point coordinates mapped back to
+ * the original frame, (x * stride / upsample_ratio - pad) / scale evaluated in float64 exactly like the reference's
+ * Python expression, truncated by int(), gathered per pose into an [18][2] int32 table (-1, -1 for a missing
+ * key-point); plus Pose.get_bbox (modules/pose.py:30-39: cv2.boundingRect of the found key-points = x, y, w, h) and the
+ * pose confidence pose_entries[n][18] (demo.py:114).
+ * xform: [n][3] doubles (pad_left = pad[1], pad_top = pad[0], scale) as returned by infer_fast for each image.
+ * pose_kpts: [n][cap_poses][18][2]; bbox: [n][cap_poses][4]; confidence: [n][cap_poses]; entries >= n_poses[i] untouched.
+ */
+int lwp_pose_convert(const double *pose_entries, const int32_t *n_poses, int cap_poses, const lwp_keypoint *kpts,
+                     const int32_t *kpt_start, int cap_kpts, int n, double stride, double upsample_ratio,
+                     const double *xform, int32_t *pose_kpts, int32_t *bbox, double *confidence, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Network forward: a "plan" is a recorded list of layer launches with pre-built TMA descriptors
  * for one (batch, height, width, dtype).  It replaces PoseEstimationWithMobileNet.forward

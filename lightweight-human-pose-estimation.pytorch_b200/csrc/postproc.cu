@@ -1108,3 +1108,52 @@ extern "C" int lwp_group_keypoints_fused(const lwp_keypoint *kpts, const int32_t
   return group_common(true, kpts, counts, kpt_start, cap_kpts, src, &u, n, H, W, ld, demo, min_paf_score, pose_entries,
                       n_poses, cap_poses, cap_connections, workspace, workspace_bytes, overflow, stream);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Result post-conversion: what demo.py:101-115 does with the pose table -- key-point coordinates back in the original
+// frame, (x * stride / upsample_ratio - pad) / scale in float64 with every operation rounded separately, Python int()
+// truncation -- plus Pose.get_bbox (modules/pose.py:30-39: cv2.boundingRect of the found key-points).  One thread per pose.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pose_convert_kernel(const double *__restrict__ pose_entries, const int *__restrict__ n_poses, int cap_poses,
+                    const lwp_keypoint *__restrict__ kpts, const int *__restrict__ kpt_start, int cap_kpts,
+                    double stride, double upsample_ratio, const double *__restrict__ xform, int32_t *__restrict__ pose_kpts,
+                    int32_t *__restrict__ bbox, double *__restrict__ confidence) {
+  const int img = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_poses[img] || j >= cap_poses) return;
+  const double pad_left = xform[img * 3 + 0], pad_top = xform[img * 3 + 1], scale = xform[img * 3 + 2];
+  const double *pe = pose_entries + ((size_t)img * cap_poses + j) * LWP_POSE_ENTRY;
+  int32_t *pk = pose_kpts + ((size_t)img * cap_poses + j) * LWP_NUM_KPT_TYPES * 2;
+  const int *starts = kpt_start + img * (LWP_NUM_KPT_TYPES + 1);
+  int minx = INT_MAX, miny = INT_MAX, maxx = INT_MIN, maxy = INT_MIN;
+  for (int k = 0; k < LWP_NUM_KPT_TYPES; ++k) {
+    int x = -1, y = -1;
+    const double v = pe[k];
+    if (v != -1.0) {
+      const int id = (int)v;                     // global id -> (channel k, index id - start of the channel)
+      const lwp_keypoint kp = kpts[((size_t)img * LWP_NUM_KPT_TYPES + k) * cap_kpts + (id - starts[k])];
+      x = __double2int_rz(__ddiv_rn(__dsub_rn(__ddiv_rn(__dmul_rn((double)kp.x, stride), upsample_ratio), pad_left), scale));
+      y = __double2int_rz(__ddiv_rn(__dsub_rn(__ddiv_rn(__dmul_rn((double)kp.y, stride), upsample_ratio), pad_top), scale));
+      minx = min(minx, x); maxx = max(maxx, x); miny = min(miny, y); maxy = max(maxy, y);
+    }
+    pk[2 * k] = x; pk[2 * k + 1] = y;
+  }
+  int32_t *bb = bbox + ((size_t)img * cap_poses + j) * 4;
+  if (maxx >= minx) { bb[0] = minx; bb[1] = miny; bb[2] = maxx - minx + 1; bb[3] = maxy - miny + 1; }
+  else { bb[0] = bb[1] = bb[2] = bb[3] = 0; }
+  confidence[(size_t)img * cap_poses + j] = pe[18];
+}
+
+extern "C" int lwp_pose_convert(const double *pose_entries, const int32_t *n_poses, int cap_poses, const lwp_keypoint *kpts,
+                                const int32_t *kpt_start, int cap_kpts, int n, double stride, double upsample_ratio,
+                                const double *xform, int32_t *pose_kpts, int32_t *bbox, double *confidence, void *stream) {
+  LWP_REQUIRE(pose_entries && n_poses && kpts && kpt_start && xform && pose_kpts && bbox && confidence,
+              "lwp_pose_convert: null pointer");
+  LWP_REQUIRE(n > 0 && cap_poses > 0 && cap_kpts > 0 && upsample_ratio != 0.0, "lwp_pose_convert: bad arguments");
+  dim3 grid(ceil_div(cap_poses, 128), n);
+  pose_convert_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(pose_entries, n_poses, cap_poses, kpts, kpt_start, cap_kpts,
+                                                              stride, upsample_ratio, xform, pose_kpts, bbox, confidence);
+  LWP_LAUNCH_CHECK();
+  return LWP_OK;
+}

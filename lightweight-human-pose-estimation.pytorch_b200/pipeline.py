@@ -22,9 +22,20 @@ from .engine import HEAD_LD
 class PoseResult:
     """Host copy of one batch of results (NumPy views of pinned staging buffers; valid until the next call)."""
 
-    def __init__(self, pose_entries, n_poses, kpts, counts, kpt_start, overflow):
+    def __init__(self, pose_entries, n_poses, kpts, counts, kpt_start, overflow, pose_kpts=None, bbox=None, confidence=None):
         self.pose_entries, self.n_poses = pose_entries, n_poses
         self.kpts, self.counts, self.kpt_start, self.overflow = kpts, counts, kpt_start, overflow
+        # device-side result post-conversion (PosePipeline(convert=...)): per pose the [18, 2] int32 key-points in
+        # original-frame coordinates, the bounding box and the confidence
+        self.pose_kpts, self.bbox, self.confidence = pose_kpts, bbox, confidence
+
+    def poses(self, i):
+        """The list of Pose objects demo.py:104-115 builds for frame i (key-points un-scaled to the original frame)."""
+        if self.pose_kpts is None:
+            raise RuntimeError("build the PosePipeline with convert=dict(pad=..., scale=...) to get Pose objects")
+        from .modules.pose import Pose
+        return [Pose(self.pose_kpts[i, j].copy(), self.confidence[i, j], bbox=self.bbox[i, j])
+                for j in range(int(self.n_poses[i]))]
 
     def check(self):
         postproc.raise_on_overflow(self.overflow)
@@ -64,6 +75,10 @@ class _Chunk:
         # the post-processing runs on its own stream on a private copy of the heads, so the network of the next
         # batch (which overwrites the plan's head buffer) can start while this batch is still being grouped
         self.heads_pp = torch.empty((n, pipe.h, pipe.w, HEAD_LD), dtype=torch.float32, device=dev)
+        if pipe.convert is not None:
+            self.pose_kpts = torch.empty((n, cp, postproc.NUM_KPT_TYPES, 2), dtype=torch.int32, device=dev)
+            self.bbox = torch.empty((n, cp, 4), dtype=torch.int32, device=dev)
+            self.confidence = torch.empty((n, cp), dtype=torch.float64, device=dev)
         self.net_done = torch.cuda.Event()
         self.pp_done = torch.cuda.Event()
 
@@ -107,6 +122,7 @@ class _Chunk:
                 postproc.group_keypoints_fused(self.kb, heads, r, demo=pipe.demo, min_paf_score=pipe.min_paf_score,
                                                cap_poses=cp, cap_connections=cn, workspace=self.ws_group,
                                                out=(self.pose_entries, self.n_poses))
+                self.enqueue_convert()
             return
         if stage in (None, "upsample"):
             postproc.upsample_cubic(heads, channels=19, fx=r, fy=r, out=self.heat_up, channel_offset=0)
@@ -118,6 +134,19 @@ class _Chunk:
             postproc.group_keypoints_batched(self.kb, self.paf_up, demo=pipe.demo, min_paf_score=pipe.min_paf_score,
                                              cap_poses=cp, cap_connections=cn, workspace=self.ws_group,
                                              out=(self.pose_entries, self.n_poses))
+            self.enqueue_convert()
+
+    def enqueue_convert(self):
+        """Result post-conversion (demo.py:101-115) on the device, when the pipeline was built with convert=..."""
+        cv = self.pipe.convert
+        if cv is None:
+            return
+        pad, scale = cv["pad"], cv["scale"]
+        if np.ndim(scale) > 0:   # per-frame transforms: this chunk's slice
+            pad, scale = np.asarray(pad)[self.lo:self.lo + self.n], np.asarray(scale)[self.lo:self.lo + self.n]
+        postproc.pose_convert(self.pose_entries, self.n_poses, self.kb, stride=cv.get("stride", 8),
+                              upsample_ratio=self.pipe.ratio, pad=pad, scale=scale,
+                              out=(self.pose_kpts, self.bbox, self.confidence))
 
 
 class _Slot:
@@ -136,13 +165,18 @@ class _Slot:
         self.h_counts = torch.empty((b, 18), dtype=torch.int32, **pin)
         self.h_kpt_start = torch.empty((b, 19), dtype=torch.int32, **pin)
         self.h_overflow = torch.empty((b,), dtype=torch.int32, **pin)
+        self.h_conv = None
+        if pipe.convert is not None:
+            self.h_conv = (torch.empty((b, cp, 18, 2), dtype=torch.int32, **pin), torch.empty((b, cp, 4), dtype=torch.int32, **pin),
+                           torch.empty((b, cp), dtype=torch.float64, **pin))
         self.copied = torch.cuda.Event()   # H2D of this slot's input finished
         self.consumed = torch.cuda.Event() # the network has finished reading x_dev
         self.done = torch.cuda.Event()     # compute + D2H of this slot finished
         self.busy = False
 
     def tables(self):
-        return (self.h_pose_entries, self.h_n_poses, self.h_kpts, self.h_counts, self.h_kpt_start, self.h_overflow)
+        return (self.h_pose_entries, self.h_n_poses, self.h_kpts, self.h_counts, self.h_kpt_start, self.h_overflow) + (
+            self.h_conv if self.h_conv is not None else ())
 
     def result(self):
         return PoseResult(*[t.numpy() for t in self.tables()])
@@ -157,7 +191,7 @@ class PosePipeline:
     def __init__(self, net, batch, height, width, precision="bf16", upsample_ratio=4, demo=True,
                  min_paf_score=0.05, cap_kpts=128, cap_candidates=2048, cap_poses=256, cap_connections=2048,
                  heads_hook=None, fused=True, chunk=None, depth=2, overlap_postproc=True, input_format="f32_nchw",
-                 img_mean=(128, 128, 128), img_scale=1 / 256, graph=False):
+                 img_mean=(128, 128, 128), img_scale=1 / 256, graph=False, convert=None):
         _lib.require_cuda()
         self.net, self.precision = net, precision
         self.n, self.H, self.W = batch, height, width
@@ -173,6 +207,9 @@ class PosePipeline:
         # graph=True: the ~60 launches of one pass (network, post-processing, result read-back) are captured once per
         # input buffer into a CUDA graph and replayed -- for small batches (the reference's batch-1 demo loop) the
         # launches, not the kernels, are the cost.  Everything then runs on one stream.
+        # convert=dict(pad=[top, left, bottom, right], scale=s[, stride=8]) (or per-frame sequences of both): the result
+        # post-conversion of demo.py:101-115 + Pose.get_bbox runs on the device too and PoseResult.poses(i) is available
+        self.convert = convert
         self.graph = bool(graph)
         if self.graph:
             self.overlap_postproc = False
@@ -297,6 +334,10 @@ class PosePipeline:
                     slot.h_counts[sl].copy_(c.kb.counts, non_blocking=True)
                     slot.h_kpt_start[sl].copy_(c.kb.kpt_start, non_blocking=True)
                     slot.h_overflow[sl].copy_(c.kb.overflow, non_blocking=True)
+                    if slot.h_conv is not None:
+                        slot.h_conv[0][sl].copy_(c.pose_kpts, non_blocking=True)
+                        slot.h_conv[1][sl].copy_(c.bbox, non_blocking=True)
+                        slot.h_conv[2][sl].copy_(c.confidence, non_blocking=True)
 
             if self.graph:
                 def whole_pass():

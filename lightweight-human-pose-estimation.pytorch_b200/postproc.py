@@ -173,6 +173,33 @@ def group_keypoints_fused(kb, maps, ratio, channel_offset=19, demo=False, min_pa
     return pose_entries, n_poses
 
 
+def pose_convert(pose_entries, n_poses, kb, stride=8, upsample_ratio=4, pad=(0, 0, 0, 0), scale=1.0, out=None):
+    """Batched result post-conversion on the device (reference demo.py:101-115 + modules/pose.py:30-39).
+    pose_entries float64 [n, cap, 20] / n_poses int32 [n] as returned by group_keypoints_*; kb: the KeypointBatch.
+    pad = [top, left, bottom, right] and scale as returned by infer_fast -- one pair for the whole batch, or per-image
+    sequences.  Returns (pose_kpts int32 [n, cap, 18, 2], bbox int32 [n, cap, 4], confidence float64 [n, cap])."""
+    L = _lib.load()
+    n, cap = pose_entries.shape[0], pose_entries.shape[1]
+    dev = pose_entries.device
+    pads = np.asarray(pad, np.float64).reshape(-1, 4)
+    scales = np.asarray(scale, np.float64).reshape(-1)
+    xf = np.empty((n, 3), np.float64)
+    xf[:, 0] = pads[:, 1] if pads.shape[0] == n else pads[0, 1]
+    xf[:, 1] = pads[:, 0] if pads.shape[0] == n else pads[0, 0]
+    xf[:, 2] = scales if scales.shape[0] == n else scales[0]
+    xform = torch.from_numpy(xf).to(dev)
+    if out is None:
+        out = (torch.empty((n, cap, NUM_KPT_TYPES, 2), dtype=torch.int32, device=dev),
+               torch.empty((n, cap, 4), dtype=torch.int32, device=dev),
+               torch.empty((n, cap), dtype=torch.float64, device=dev))
+    pk, bb, conf = out
+    _lib.check(L.lwp_pose_convert(_ptr(pose_entries), _ptr(n_poses), cap, _ptr(kb.kpts), _ptr(kb.kpt_start), kb.cap_kpts, n,
+                                  float(stride), float(upsample_ratio), _ptr(xform), _ptr(pk), _ptr(bb), _ptr(conf),
+                                  _lib.current_stream()), "lwp_pose_convert")
+    kb._xform = xform  # keep alive until the stream has consumed it
+    return pk, bb, conf
+
+
 def raise_on_overflow(overflow_h):
     bad = np.nonzero(np.asarray(overflow_h))[0]
     if bad.size:

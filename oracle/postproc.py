@@ -107,3 +107,26 @@ def group_keypoints(all_keypoints_by_type, pafs, pose_entry_size=20, min_paf_sco
         raise RuntimeError("orc_group_keypoints overflow/alloc failure: %d" % n)
     pose_entries = np.asarray([out[i].copy() for i in range(n)])  # shape (0,) when empty, like the reference
     return pose_entries, all_keypoints
+
+
+def pose_convert(pose_entries, all_keypoints, stride, upsample_ratio, pad, scale):
+    """Plain-Python restatement of the reference's result post-conversion (demo.py:101-115) and of Pose.get_bbox
+    (modules/pose.py:30-39; cv2.boundingRect of integer points = min corner and max - min + 1 extents).
+    Returns (pose_keypoints int32 [P, 18, 2], bbox int32 [P, 4], confidence float64 [P]); all_keypoints is NOT modified."""
+    allk = np.array(all_keypoints, dtype=np.float64).reshape(-1, 4).copy()
+    for k in range(allk.shape[0]):
+        allk[k, 0] = (allk[k, 0] * stride / upsample_ratio - pad[1]) / scale
+        allk[k, 1] = (allk[k, 1] * stride / upsample_ratio - pad[0]) / scale
+    poses = np.asarray(pose_entries, np.float64).reshape(-1, 20)
+    kp = -np.ones((poses.shape[0], 18, 2), np.int32)
+    bbox = np.zeros((poses.shape[0], 4), np.int32)
+    for n in range(poses.shape[0]):
+        for k in range(18):
+            if poses[n, k] != -1.0:
+                kp[n, k, 0] = int(allk[int(poses[n, k]), 0])
+                kp[n, k, 1] = int(allk[int(poses[n, k]), 1])
+        found = kp[n][kp[n][:, 0] != -1]
+        if len(found):
+            x0, y0 = found[:, 0].min(), found[:, 1].min()
+            bbox[n] = (x0, y0, found[:, 0].max() - x0 + 1, found[:, 1].max() - y0 + 1)
+    return kp, bbox, poses[:, 18].copy()

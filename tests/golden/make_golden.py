@@ -114,6 +114,65 @@ def gen_postproc(out, ref):
             out[tag + "_allk"] = np.asarray(allk, np.float64).reshape(-1, 4) if len(allk) else np.zeros((0, 4))
 
 
+POSE_CASES = [("p3", (0, 3, 0, 5), 256 / 720), ("p8", (2, 0, 1, 0), 368 / 480), ("p15n", (0, 0, 0, 1), 0.3555555555555555)]
+
+
+def ref_poses(ref, pose_mod, case_name, pad, scale, stride=8, upsample=4):
+    """demo.py:100-115 through the real reference objects: returns (list of reference Pose, pose_entries, all_keypoints)."""
+    case = [c for c in POSTPROC_CASES if c[0] == case_name][0]
+    hm, paf = postproc_maps(case)
+    _, pose_entries, all_keypoints = run_reference_postproc(ref, hm.copy(), paf.copy(), True, upsample)
+    raw = np.array(all_keypoints, np.float64).copy()
+    for kpt_id in range(all_keypoints.shape[0]):   # the reference's own statements (demo.py:101-103)
+        all_keypoints[kpt_id, 0] = (all_keypoints[kpt_id, 0] * stride / upsample - pad[1]) / scale
+        all_keypoints[kpt_id, 1] = (all_keypoints[kpt_id, 1] * stride / upsample - pad[0]) / scale
+    poses = []
+    for n in range(len(pose_entries)):
+        pose_keypoints = np.ones((18, 2), dtype=np.int32) * -1
+        for kpt_id in range(18):
+            if pose_entries[n][kpt_id] != -1.0:
+                pose_keypoints[kpt_id, 0] = int(all_keypoints[int(pose_entries[n][kpt_id]), 0])
+                pose_keypoints[kpt_id, 1] = int(all_keypoints[int(pose_entries[n][kpt_id]), 1])
+        poses.append(pose_mod.Pose(pose_keypoints, pose_entries[n][18]))
+    return poses, np.asarray(pose_entries, np.float64).reshape(-1, 20), raw
+
+
+def gen_pose(out, ref):
+    import importlib
+    pose_mod = importlib.import_module("modules.pose")   # the reference's Pose / track_poses
+    for name, pad, scale in POSE_CASES:
+        poses, entries, raw = ref_poses(ref, pose_mod, name, pad, scale)
+        out["pose_%s_kpts" % name] = np.stack([p.keypoints for p in poses]).astype(np.int32)
+        out["pose_%s_bbox" % name] = np.asarray([p.bbox for p in poses], np.int32)
+        out["pose_%s_conf" % name] = np.asarray([p.confidence for p in poses], np.float64)
+    # tracking over three "frames": the same persons drifting by a few pixels, smooth on and off
+    for smooth in (False, True):
+        pose_mod.Pose.last_id = -1
+        prev = []
+        for f in range(3):
+            poses, _, _ = ref_poses(ref, pose_mod, "p8", (0, 0, 0, 0), 1.0)
+            rng = np.random.default_rng(50 + f)
+            for p in poses:
+                m = p.keypoints[:, 0] != -1
+                p.keypoints[m] += rng.integers(-3, 4, size=(int(m.sum()), 2)).astype(np.int32) + 2 * f
+                p.bbox = pose_mod.Pose.get_bbox(p.keypoints)
+            if f == 2:
+                poses = poses[::-1][:-2]   # two persons leave, order changes
+            out["track_s%d_f%d_in" % (smooth, f)] = np.stack([p.keypoints for p in poses]).astype(np.int32)
+            out["track_s%d_f%d_conf" % (smooth, f)] = np.asarray([p.confidence for p in poses], np.float64)
+            pose_mod.track_poses(prev, poses, smooth=smooth)
+            out["track_s%d_f%d_ids" % (smooth, f)] = np.asarray([p.id for p in poses], np.int64)
+            out["track_s%d_f%d_out" % (smooth, f)] = np.stack([p.keypoints for p in poses]).astype(np.int32)
+            out["track_s%d_f%d_bbox" % (smooth, f)] = np.asarray([p.bbox for p in poses], np.int32)
+            prev = poses
+    sim = [[pose_mod.get_similarity(a, b) for b in prev] for a in prev]
+    out["track_similarity"] = np.asarray(sim, np.int64)
+    # One-Euro filter trace
+    oef = importlib.import_module("modules.one_euro_filter")
+    f = oef.OneEuroFilter(freq=15, beta=0.1)
+    out["one_euro_trace"] = np.asarray([f(v + (-1) ** (v % 2)) for v in range(12)], np.float64)
+
+
 # (name, refinement stages, H, W, batch, head gain)
 NET_CASES = [("r1_64x96", 1, 64, 96, 1, 1.0), ("r2_48x72", 2, 48, 72, 2, 1.0), ("r1_gain", 1, 64, 64, 1, 4.0)]
 
@@ -147,7 +206,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, "postproc_golden.npz"), **p)
     gen_net(n, ref)
     np.savez_compressed(os.path.join(HERE, "net_golden.npz"), **n)
-    for f in ("resize_golden.npz", "postproc_golden.npz", "net_golden.npz"):
+    q = {}
+    gen_pose(q, ref)
+    np.savez_compressed(os.path.join(HERE, "pose_golden.npz"), **q)
+    for f in ("resize_golden.npz", "postproc_golden.npz", "net_golden.npz", "pose_golden.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 
 

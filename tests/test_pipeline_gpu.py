@@ -230,3 +230,34 @@ def test_uint8_frames_equal_normalised_float_input(env):
     assert np.array_equal(hf.view(np.int32), h8.view(np.int32))
     assert np.array_equal(rf.n_poses, r8.n_poses)
     assert p8.h2d_bytes * 4 == pf.h2d_bytes
+
+
+def test_pipeline_convert_gives_pose_objects(env):
+    """PosePipeline(convert=...): the result post-conversion of demo.py:101-115 runs on the device; PoseResult.poses(i)
+    returns Pose objects whose key-points / boxes / confidences equal the oracle's restatement on the same tables."""
+    torch, net = env
+    from lwpose_b200 import synth
+    from lwpose_b200.pipeline import PosePipeline
+    from oracle import postproc as orc
+    B, H, W = 3, 128, 192
+    hm, paf, _ = synth.synthetic_pose_maps(B, H // 8, W // 8, seed=41, max_persons=3)
+    inj = np.zeros((B, H // 8, W // 8, 64), np.float32)
+    inj[..., :19] = hm.transpose(0, 2, 3, 1)
+    inj[..., 19:57] = paf.transpose(0, 2, 3, 1)
+    inj_d = torch.from_numpy(inj).cuda()
+    pads = [[0, 3, 0, 5], [2, 0, 1, 0], [0, 0, 0, 1]]
+    scales = [256 / 720, 0.5, 1.25]
+    pipe = PosePipeline(net, B, H, W, precision="bf16", demo=True, chunk=2, convert=dict(pad=pads, scale=scales),
+                        heads_hook=lambda t, lo: t.add_(inj_d[lo:lo + t.shape[0]]))
+    res = pipe(synth.synthetic_net_input(B, H, W, seed=2).pin_memory()).check()
+    total = 0
+    for b in range(B):
+        poses, allk = res.frame(b)
+        kp, bbox, conf = orc.pose_convert(poses, allk, 8, 4, pads[b], scales[b])
+        objs = res.poses(b)
+        assert len(objs) == kp.shape[0]
+        for j, p in enumerate(objs):
+            assert np.array_equal(p.keypoints, kp[j]) and tuple(p.bbox) == tuple(int(v) for v in bbox[j])
+            assert p.confidence == conf[j]
+        total += len(objs)
+    assert total >= B

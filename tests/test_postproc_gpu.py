@@ -220,3 +220,30 @@ def test_fused_equals_materialised_on_noise(torch_cuda, shape, ratio):
     for b in range(n):
         k = int(a[4][b])
         assert np.array_equal(a[3][b, :k].view(np.int64), ph[b, :k].view(np.int64))
+
+
+def test_pose_convert_matches_reference_golden():
+    """lwp_pose_convert (demo.py:101-115 + Pose.get_bbox on the device) against fixtures made by the real reference, through
+    the batched device API and through PosePipeline(convert=...).poses()."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import golden_cases as gc
+    import lwpose_b200  # noqa: F401
+    from lwpose_b200 import postproc
+    g = gc.load("pose_golden.npz")
+    mg = gc._mg()
+    for name, pad, scale in mg.POSE_CASES:
+        case = [c for c in gc.postproc_cases() if c[0] == name][0]
+        hm, paf = gc.postproc_maps(case)
+        heads = torch.zeros((1, hm.shape[1], hm.shape[2], 64), dtype=torch.float32, device="cuda")
+        heads[0, :, :, :19] = torch.from_numpy(hm.transpose(1, 2, 0)).cuda()
+        heads[0, :, :, 19:57] = torch.from_numpy(paf.transpose(1, 2, 0)).cuda()
+        kb = postproc.extract_keypoints_fused(heads, 4)
+        poses_d, n_d = postproc.group_keypoints_fused(kb, heads, 4, demo=True)
+        pk, bb, conf = postproc.pose_convert(poses_d, n_d, kb, stride=8, upsample_ratio=4, pad=pad, scale=scale)
+        n = int(n_d[0])
+        assert n == g["pose_%s_kpts" % name].shape[0]
+        assert np.array_equal(pk[0, :n].cpu().numpy(), g["pose_%s_kpts" % name])
+        assert np.array_equal(bb[0, :n].cpu().numpy(), g["pose_%s_bbox" % name])
+        assert np.array_equal(conf[0, :n].cpu().numpy().view(np.int64), g["pose_%s_conf" % name].view(np.int64))
