@@ -145,6 +145,11 @@ int lwp_pose_convert(const double *pose_entries, const int32_t *n_poses, int cap
                      const int32_t *kpt_start, int cap_kpts, int n, double stride, double upsample_ratio,
                      const double *xform, int32_t *pose_kpts, int32_t *bbox, double *confidence, void *stream);
 
+/* dst[i] = src[i] (items of bytes_per_item bytes, multiple of 16) for every i < n with flags[i] != 0.  The batched
+ * pipeline uses it to keep the network output of exactly those frames whose fixed-capacity tables overflowed (flags = the
+ * overflow array of lwp_extract_keypoints* / lwp_group_keypoints*), so that they can be re-processed with larger tables. */
+int lwp_copy_flagged(const void *src, void *dst, const int32_t *flags, int n, size_t bytes_per_item, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Network forward: a "plan" is a recorded list of layer launches with pre-built TMA descriptors
  * for one (batch, height, width, dtype).  It replaces PoseEstimationWithMobileNet.forward

@@ -34,6 +34,7 @@ SIGNATURES = {
                                      _c_size_t, _c_void_p, _c_void_p]),
     "lwp_pose_convert": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_double, _c_double,
                                   _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "lwp_copy_flagged": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_size_t, _c_void_p]),
     "lwp_plan_create": (_c_int, [_c_int, ctypes.POINTER(_c_void_p)]),
     "lwp_plan_destroy": (None, [_c_void_p]),
     "lwp_plan_num_ops": (_c_int, [_c_void_p]),

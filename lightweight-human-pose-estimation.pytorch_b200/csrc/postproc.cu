@@ -1157,3 +1157,23 @@ extern "C" int lwp_pose_convert(const double *pose_entries, const int32_t *n_pos
   LWP_LAUNCH_CHECK();
   return LWP_OK;
 }
+
+// Copy item i of `src` to item i of `dst` only where flags[i] != 0 (16-byte granularity).  The pipeline keeps the heads of
+// frames whose fixed-capacity tables overflowed, so that exactly those frames can be re-processed with larger tables.
+__global__ void __launch_bounds__(256)
+copy_flagged_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, const int *__restrict__ flags, size_t vec_per_item) {
+  const int item = blockIdx.y;
+  if (flags[item] == 0) return;
+  const uint4 *s = src + (size_t)item * vec_per_item;
+  uint4 *d = dst + (size_t)item * vec_per_item;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vec_per_item; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+extern "C" int lwp_copy_flagged(const void *src, void *dst, const int32_t *flags, int n, size_t bytes_per_item, void *stream) {
+  LWP_REQUIRE(src && dst && flags && n > 0, "lwp_copy_flagged: bad arguments");
+  LWP_REQUIRE(bytes_per_item % 16 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0, "lwp_copy_flagged: 16-byte alignment");
+  dim3 grid(16, n);
+  copy_flagged_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4 *)src, (uint4 *)dst, flags, bytes_per_item / 16);
+  LWP_LAUNCH_CHECK();
+  return LWP_OK;
+}

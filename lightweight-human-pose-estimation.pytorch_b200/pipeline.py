@@ -37,21 +37,37 @@ class PoseResult:
         return [Pose(self.pose_kpts[i, j].copy(), self.confidence[i, j], bbox=self.bbox[i, j])
                 for j in range(int(self.n_poses[i]))]
 
+    retried = None   # {frame index: (pose_entries [1,cap',20], n_poses [1], kpts, counts, kpt_start)} of frames that
+                     # overflowed the pipeline's fixed-capacity tables and were re-processed with larger ones by collect()
+
     def check(self):
-        postproc.raise_on_overflow(self.overflow)
+        """Raises CapacityOverflow if some frame overflowed even the largest tables collect() retries with."""
+        bad = np.asarray(self.overflow).copy()
+        for i in (self.retried or {}):
+            bad[i] = 0
+        postproc.raise_on_overflow(bad)
         return self
 
+    def _tables(self, i):
+        if self.retried and i in self.retried:
+            pe, npz, kp, cnt, st = self.retried[i]
+            return pe, npz, kp, cnt, st, 0
+        return self.pose_entries, self.n_poses, self.kpts, self.counts, self.kpt_start, i
+
     def keypoints_by_type(self, i):
-        return postproc.keypoint_lists(self.kpts, self.counts, self.kpt_start, i)
+        _, _, kp, cnt, st, j = self._tables(i)
+        return postproc.keypoint_lists(kp, cnt, st, j)
 
     def frame(self, i):
         """(pose_entries, all_keypoints) of frame i with the reference's dtypes/shapes (modules/keypoints.py:201)."""
         by_type = self.keypoints_by_type(i)
         all_keypoints = np.array([item for sub in by_type for item in sub])
-        return postproc.pose_entries_array(self.pose_entries, self.n_poses, i), all_keypoints
+        pe, npz, _, _, _, j = self._tables(i)
+        return postproc.pose_entries_array(pe, npz, j), all_keypoints
 
     def total_poses(self):
-        return int(self.n_poses.sum())
+        extra = sum(int(t[1][0]) - int(self.n_poses[i]) for i, t in (self.retried or {}).items())
+        return int(self.n_poses.sum()) + extra
 
 
 class _Chunk:
@@ -169,6 +185,8 @@ class _Slot:
         if pipe.convert is not None:
             self.h_conv = (torch.empty((b, cp, 18, 2), dtype=torch.int32, **pin), torch.empty((b, cp, 4), dtype=torch.int32, **pin),
                            torch.empty((b, cp), dtype=torch.float64, **pin))
+        # heads of the frames whose tables overflowed (copied only for those: lwp_copy_flagged), for the retry in collect()
+        self.heads_keep = torch.empty((b, pipe.h, pipe.w, HEAD_LD), dtype=torch.float32, device=pipe.device)
         self.copied = torch.cuda.Event()   # H2D of this slot's input finished
         self.consumed = torch.cuda.Event() # the network has finished reading x_dev
         self.done = torch.cuda.Event()     # compute + D2H of this slot finished
@@ -334,6 +352,10 @@ class PosePipeline:
                     slot.h_counts[sl].copy_(c.kb.counts, non_blocking=True)
                     slot.h_kpt_start[sl].copy_(c.kb.kpt_start, non_blocking=True)
                     slot.h_overflow[sl].copy_(c.kb.overflow, non_blocking=True)
+                    src = c.heads_pp if (self.overlap_postproc and not self.graph) else c.heads
+                    _lib.check(self.L.lwp_copy_flagged(src.data_ptr(), slot.heads_keep[sl].data_ptr(), c.kb.overflow.data_ptr(),
+                                                       c.n, self.h * self.w * HEAD_LD * 4, _lib.current_stream()),
+                               "lwp_copy_flagged")
                     if slot.h_conv is not None:
                         slot.h_conv[0][sl].copy_(c.pose_kpts, non_blocking=True)
                         slot.h_conv[1][sl].copy_(c.bbox, non_blocking=True)
@@ -368,7 +390,36 @@ class PosePipeline:
             raise RuntimeError("nothing submitted")
         slot = self._pending.pop(0)
         slot.done.synchronize()
-        return slot.result()
+        res = slot.result()
+        bad = np.nonzero(res.overflow)[0]
+        if bad.size:
+            res.retried = {int(i): self._retry_frame(slot, int(i)) for i in bad}
+            res.retried = {i: t for i, t in res.retried.items() if t is not None}
+        return res
+
+    def _retry_frame(self, slot, i):
+        """One frame exceeded cap_kpts / cap_candidates / cap_connections / cap_poses: re-run its post-processing alone on
+        the kept heads with tables 4x, 16x ... larger (the 63 other frames of the batch keep their results).  Returns host
+        tables, or None if even the largest tables overflow (check() then raises)."""
+        ck, cc, cp, cn = self.caps
+        heads = slot.heads_keep[i:i + 1]
+        with torch.cuda.device(self.device):
+            for _ in range(3):
+                ck, cc, cp, cn = ck * 4, cc * 4, cp * 4, min(cn * 4, 1 << 15)
+                if self.fused:
+                    kb = postproc.extract_keypoints_fused(heads, self.ratio, cap_kpts=ck, cap_candidates=cc)
+                    pe, npz = postproc.group_keypoints_fused(kb, heads, self.ratio, demo=self.demo, min_paf_score=self.min_paf_score,
+                                                             cap_poses=cp, cap_connections=cn)
+                else:
+                    heat = postproc.upsample_cubic(heads, channels=19, fx=self.ratio, fy=self.ratio, channel_offset=0)
+                    paf = postproc.upsample_cubic(heads, channels=38, fx=self.ratio, fy=self.ratio, channel_offset=19)
+                    kb = postproc.extract_keypoints_batched(heat, cap_kpts=ck, cap_candidates=cc)
+                    pe, npz = postproc.group_keypoints_batched(kb, paf, demo=self.demo, min_paf_score=self.min_paf_score,
+                                                               cap_poses=cp, cap_connections=cn)
+                kp, cnt, st, ovf = kb.to_host()
+                if not ovf[0]:
+                    return pe.cpu().numpy(), npz.cpu().numpy(), kp, cnt, st
+        return None
 
     def __call__(self, frames):
         """End to end, synchronous: frames -> PoseResult on the host."""

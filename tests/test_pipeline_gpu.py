@@ -261,3 +261,35 @@ def test_pipeline_convert_gives_pose_objects(env):
             assert p.confidence == conf[j]
         total += len(objs)
     assert total >= B
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_one_crowded_frame_is_retried_not_fatal(env, overlap):
+    """One frame exceeds the pipeline's fixed table capacities: only that frame is re-processed (larger tables) by
+    collect(); every frame's result -- the crowded one included -- is bit-exact against the oracle, nothing raises."""
+    torch, net = env
+    import golden_cases as gc
+    from lwpose_b200 import synth
+    from lwpose_b200.pipeline import PosePipeline
+    B, H, W = 3, 368, 656
+    maps = [synth.synthetic_pose_maps(1, H // 8, W // 8, seed=60 + b, persons=p) for b, p in enumerate((1, 12, 2))]
+    inj = np.zeros((B, H // 8, W // 8, 64), np.float32)
+    for b, (hm, paf, _) in enumerate(maps):
+        inj[b, :, :, :19] = hm[0].transpose(1, 2, 0)
+        inj[b, :, :, 19:57] = paf[0].transpose(1, 2, 0)
+    inj_d = torch.from_numpy(inj).cuda()
+    pipe = PosePipeline(net, B, H, W, precision="bf16", demo=True, cap_kpts=8, cap_poses=8, overlap_postproc=overlap,
+                        heads_hook=lambda t, lo: t.add_(inj_d[lo:lo + t.shape[0]]))
+    x = synth.synthetic_net_input(B, H, W, seed=2).pin_memory()
+    res = pipe(x)
+    assert res.overflow.tolist() == [0, 1, 0] and list(res.retried) == [1]
+    res.check()
+    heads = pipe.heads.cpu().numpy()
+    for b in range(B):
+        by_type, (ref_poses, ref_allk) = _oracle_post(heads[b], True)
+        assert gc.pack_keypoints(res.keypoints_by_type(b)).tolist() == gc.pack_keypoints(by_type).tolist()
+        poses, _ = res.frame(b)
+        rp = np.asarray(ref_poses, np.float64).reshape(-1, 20)
+        gp = np.asarray(poses, np.float64).reshape(-1, 20)
+        assert rp.shape == gp.shape and np.array_equal(rp.view(np.int64), gp.view(np.int64))
+    assert len(res.frame(1)[0]) >= 12
