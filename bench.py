@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--steady-seconds", type=float, default=2.0, help="length of the extra steady-state run (0 = skip)")
     ap.add_argument("--no-configs", action="store_true", help="skip the config0 / config3 / config4 extra keys")
     ap.add_argument("--config3-batch", type=int, default=256, help="GLOBAL batch of configs[3] (strong scaling over the ranks)")
+    ap.add_argument("--config4-frames", type=int, default=64, help="GLOBAL number of 480x640 frames of configs[4] per step (sharded over the ranks)")
     return ap.parse_args()
 
 
@@ -423,6 +424,7 @@ def extra_configs(args, net, dev, rank, world, barrier):
     """The other configurations BASELINE.json names, as extra keys of the same JSON line (the headline stays configs[1])."""
     out = {}
     out["config3"] = config3(args, dev, rank, world, barrier)
+    out["config4"] = config4(args, net, dev, rank, world, barrier)
     if rank == 0:
         out["config0_latency"] = config0_latency(args, net, dev)
     return out
@@ -477,6 +479,98 @@ def config3(args, dev, rank, world, barrier):
             raise RuntimeError("config3 net_parity FAILED: %g" % err)
     del pipe
     return res
+
+
+def config4(args, net, dev, rank, world, barrier):
+    """configs[4]: val.py-style multi-scale inference (scales 0.5 / 1 / 1.5 / 2 x 368: net inputs 368x368, 368x496, 552x736,
+    736x984 for a 480x640 frame), maps resized x8, cropped, resized to the frame size and averaged, 18 x extract +
+    group(demo=False) at 480x640, convert_to_coco_format -- end to end from pinned uint8 frames to COCO lists on the host,
+    frames sharded over the ranks (each frame's four scales stay on one GPU)."""
+    import numpy as np
+    import torch
+    from lwpose_b200 import parallel, postproc, synth, val
+    Hf, Wf, chunk = 480, 640, 8
+    scales = [0.5, 1.0, 1.5, 2.0]
+    lo, hi = parallel.shard_range(args.config4_frames, rank, world)
+    per = hi - lo
+    frames = torch.from_numpy(synth.synthetic_frames(max(per, 1), Hf, Wf, seed=300 + rank)).pin_memory()
+    # synthetic persons at the frame resolution: stride-8 maps (1..10 persons) up-sampled x8 once, added to the averaged maps
+    hm, paf, persons = synth.synthetic_pose_maps(chunk, Hf // 8, Wf // 8, seed=400 + rank, max_persons=10)
+    m = np.zeros((chunk, Hf // 8, Wf // 8, 64), np.float32)
+    m[..., :19] = hm.transpose(0, 2, 3, 1)
+    m[..., 19:57] = paf.transpose(0, 2, 3, 1)
+    md = torch.from_numpy(m).to(dev)
+    inj_h = postproc.upsample_cubic(md, channels=19, fx=8, fy=8, channel_offset=0)
+    inj_p = postproc.upsample_cubic(md, channels=38, fx=8, fy=8, channel_offset=19)
+    net.precision = args.precision
+
+    def hook(avg_h, avg_p):
+        avg_h.add_(inj_h[:avg_h.shape[0]])
+        avg_p.add_(inj_p[:avg_p.shape[0]])
+
+    def one_pass():
+        n = 0
+        for c0 in range(0, per, chunk):
+            res = val.evaluate_batch(net, frames[c0:c0 + chunk], scales=scales, base_height=368, maps_hook=hook)
+            n += sum(len(r[0]) for r in res)
+        return n
+    one_pass()
+    torch.cuda.synchronize()
+    barrier()
+    steps = 2
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        n_poses = one_pass()
+    torch.cuda.synchronize()
+    dt = parallel.max_over_ranks((time.perf_counter() - t0) / steps, device=dev)
+    barrier()
+    res = {"workload": "configs[4]: %d frames 480x640 uint8 (global, %d per GPU), scales %s x 368, R=1 network, averaged maps + 1..10 "
+                       "synthetic persons, extract / group(demo=False) at 480x640, COCO conversion; host frames in, host lists out"
+                       % (args.config4_frames, per, scales),
+           "value": args.config4_frames / dt, "unit": "frames/s", "ms_per_step": dt * 1000.0, "steps": steps, "scaling": "strong",
+           "dtype": args.precision, "coco_poses_rank0": n_poses, "timing": "wall clock around the public call, device synchronised"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res["cpu_port"] = config4_cpu(net, frames[0].numpy(), scales, hm[0], paf[0])
+    return res
+
+
+def config4_cpu(net, frame, scales, hm8, paf8):
+    """Oracle port of reference val.py:81-110,129-136 on ONE frame (host cv2 float64 input resize, torch CPU fp32 network at the
+    four sizes, OpenCV-exact output resizes, averaging, extract / group(demo=False), COCO conversion)."""
+    import cv2
+    import numpy as np
+    import torch
+    from lwpose_b200 import val
+    from oracle import net as onet
+    from oracle import postproc as orc
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    inj_h = orc.resize_cubic(np.ascontiguousarray(hm8.transpose(1, 2, 0)), fx=8, fy=8)
+    inj_p = orc.resize_cubic(np.ascontiguousarray(paf8.transpose(1, 2, 0)), fx=8, fy=8)
+    t0 = time.perf_counter()
+    height, width = frame.shape[:2]
+    normed = val.normalize(frame, (128, 128, 128), 1 / 256)
+    avg_h = np.zeros((height, width, 19), np.float32)
+    avg_p = np.zeros((height, width, 38), np.float32)
+    for s in scales:
+        ratio = s * 368 / float(height)
+        scaled = cv2.resize(normed, (0, 0), fx=ratio, fy=ratio, interpolation=cv2.INTER_CUBIC)
+        padded, pad = val.pad_width(scaled, 8, (0, 0, 0), [368, max(scaled.shape[1], 368)])
+        outs = onet.forward(sd, torch.from_numpy(padded).permute(2, 0, 1).unsqueeze(0).float())
+        for o, avg in ((outs[-2], avg_h), (outs[-1], avg_p)):
+            mm = orc.resize_cubic(np.ascontiguousarray(o[0].numpy().transpose(1, 2, 0)), fx=8, fy=8)
+            mm = mm[pad[0]:mm.shape[0] - pad[2], pad[1]:mm.shape[1] - pad[3], :]
+            avg += orc.resize_cubic(np.ascontiguousarray(mm), dsize=(width, height)) / len(scales)
+    avg_h += inj_h
+    avg_p += inj_p
+    total, by_type = 0, []
+    for k in range(18):
+        total += orc.extract_keypoints(avg_h[:, :, k], by_type, total)
+    poses, allk = orc.group_keypoints(by_type, avg_p, demo=False)
+    coco, _ = val.convert_to_coco_format(poses, allk)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "frames/s", "seconds_per_frame": dt, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "1 frame, 4 scales", "coco_poses": len(coco)}
 
 
 def config0_latency(args, net, dev):

@@ -167,6 +167,14 @@ def gen_pose(out, ref):
             prev = poses
     sim = [[pose_mod.get_similarity(a, b) for b in prev] for a in prev]
     out["track_similarity"] = np.asarray(sim, np.int64)
+    # convert_to_coco_format (val.py:52-78) on the val-mode (demo=False) tables of two cases
+    for name in ("p8", "p15n"):
+        case = [c for c in POSTPROC_CASES if c[0] == name][0]
+        hm, paf = postproc_maps(case)
+        _, pose_entries, all_keypoints = run_reference_postproc(ref, hm.copy(), paf.copy(), False)
+        coco, scores = ref.val.convert_to_coco_format(pose_entries, all_keypoints)
+        out["coco_%s_kpts" % name] = np.asarray(coco, np.float64)
+        out["coco_%s_scores" % name] = np.asarray(scores, np.float64)
     # One-Euro filter trace
     oef = importlib.import_module("modules.one_euro_filter")
     f = oef.OneEuroFilter(freq=15, beta=0.1)

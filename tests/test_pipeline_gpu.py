@@ -293,3 +293,55 @@ def test_one_crowded_frame_is_retried_not_fatal(env, overlap):
         gp = np.asarray(poses, np.float64).reshape(-1, 20)
         assert rp.shape == gp.shape and np.array_equal(rp.view(np.int64), gp.view(np.int64))
     assert len(res.frame(1)[0]) >= 12
+
+
+def test_val_infer_batch_matches_oracle(env):
+    """val.infer_batch (configs[4]: batched multi-scale inference entirely on the device) against the oracle restatement of
+    val.py:81-110 (host cv2 float64 input resize, CPU fp32 network, OpenCV-exact output resizes) frame by frame, and
+    evaluate_batch's COCO conversion against the oracle post-processing of the device's own averaged maps."""
+    torch, net = env
+    import cv2
+    import golden_cases as gc
+    from lwpose_b200 import postproc, val
+    from oracle import net as onet
+    from oracle import postproc as orc
+    net.precision = "tf32"
+    frames = np.random.default_rng(5).integers(0, 256, (2, 96, 128, 3), dtype=np.uint8)
+    scales, base = [0.5, 1.0, 1.5], 64
+    got_h, got_p = val.infer_batch(net, frames, scales, base, 8)
+    assert tuple(got_h.shape) == (2, 96, 128, 19) and tuple(got_p.shape) == (2, 96, 128, 38)
+    for b in range(2):
+        normed = val.normalize(frames[b], (128, 128, 128), 1 / 256)
+        avg_h = np.zeros((96, 128, 19), np.float32)
+        avg_p = np.zeros((96, 128, 38), np.float32)
+        for s in scales:
+            ratio = s * base / 96.0
+            scaled = cv2.resize(normed, (0, 0), fx=ratio, fy=ratio, interpolation=cv2.INTER_CUBIC)
+            padded, pad = val.pad_width(scaled, 8, (0, 0, 0), [base, max(scaled.shape[1], base)])
+            x = torch.from_numpy(padded).permute(2, 0, 1).unsqueeze(0).float()
+            outs = onet.forward(net.state_dict(), x)
+            for o, avg in ((outs[-2], avg_h), (outs[-1], avg_p)):
+                m = orc.resize_cubic(np.ascontiguousarray(o[0].numpy().transpose(1, 2, 0)), fx=8, fy=8)
+                m = m[pad[0]:m.shape[0] - pad[2], pad[1]:m.shape[1] - pad[3], :]
+                avg += orc.resize_cubic(np.ascontiguousarray(m), dsize=(128, 96)) / len(scales)
+        assert np.abs(got_h[b].cpu().numpy() - avg_h).max() < 1e-3 and np.abs(got_p[b].cpu().numpy() - avg_p).max() < 1e-3
+    # end-to-end body of val.evaluate on the device vs the oracle post-processing of the same averaged maps
+    hm, paf, _ = __import__("lwpose_b200").synth.synthetic_pose_maps(2, 96, 128, seed=3, persons=2)
+    ah = torch.from_numpy(np.ascontiguousarray(hm.transpose(0, 2, 3, 1))).cuda()
+    ap = torch.from_numpy(np.ascontiguousarray(paf.transpose(0, 2, 3, 1))).cuda()
+    kb = postproc.extract_keypoints_batched(ah)
+    poses_d, n_d = postproc.group_keypoints_batched(kb, ap, demo=False)
+    kp, cnt, st, _ = kb.to_host()
+    for b in range(2):
+        by_type = postproc.keypoint_lists(kp, cnt, st, b)
+        allk = np.array([item for sub in by_type for item in sub])
+        got = val.convert_to_coco_format(postproc.pose_entries_array(poses_d.cpu().numpy(), n_d.cpu().numpy(), b), allk)
+        total, ref_by = 0, []
+        heat = ah[b].cpu().numpy().copy()
+        for k in range(18):
+            total += orc.extract_keypoints(heat[:, :, k], ref_by, total)
+        rp, ra = orc.group_keypoints(ref_by, ap[b].cpu().numpy(), demo=False)
+        want = val.convert_to_coco_format(rp, ra)
+        assert len(got[0]) == len(want[0]) >= 2 and got[0] == want[0] and [float(v) for v in got[1]] == [float(v) for v in want[1]]
+    res = val.evaluate_batch(net, frames, scales=[1.0], base_height=base)
+    assert len(res) == 2 and all(len(r) == 2 for r in res)

@@ -65,3 +65,24 @@ def test_pose_class_surface():
     assert p.id == 5 and pose.Pose.last_id == 5
     p.update_id(2)
     assert p.id == 2
+
+
+def test_convert_to_coco_format_matches_reference_golden():
+    import lwpose_b200  # noqa: F401
+    from lwpose_b200 import val
+    g = gc.load("pose_golden.npz")
+    pp = gc.load("postproc_golden.npz")
+    for name in ("p8", "p15n"):
+        coco, scores = val.convert_to_coco_format(pp["pp_%s_val_poses" % name], pp["pp_%s_val_allk" % name])
+        assert np.array_equal(np.asarray(coco, np.float64), g["coco_%s_kpts" % name])
+        assert np.array_equal(np.asarray(scores, np.float64).view(np.int64), g["coco_%s_scores" % name].view(np.int64))
+    assert val.convert_to_coco_format(np.asarray([]), np.asarray([])) == ([], [])
+
+
+def test_val_scale_geometry():
+    """Net input sizes and pads of val.infer's four scales for a 480x640 frame."""
+    import lwpose_b200  # noqa: F401
+    from lwpose_b200 import val
+    geo = val.scale_geometry(480, 640, [0.5, 1.0, 1.5, 2.0], 368, 8)
+    assert [g[2] for g in geo] == [(368, 368), (368, 496), (552, 736), (736, 984)]
+    assert [g[3] for g in geo] == [[92, 61, 92, 62], [0, 2, 0, 3], [0, 0, 0, 0], [0, 1, 0, 2]]
