@@ -253,6 +253,35 @@ int lwp_plan_num_launches(const lwp_plan *p);
  * out inside a tcgen05 GEMM kernel (the kernels never spin forever). */
 int lwp_plan_error_flag(lwp_plan *p);
 
+/* ---------------------------------------------------------------------------------------------
+ * The whole path in three calls, for hosts that are not Python.  lwp_net_load rebuilds a runnable network from a
+ * self-contained blob (written once from a reference state_dict by the Python mirror: Plan.export_blob(); BatchNorm
+ * already folded, weights already packed for the tcgen05 kernels, the layer list with every argument) -- it replaces
+ * PoseEstimationWithMobileNet(...) + load_state(net, checkpoint) + net.cuda() (models/with_mobilenet.py:89-112,
+ * modules/load_state.py:4-15) for one (dtype, batch, height, width); lwp_net_forward replaces forward (:114-123);
+ * lwp_postprocess replaces the cubic up-sampling + 18 x extract_keypoints + group_keypoints of demo.py:72-100.
+ * The library owns the network's device memory (allocated in lwp_net_load, freed in lwp_net_destroy).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lwp_net lwp_net;
+int lwp_net_load(const void *blob_host, size_t bytes, lwp_net **out);
+void lwp_net_destroy(lwp_net *net);
+int lwp_net_info(const lwp_net *net, int *dtype, int *n, int *H, int *W, int *n_stages);
+/* x: NCHW float32 [n][3][H][W] (or uint8 [n][H][W][3] for a blob exported with the uint8 stem), device memory.
+ * with_nchw != 0 also fills the NCHW float32 tensors `forward` returns (lwp_net_output_nchw). */
+int lwp_net_forward(lwp_net *net, const void *x, int with_nchw, void *stream);
+/* float32 heads of stage `stage` (-1 = last): [n * H/8 * W/8] pixels x *ld floats, 19 heat-maps + 38 PAFs + zero pad */
+int lwp_net_heads(const lwp_net *net, int stage, const float **heads, int *ld);
+/* index-th entry of the list `forward` returns: [hm_0, paf_0, ..., hm_R, paf_R], NCHW float32 */
+int lwp_net_output_nchw(const lwp_net *net, int index, const float **out);
+
+size_t lwp_postprocess_workspace_bytes(int n, int cap_kpts, int cap_candidates, int cap_connections, int cap_poses);
+/* heads: [n][h][w] pixels x ld floats (19 heat-map + 38 PAF channels first), e.g. lwp_net_heads(net, -1, ...).
+ * Outputs as for lwp_extract_keypoints_fused + lwp_group_keypoints_fused (up-sampled size = h, w times upsample_ratio). */
+int lwp_postprocess(const float *heads, int n, int h, int w, int ld, int upsample_ratio, int demo, double min_paf_score,
+                    lwp_keypoint *kpts, int32_t *counts, int32_t *kpt_start, int cap_kpts, int cap_candidates,
+                    double *pose_entries, int32_t *n_poses, int cap_poses, int cap_connections, void *workspace,
+                    size_t workspace_bytes, int32_t *overflow, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

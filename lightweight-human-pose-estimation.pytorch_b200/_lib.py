@@ -35,6 +35,16 @@ SIGNATURES = {
     "lwp_pose_convert": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_double, _c_double,
                                   _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "lwp_copy_flagged": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_size_t, _c_void_p]),
+    "lwp_net_load": (_c_int, [_c_void_p, _c_size_t, ctypes.POINTER(_c_void_p)]),
+    "lwp_net_destroy": (None, [_c_void_p]),
+    "lwp_net_info": (_c_int, [_c_void_p] + [ctypes.POINTER(_c_int)] * 5),
+    "lwp_net_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p]),
+    "lwp_net_heads": (_c_int, [_c_void_p, _c_int, ctypes.POINTER(_c_void_p), ctypes.POINTER(_c_int)]),
+    "lwp_net_output_nchw": (_c_int, [_c_void_p, _c_int, ctypes.POINTER(_c_void_p)]),
+    "lwp_postprocess_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int, _c_int]),
+    "lwp_postprocess": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_double, _c_void_p, _c_void_p,
+                                 _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_size_t,
+                                 _c_void_p, _c_void_p]),
     "lwp_plan_create": (_c_int, [_c_int, ctypes.POINTER(_c_void_p)]),
     "lwp_plan_destroy": (None, [_c_void_p]),
     "lwp_plan_num_ops": (_c_int, [_c_void_p]),

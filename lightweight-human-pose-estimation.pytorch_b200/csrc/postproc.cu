@@ -1177,3 +1177,29 @@ extern "C" int lwp_copy_flagged(const void *src, void *dst, const int32_t *flags
   LWP_LAUNCH_CHECK();
   return LWP_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// One call for the whole post-processing of a batch (demo.py:72-100 / val.py:129-134 without the maps ever being
+// materialised): lwp_extract_keypoints_fused followed by lwp_group_keypoints_fused on one workspace.
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t lwp_postprocess_workspace_bytes(int n, int cap_kpts, int cap_candidates, int cap_connections, int cap_poses) {
+  return align_up(lwp_extract_workspace_bytes(n, LWP_NUM_KPT_TYPES, cap_candidates), 256) +
+         lwp_group_workspace_bytes(n, cap_kpts, cap_connections, cap_poses);
+}
+
+extern "C" int lwp_postprocess(const float *heads, int n, int h, int w, int ld, int upsample_ratio, int demo, double min_paf_score,
+                               lwp_keypoint *kpts, int32_t *counts, int32_t *kpt_start, int cap_kpts, int cap_candidates,
+                               double *pose_entries, int32_t *n_poses, int cap_poses, int cap_connections, void *workspace,
+                               size_t workspace_bytes, int32_t *overflow, void *stream) {
+  LWP_REQUIRE(heads && workspace && ld >= 57 && upsample_ratio >= 3, "lwp_postprocess: bad arguments (needs the 19 + 38 head channels and a ratio >= 3)");
+  LWP_REQUIRE(workspace_bytes >= lwp_postprocess_workspace_bytes(n, cap_kpts, cap_candidates, cap_connections, cap_poses),
+              "lwp_postprocess: workspace too small");
+  const size_t ews = align_up(lwp_extract_workspace_bytes(n, LWP_NUM_KPT_TYPES, cap_candidates), 256);
+  const int H = h * upsample_ratio, W = w * upsample_ratio;
+  int rc = lwp_extract_keypoints_fused(heads, n, h, w, ld, LWP_NUM_KPT_TYPES, 19, H, W, (double)upsample_ratio, (double)upsample_ratio,
+                                       kpts, counts, kpt_start, cap_kpts, cap_candidates, workspace, ews, overflow, stream);
+  if (rc != LWP_OK) return rc;
+  return lwp_group_keypoints_fused(kpts, counts, kpt_start, cap_kpts, heads + 19, n, h, w, ld, H, W, (double)upsample_ratio,
+                                   (double)upsample_ratio, demo, min_paf_score, pose_entries, n_poses, cap_poses, cap_connections,
+                                   (char *)workspace + ews, workspace_bytes - ews, overflow, stream);
+}

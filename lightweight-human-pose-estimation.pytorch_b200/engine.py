@@ -153,13 +153,55 @@ class _Packed:
             self.refine.append((blks, _merge_heads(st.heatmaps, st.pafs, tdtype)))
 
 
+class _RecordingLib:
+    """Proxy of the ctypes library that remembers every successful lwp_plan_add_* call (name + arguments after the
+    plan handle): Plan.export_blob() serialises that list, so a non-Python host can rebuild the same plan with
+    lwp_net_load() without re-implementing this file's layer walk."""
+
+    def __init__(self, lib, log):
+        self._lib, self._log = lib, log
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith("lwp_plan_add_"):
+            return fn
+
+        def call(handle, *args):
+            rc = fn(handle, *args)
+            if rc == 0:
+                self._log.append((name, args))
+            return rc
+        return call
+
+
+# function ids of the blob format (csrc/net_blob.cu must agree)
+_BLOB_FUNCS = {"lwp_plan_add_stem": 0, "lwp_plan_add_stem_u8": 1, "lwp_plan_add_depthwise": 2, "lwp_plan_add_conv_gemm": 3,
+               "lwp_plan_add_dwpw": 4, "lwp_plan_add_sepconv": 5, "lwp_plan_add_heads_fused": 6, "lwp_plan_add_nhwc_to_nchw": 7}
+
+
+def _all_tensors(obj, out, seen):
+    """Every torch tensor reachable from the packed-weights object tree."""
+    if id(obj) in seen:
+        return
+    seen.add(id(obj))
+    if isinstance(obj, torch.Tensor):
+        out.append(obj)
+    elif isinstance(obj, (list, tuple)):
+        for o in obj:
+            _all_tensors(o, out, seen)
+    elif hasattr(obj, "__dict__"):
+        for o in vars(obj).values():
+            _all_tensors(o, out, seen)
+
+
 class Plan:
     """One recorded launch list + its buffers for a fixed (precision, N, H, W)."""
 
     def __init__(self, packed, precision, n, H, W, n_stages_out, num_heatmaps, num_pafs, device, input_u8=None):
         if H % 8 or W % 8:
             raise ValueError("input height/width must be multiples of 8 (got %dx%d)" % (H, W))
-        self.lib = _lib.load()
+        self.call_log = []
+        self.lib = _RecordingLib(_lib.load(), self.call_log)
         self.n, self.H, self.W = n, H, W
         self.h, self.w = H // 8, W // 8
         self.precision = precision
@@ -187,6 +229,7 @@ class Plan:
         self.use_sepconv = sep not in ("", "0")
         self.sepconv_only = None if sep in ("", "0", "1", "all") else set(sep.split(","))
         self.bufs = []
+        self.buf_zero = []
         self.op_names = []
         self.op_meta = []  # per op: kind, algorithmic flops and bytes (real channel counts, no padding)
         self._build(packed, n_stages_out, num_heatmaps, num_pafs)
@@ -203,6 +246,7 @@ class Plan:
     def _buf(self, *shape, dtype=None, zero=False):
         t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype or self.tdtype, device=self.device)
         self.bufs.append(t)
+        self.buf_zero.append(bool(zero))
         return t
 
     def _gemm(self, name, src, src_ld, g, n, H, W, out=None, out_ld=0, out_ptr_off=0, residual=None, res_ld=0,
@@ -421,6 +465,58 @@ class Plan:
                 self.op_names.append("to_nchw.%d" % s)
                 self.op_meta.append(dict(kind="layout", flops=0.0, bytes=float(2 * n * cc * h * w * 4)))
             self.outputs += [hm, paf]
+
+    # -- export -------------------------------------------------------------------------------
+    def export_blob(self):
+        """Serialise this plan -- the op list with every argument, the pre-folded / pre-packed constants (data) and the
+        activation buffers (sizes only) -- into the self-contained blob lwp_net_load() (include/lwpose_b200.h) rebuilds
+        a runnable network from, without Python.  Format: csrc/net_blob.cu."""
+        import ctypes
+        import struct
+        torch.cuda.synchronize(self.device)
+        consts = []
+        _all_tensors(self.packed, consts, set())
+        consts = [t for t in consts if t.is_cuda]
+        tensors = [(t, 1 if z else 0) for t, z in zip(self.bufs, self.buf_zero)] + [(t, 2) for t in consts]
+        spans = sorted((t.data_ptr(), t.data_ptr() + t.numel() * t.element_size(), i) for i, (t, _) in enumerate(tensors)
+                       if t.numel() > 0)
+
+        def resolve(ptr):
+            for lo, hi, i in spans:
+                if lo <= ptr < hi:
+                    return i, ptr - lo
+            raise _lib.LwpError("export_blob: a plan argument points outside every known tensor")
+
+        out = [struct.pack("<4sI", b"LWPB", 1),
+               struct.pack("<7i", _PREC[self.precision][0], self.n, self.H, self.W, len(tensors), len(self.call_log),
+                           self.num_compute_ops)]
+        for t, kind in tensors:
+            nbytes = t.numel() * t.element_size()
+            out.append(struct.pack("<Qi", nbytes, kind))
+            if kind == 2:
+                raw = t.detach().contiguous().view(torch.uint8).cpu().numpy().tobytes()
+                out.append(raw + b"\0" * (-len(raw) % 16))
+        for name, args in self.call_log:
+            argtypes = _lib.SIGNATURES[name][1][1:]
+            out.append(struct.pack("<2i", _BLOB_FUNCS[name], len(args)))
+            for a, ty in zip(args, argtypes):
+                if ty is ctypes.c_void_p:
+                    if a is None:
+                        out.append(struct.pack("<i", 3))
+                    else:
+                        tid, off = resolve(int(a))
+                        out.append(struct.pack("<iiQ", 2, tid, off))
+                elif ty is ctypes.c_double:
+                    out.append(struct.pack("<id", 1, float(a)))
+                elif ty is ctypes.c_int:
+                    out.append(struct.pack("<iq", 0, int(a)))
+                else:   # POINTER(c_double): the three channel means of the uint8 stem
+                    out.append(struct.pack("<i3d", 4, *[float(a[i]) for i in range(3)]))
+        heads = [resolve(t.data_ptr())[0] for t in self.heads_f32]
+        nchw = [resolve(t.data_ptr())[0] for t in self.outputs]
+        out.append(struct.pack("<2i", len(heads), len(nchw)))
+        out.append(struct.pack("<%di" % (len(heads) + len(nchw)), *(heads + nchw)))
+        return b"".join(out)
 
     # -- execution ----------------------------------------------------------------------------
     def run(self, x, first=0, last=None):

@@ -180,3 +180,15 @@ def test_debug_switches_are_refused(monkeypatch):
         _lib.refuse_debug_env()
     monkeypatch.setenv("LWP_DEBUG_GEMM", "0")
     _lib.refuse_debug_env()
+
+
+def test_net_load_rejects_garbage_without_a_gpu():
+    """lwp_net_load checks the blob header before it touches CUDA."""
+    import ctypes
+    import lwpose_b200  # noqa: F401
+    from lwpose_b200 import _lib
+    L = _lib.load()
+    h = _lib._c_void_p()
+    buf = ctypes.create_string_buffer(b"not a blob at all.." * 4)
+    assert L.lwp_net_load(ctypes.cast(buf, ctypes.c_void_p), 64, h) == 1   # LWP_EINVAL
+    assert b"LWPB" in L.lwp_last_error()

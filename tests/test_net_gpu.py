@@ -461,3 +461,50 @@ def test_sepconv_network(env, monkeypatch):
     for i, y in enumerate(outs):
         ref = torch.from_numpy(g["net_%s_out%d" % (name, i)])
         assert _rel(y.cpu(), ref) < NET_TOL["bf16"] * gain, i
+
+
+@pytest.mark.parametrize("precision,R", [("bf16", 1), ("tf32", 2)])
+def test_c_entry_points_run_the_network_without_the_python_engine(env, precision, R, tmp_path):
+    """lwp_net_load / lwp_net_forward / lwp_net_heads (the three-call C API): a blob exported once from the module
+    gives, through ctypes only, bit-identical heads and NCHW outputs to the Python engine; lwp_postprocess on those
+    heads gives the same tables as the two-call form; the on-disk cache is keyed by the checkpoint hash."""
+    torch, _lib, engine = env
+    from lwpose_b200 import cnet, postproc, synth
+    B, H, W = 2, 64, 96
+    net = _build_net(torch, "c", R, 4.0).cuda()
+    net.precision = precision
+    x = synth.synthetic_net_input(B, H, W, seed=9).cuda()
+    want = [o.clone() for o in net(x)]
+    want_heads = net.engine().plan(precision, B, H, W).heads_f32[-1].view(B, H // 8, W // 8, 64).clone()
+    path = cnet.cached_blob(net, precision, B, H, W, cache_dir=str(tmp_path))
+    assert cnet.cached_blob(net, precision, B, H, W, cache_dir=str(tmp_path)) == path and len(list(tmp_path.iterdir())) == 1
+    c = cnet.CNet(path)
+    assert (c.n, c.H, c.W, c.n_stages) == (B, H, W, 1 + R)
+    c.forward(x, with_nchw=True)
+    torch.cuda.synchronize()
+    assert torch.equal(c.heads(), want_heads)
+    for i, w_ in enumerate(want):
+        assert torch.equal(c.output_nchw(i, w_.shape[1]), w_)
+    # one-call post-processing on the C network's heads == extract_fused + group_fused
+    heads = c.heads().contiguous()
+    kb = postproc.extract_keypoints_fused(heads, 4)
+    pe, npz = postproc.group_keypoints_fused(kb, heads, 4, demo=True)
+    L = _lib.load()
+    ck, cc, cp, cn = 128, 2048, 128, 2048
+    kb2 = postproc.KeypointBatch(B, 18, ck, heads.device)
+    pe2 = torch.empty((B, cp, 20), dtype=torch.float64, device="cuda")
+    n2 = torch.empty((B,), dtype=torch.int32, device="cuda")
+    ws = torch.empty((L.lwp_postprocess_workspace_bytes(B, ck, cc, cn, cp),), dtype=torch.uint8, device="cuda")
+    _lib.check(L.lwp_postprocess(heads.data_ptr(), B, H // 8, W // 8, 64, 4, 1, 0.05, kb2.kpts.data_ptr(), kb2.counts.data_ptr(),
+                                 kb2.kpt_start.data_ptr(), ck, cc, pe2.data_ptr(), n2.data_ptr(), cp, cn, ws.data_ptr(), ws.numel(),
+                                 kb2.overflow.data_ptr(), _lib.current_stream()), "lwp_postprocess")
+    torch.cuda.synchronize()
+    assert torch.equal(n2, npz) and torch.equal(kb2.counts, kb.counts)
+    for b in range(B):
+        k = int(npz[b])
+        assert torch.equal(pe2[b, :k], pe[b, :k])
+    c.close()
+    # a truncated blob is refused, not crashed on
+    blob = open(path, "rb").read()
+    with pytest.raises(_lib.LwpError):
+        cnet.CNet(blob[:len(blob) // 2])
