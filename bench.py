@@ -352,6 +352,39 @@ def main():
                   "h2d_bytes_per_step": pipe8.h2d_bytes, "d2h_bytes_per_step": pipe8.d2h_bytes,
                   "input": "uint8 BGR frames [n,368,656,3], normalisation fused into the stem"}
         del pipe8
+    # the same streaming run from RAW camera frames (720x1280 uint8, what demo.py:91-93 hands to infer_fast): cubic resize + pad
+    # on the GPU (row f1), result post-conversion to per-pose key-points / boxes on the GPU too (row f3)
+    e2e_raw = None
+    if not args.no_u8:
+        from lwpose_b200 import postproc as _pp
+        rscale, _, rpadded, rpad = _pp.infer_fast_geometry(720, 1280, HEIGHT)
+        assert tuple(rpadded) == (HEIGHT, WIDTH), rpadded
+        pipe_r = PosePipeline(net, args.batch, HEIGHT, WIDTH, precision=args.precision, demo=True,
+                              heads_hook=lambda heads, lo: heads.add_(inject[lo:lo + heads.shape[0]]),
+                              fused=not args.unfused_postproc, chunk=args.chunk or None,
+                              overlap_postproc=not args.no_overlap_postproc, input_format="u8_raw", raw_size=(720, 1280),
+                              convert=dict(pad=rpad, scale=rscale))
+        xr = torch.from_numpy(synth.synthetic_frames(args.batch, 720, 1280, seed=1 + rank)).pin_memory()
+        for _ in range(2):
+            pipe_r(xr)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        pipe_r.submit(xr)
+        for _ in range(args.steps - 1):
+            pipe_r.submit(xr)
+            pipe_r.collect()
+        rres = pipe_r.collect().check()
+        r1.record()
+        r1.synchronize()
+        barrier()
+        raw_ms = parallel.max_over_ranks(r0.elapsed_time(r1) / args.steps, device=dev)
+        e2e_raw = {"value": world * args.batch / (raw_ms / 1000.0), "unit": "frames/s", "ms_per_step": raw_ms,
+                   "h2d_bytes_per_step": pipe_r.h2d_bytes, "d2h_bytes_per_step": pipe_r.d2h_bytes,
+                   "input": "raw uint8 BGR camera frames [n,720,1280,3] (pinned); cubic resize to 368x655 + pad to 368x656 + normalisation "
+                            "on the GPU; output: pose tables + per-pose key-points / boxes in frame coordinates",
+                   "pose_objects_frame0": len(rres.poses(0))}
+        del pipe_r, xr
     # the other arithmetic of BASELINE.json configs[1] ("fp32 and bf16"): the same device-resident measurement on the
     # other precision's plan (fp32 storage + TF32 tensor-core products when the headline is bf16, and vice versa)
     other = None
@@ -398,6 +431,7 @@ def main():
         # step, which is PCIe time comparable to the whole step) is reported next to it.
         "e2e": dict(e2e_u8, mode="PosePipeline.submit/collect, 2 batches in flight") if e2e_u8 is not None else e2e_f32,
         "e2e_f32": e2e_f32,
+        "e2e_raw_frames": e2e_raw,
         "steady_state": steady,
         "other_precision": other,
         "gpu_launches": pipe.launches_per_step * args.steps,

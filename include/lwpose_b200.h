@@ -52,6 +52,22 @@ int lwp_timing_experiments(void);
 int lwp_check_device(int dev);
 
 /* ---------------------------------------------------------------------------------------------
+ * Frame preparation
+ * ------------------------------------------------------------------------------------------- */
+
+/*
+ * Replaces cv2.resize(img, (0, 0), fx=scale, fy=scale, INTER_CUBIC) on the uint8 BGR camera frame (demo.py:59) and the
+ * centred pad of val.pad_width (demo.py:61-62, val.py:36-49) for n frames at once.  Bit-exact with OpenCV's generic
+ * uint8 cubic path (fixed-point coefficients; builds that route this call through IPP differ by +-1 in ~5 % of pixels).
+ * src: [n][h][w][3] uint8; dst: [n][Hp][Wp][3] uint8: the resized H x W frame at rows [top, top + H), columns
+ * [left, left + W), the pad value everywhere else (use the mean, 128: the stem's normalisation turns it into the 0 the
+ * reference pads the normalised image with).  inv_scale_* is OpenCV's inv_scale: fx (fy) when the caller gives factors
+ * (then W = round(w * fx)), (double)W / w when the caller gives dsize.  dst feeds lwp_plan_add_stem_u8 plans directly.
+ */
+int lwp_resize_pad_u8(const uint8_t *src, int n, int h, int w, uint8_t *dst, int Hp, int Wp, int H, int W, int top, int left,
+                      double inv_scale_x, double inv_scale_y, int pad_b, int pad_g, int pad_r, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Post-processing
  * ------------------------------------------------------------------------------------------- */
 

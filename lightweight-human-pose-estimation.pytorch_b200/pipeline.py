@@ -174,6 +174,9 @@ class _Slot:
             self.x_dev = torch.empty((b, 3, pipe.H, pipe.W), dtype=torch.float32, device=pipe.device)
         else:
             self.x_dev = torch.empty((b, pipe.H, pipe.W, 3), dtype=torch.uint8, device=pipe.device)
+        self.raw_dev = None
+        if pipe.raw is not None:
+            self.raw_dev = torch.empty((b,) + pipe.raw["size"] + (3,), dtype=torch.uint8, device=pipe.device)
         pin = dict(pin_memory=True)
         self.h_pose_entries = torch.empty((b, cp, postproc.POSE_ENTRY), dtype=torch.float64, **pin)
         self.h_n_poses = torch.empty((b,), dtype=torch.int32, **pin)
@@ -209,7 +212,7 @@ class PosePipeline:
     def __init__(self, net, batch, height, width, precision="bf16", upsample_ratio=4, demo=True,
                  min_paf_score=0.05, cap_kpts=128, cap_candidates=2048, cap_poses=256, cap_connections=2048,
                  heads_hook=None, fused=True, chunk=None, depth=2, overlap_postproc=True, input_format="f32_nchw",
-                 img_mean=(128, 128, 128), img_scale=1 / 256, graph=False, convert=None):
+                 img_mean=(128, 128, 128), img_scale=1 / 256, graph=False, convert=None, raw_size=None):
         _lib.require_cuda()
         self.net, self.precision = net, precision
         self.n, self.H, self.W = batch, height, width
@@ -234,9 +237,23 @@ class PosePipeline:
         self._graphs = {}
         # "f32_nchw": normalised float32 [n,3,H,W] like the reference's tensor_img; "u8_nhwc": raw BGR frames uint8
         # [n,H,W,3] already at the network size -- (img - mean) * scale (val.normalize) is fused into the stem kernel
-        if input_format not in ("f32_nchw", "u8_nhwc"):
-            raise ValueError("input_format must be 'f32_nchw' or 'u8_nhwc'")
-        self.input_u8 = (tuple(img_mean), float(img_scale)) if input_format == "u8_nhwc" else None
+        # "u8_raw": camera frames uint8 [n, h, w, 3] at their own size raw_size=(h, w): the cubic resize to the network height
+        # and the centred pad of infer_fast (demo.py:57-62) run on the GPU too (lwp_resize_pad_u8), then as "u8_nhwc"
+        if input_format not in ("f32_nchw", "u8_nhwc", "u8_raw"):
+            raise ValueError("input_format must be 'f32_nchw', 'u8_nhwc' or 'u8_raw'")
+        self.input_u8 = (tuple(img_mean), float(img_scale)) if input_format in ("u8_nhwc", "u8_raw") else None
+        self.raw = None
+        if input_format == "u8_raw":
+            if raw_size is None:
+                raise ValueError("input_format='u8_raw' needs raw_size=(frame height, frame width)")
+            scale, (rh, rw), padded, pad = postproc.infer_fast_geometry(raw_size[0], raw_size[1], height)
+            if tuple(padded) != (height, width):
+                raise ValueError("a %dx%d frame resized to height %d pads to %dx%d, not to the pipeline's %dx%d"
+                                 % (raw_size[0], raw_size[1], height, padded[0], padded[1], height, width))
+            # pad with the mean: the stem normalises it to exactly 0, the reference's pad value in the normalised image
+            self.raw = dict(size=(int(raw_size[0]), int(raw_size[1])), scale=scale, resized=(rh, rw), pad=pad,
+                            pad_value=tuple(int(round(float(m))) for m in img_mean))
+
         self._engine = net.engine()      # the packed weights this pipeline's plans were recorded with
         self.device = self._engine.device
         self.h, self.w = height // 8, width // 8
@@ -257,6 +274,8 @@ class PosePipeline:
         self._next, self._pending = 0, []
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0].tables())
         self.h2d_bytes = batch * 3 * height * width * (4 if self.input_u8 is None else 1)
+        if self.raw is not None:
+            self.h2d_bytes = batch * 3 * self.raw["size"][0] * self.raw["size"][1]
 
     @property
     def heads(self):
@@ -332,7 +351,19 @@ class PosePipeline:
         slot = self.slots[self._next]
         self._next = (self._next + 1) % len(self.slots)
         with torch.cuda.device(self.device):
-            if frames.is_cuda:
+            if self.raw is not None:
+                # camera frames: H2D of the raw frames (or none, if they are on the device), then resize + pad on the GPU
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(slot.consumed)
+                    if frames.is_cuda:
+                        self.copy_stream.wait_stream(torch.cuda.current_stream())
+                    slot.raw_dev.copy_(frames, non_blocking=True)
+                    r = self.raw
+                    postproc.resize_pad_u8(slot.raw_dev, fx=r["scale"], fy=r["scale"], padded=(self.H, self.W), top=r["pad"][0],
+                                           left=r["pad"][1], pad_value=r["pad_value"], out=slot.x_dev)
+                    slot.copied.record(self.copy_stream)
+                x = slot.x_dev
+            elif frames.is_cuda:
                 x = frames
                 slot.copied.record(torch.cuda.current_stream())
             else:

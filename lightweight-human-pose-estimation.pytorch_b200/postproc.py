@@ -47,6 +47,44 @@ def upsample_cubic(src, channels=None, fx=None, fy=None, dsize=None, out=None, c
     return out
 
 
+def resize_pad_u8(frames, fx=None, fy=None, dsize=None, padded=None, top=0, left=0, pad_value=(128, 128, 128), out=None):
+    """Frame preparation on the device (reference demo.py:59,61-62): uint8 cuda [n, h, w, 3] -> cubic resize (factors fx/fy
+    like cv2.resize(img, (0, 0), fx=, fy=) or dsize=(W, H)) placed at (top, left) of a padded=(Hp, Wp) frame filled with
+    pad_value.  Returns uint8 [n, Hp, Wp, 3] -- what a stem built with input_format='u8_nhwc' consumes."""
+    L = _lib.load()
+    assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3 and frames.is_contiguous()
+    n, h, w, _ = frames.shape
+    if dsize is None:
+        inv_x, inv_y = float(fx), float(fy)
+        W, H = int(np.rint(w * inv_x)), int(np.rint(h * inv_y))
+    else:
+        W, H = int(dsize[0]), int(dsize[1])
+        inv_x, inv_y = W / w, H / h
+    Hp, Wp = (H, W) if padded is None else (int(padded[0]), int(padded[1]))
+    if out is None:
+        out = torch.empty((n, Hp, Wp, 3), dtype=torch.uint8, device=frames.device)
+    else:
+        assert tuple(out.shape) == (n, Hp, Wp, 3) and out.dtype == torch.uint8 and out.is_contiguous()
+    _lib.check(L.lwp_resize_pad_u8(_ptr(frames), n, h, w, _ptr(out), Hp, Wp, H, W, int(top), int(left), inv_x, inv_y,
+                                   int(pad_value[0]), int(pad_value[1]), int(pad_value[2]), _lib.current_stream()),
+               "lwp_resize_pad_u8")
+    return out
+
+
+def infer_fast_geometry(height, width, net_input_height_size, stride=8):
+    """Bookkeeping of demo.infer_fast (demo.py:57-62) without touching pixels: (scale, resized (H, W), padded (Hp, Wp),
+    pad [top, left, bottom, right])."""
+    import math
+    scale = net_input_height_size / height
+    H, W = int(np.rint(height * scale)), int(np.rint(width * scale))
+    hmin = math.ceil(net_input_height_size / float(stride)) * stride
+    Wp = math.ceil(max(W, net_input_height_size) / float(stride)) * stride
+    hh = min(net_input_height_size, H)
+    top, left = int(math.floor((hmin - hh) / 2.0)), int(math.floor((Wp - W) / 2.0))
+    bottom = int(hmin - hh - top)
+    return scale, (H, W), (H + top + bottom, int(Wp)), [top, left, bottom, int(Wp - W - left)]
+
+
 class KeypointBatch:
     """Device-side result of extract_keypoints_batched."""
 

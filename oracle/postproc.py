@@ -32,6 +32,9 @@ def lib():
         L.orc_group_keypoints.restype = ctypes.c_int
         L.orc_group_keypoints.argtypes = [ip, ip, ip, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_double, dp, ctypes.c_int]
+        L.orc_resize_pad_u8.restype = ctypes.c_int
+        L.orc_resize_pad_u8.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 6 + [
+            ctypes.c_double, ctypes.c_double, ip]
         _lib = L
     return _lib
 
@@ -130,3 +133,24 @@ def pose_convert(pose_entries, all_keypoints, stride, upsample_ratio, pad, scale
             x0, y0 = found[:, 0].min(), found[:, 1].min()
             bbox[n] = (x0, y0, found[:, 0].max() - x0 + 1, found[:, 1].max() - y0 + 1)
     return kp, bbox, poses[:, 18].copy()
+
+
+def resize_pad_u8(img, fx=None, fy=None, dsize=None, padded=None, top=0, left=0, pad_value=(128, 128, 128)):
+    """uint8 [h, w, 3] cubic resize with the bits of OpenCV's generic fixed-point path (cv2.resize(img, (0, 0), fx=, fy=,
+    INTER_CUBIC) of demo.py:59 with IPP off), optionally placed at (top, left) of a padded=(Hp, Wp) frame filled with
+    pad_value (val.py:36-49)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w, _ = img.shape
+    if dsize is None:
+        inv_x, inv_y = float(fx), float(fy)
+        W, H = int(np.rint(w * inv_x)), int(np.rint(h * inv_y))
+    else:
+        W, H = int(dsize[0]), int(dsize[1])
+        inv_x, inv_y = W / w, H / h
+    Hp, Wp = (H, W) if padded is None else padded
+    dst = np.empty((Hp, Wp, 3), np.uint8)
+    pad3 = np.asarray(pad_value, np.int32)
+    rc = lib().orc_resize_pad_u8(img.ctypes.data, h, w, dst.ctypes.data, Hp, Wp, H, W, int(top), int(left), inv_x, inv_y, _ip(pad3))
+    if rc != 0:
+        raise MemoryError("orc_resize_pad_u8")
+    return dst

@@ -114,6 +114,48 @@ def gen_postproc(out, ref):
             out[tag + "_allk"] = np.asarray(allk, np.float64).reshape(-1, 4) if len(allk) else np.zeros((0, 4))
 
 
+# uint8 frame resize (demo.py:59): (h, w, scale numerator, denominator) ; scale = num / den as infer_fast computes it
+U8_CASES = [(720, 1280, 256, 720), (480, 640, 368, 480), (180, 320, 256, 180), (375, 500, 368, 375), (97, 131, 194, 97)]
+
+
+def gen_u8(out):
+    """cv2's GENERIC uint8 cubic path: IPP is switched off for these calls (IPP-enabled builds differ by +-1 in ~5 % of
+    the pixels; that arithmetic is not published and is not what the oracle / the GPU kernel restate)."""
+    import cv2
+    was = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        for i, (h, w, num, den) in enumerate(U8_CASES):
+            img = np.random.default_rng(2000 + i).integers(0, 256, (h, w, 3), dtype=np.uint8)
+            img[::7, ::5] = 255
+            img[3::7, 2::5] = 0
+            scale = num / den
+            dst = cv2.resize(img, (0, 0), fx=scale, fy=scale, interpolation=cv2.INTER_CUBIC)
+            out["u8_%d_sha" % i] = np.array(sha(dst))
+            out["u8_%d_shape" % i] = np.array(dst.shape)
+            if dst.size <= 120000:
+                out["u8_%d_out" % i] = dst
+        cv2.ipp.setUseIPP(True)
+        img = np.random.default_rng(2000).integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+        img[::7, ::5] = 255
+        img[3::7, 2::5] = 0
+        d_ipp = cv2.resize(img, (0, 0), fx=256 / 720, fy=256 / 720, interpolation=cv2.INTER_CUBIC)
+        cv2.ipp.setUseIPP(False)
+        d_gen = cv2.resize(img, (0, 0), fx=256 / 720, fy=256 / 720, interpolation=cv2.INTER_CUBIC)
+        diff = np.abs(d_ipp.astype(np.int32) - d_gen.astype(np.int32))
+        out["u8_ipp_vs_generic"] = np.array([int(diff.max()), int((diff != 0).sum()), diff.size])
+    finally:
+        cv2.ipp.setUseIPP(was)
+
+
+def u8_input(i):
+    h, w, _, _ = U8_CASES[i]
+    img = np.random.default_rng(2000 + i).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    img[::7, ::5] = 255
+    img[3::7, 2::5] = 0
+    return img
+
+
 POSE_CASES = [("p3", (0, 3, 0, 5), 256 / 720), ("p8", (2, 0, 1, 0), 368 / 480), ("p15n", (0, 0, 0, 1), 0.3555555555555555)]
 
 
@@ -217,6 +259,9 @@ def main():
     q = {}
     gen_pose(q, ref)
     np.savez_compressed(os.path.join(HERE, "pose_golden.npz"), **q)
+    u = {}
+    gen_u8(u)
+    np.savez_compressed(os.path.join(HERE, "u8_golden.npz"), **u)
     for f in ("resize_golden.npz", "postproc_golden.npz", "net_golden.npz", "pose_golden.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

@@ -126,3 +126,21 @@ def test_net_oracle_matches_reference_golden(case):
     for i, y in enumerate(outs):
         ref = torch.from_numpy(g["net_%s_out%d" % (name, i)])
         assert float((y - ref).abs().max()) < 2e-6 * gain, i
+
+
+def test_oracle_u8_resize_matches_cv2_generic_path_golden():
+    """orc_resize_pad_u8 (OpenCV's generic fixed-point uint8 cubic path: demo.py:59) against cv2 outputs taken with IPP off;
+    the fixtures also record how far an IPP-enabled cv2 is from that path (+-1 on ~5 % of the pixels)."""
+    import golden_cases as gc
+    from oracle import postproc as orc
+    g = gc.load("u8_golden.npz")
+    mg = gc._mg()
+    for i, (h, w, num, den) in enumerate(mg.U8_CASES):
+        r = orc.resize_pad_u8(mg.u8_input(i), fx=num / den, fy=num / den)
+        assert tuple(r.shape) == tuple(g["u8_%d_shape" % i]) and gc.sha(r) == str(g["u8_%d_sha" % i])
+    assert int(g["u8_ipp_vs_generic"][0]) == 1
+    # pad placement (val.py:36-49): the resized frame sits at (top, left), the rest is the pad value
+    img = mg.u8_input(4)
+    r = orc.resize_pad_u8(img, fx=2.0, fy=2.0)
+    p = orc.resize_pad_u8(img, fx=2.0, fy=2.0, padded=(200, 272), top=3, left=5, pad_value=(128, 127, 126))
+    assert np.array_equal(p[3:3 + 194, 5:5 + 262], r) and tuple(p[0, 0]) == (128, 127, 126) and tuple(p[199, 271]) == (128, 127, 126)

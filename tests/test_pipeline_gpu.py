@@ -345,3 +345,39 @@ def test_val_infer_batch_matches_oracle(env):
         assert len(got[0]) == len(want[0]) >= 2 and got[0] == want[0] and [float(v) for v in got[1]] == [float(v) for v in want[1]]
     res = val.evaluate_batch(net, frames, scales=[1.0], base_height=base)
     assert len(res) == 2 and all(len(r) == 2 for r in res)
+
+
+def test_raw_camera_frames_pipeline(env):
+    """input_format='u8_raw' (row f1): 180x320 camera frames are resized (cubic, OpenCV generic-path bits) and padded on the GPU;
+    heads and pose tables are bit-identical to feeding the pipeline the frames prepared by the oracle on the host."""
+    torch, net = env
+    from lwpose_b200 import postproc, synth
+    from lwpose_b200.pipeline import PosePipeline
+    from oracle import postproc as orc
+    B, h, w, hn = 2, 180, 320, 128
+    scale, (H, W), (Hp, Wp), pad = postproc.infer_fast_geometry(h, w, hn)
+    raw = synth.synthetic_frames(B, h, w, seed=8)
+    host = np.stack([orc.resize_pad_u8(f, fx=scale, fy=scale, padded=(Hp, Wp), top=pad[0], left=pad[1]) for f in raw])
+    p_raw = PosePipeline(net, B, Hp, Wp, precision="bf16", input_format="u8_raw", raw_size=(h, w))
+    p_u8 = PosePipeline(net, B, Hp, Wp, precision="bf16", input_format="u8_nhwc")
+    r1 = p_raw(torch.from_numpy(raw).pin_memory()).check()
+    h1 = p_raw.heads.cpu().numpy()
+    r2 = p_u8(torch.from_numpy(host).pin_memory()).check()
+    h2 = p_u8.heads.cpu().numpy()
+    assert np.array_equal(h1.view(np.int32), h2.view(np.int32)) and np.array_equal(r1.n_poses, r2.n_poses)
+    assert p_raw.h2d_bytes == B * h * w * 3
+    with pytest.raises(ValueError):
+        PosePipeline(net, B, Hp, Wp + 8, precision="bf16", input_format="u8_raw", raw_size=(h, w))
+
+
+def test_infer_fast_gpu_preprocess(env):
+    """infer_fast(gpu_preprocess=True): same return signature; the maps equal those of the host path within the network
+    tolerance (the host cv2 may be an IPP build: +-1 LSB on a few per cent of the input pixels)."""
+    torch, net = env
+    from lwpose_b200 import demo
+    net.precision = "tf32"
+    img = np.random.default_rng(0).integers(0, 256, (180, 320, 3), dtype=np.uint8)
+    h0, p0, s0, pad0 = demo.infer_fast(net, img, 128, 8, 4, False)
+    h1, p1, s1, pad1 = demo.infer_fast(net, img, 128, 8, 4, False, gpu_preprocess=True)
+    assert h0.shape == h1.shape and p0.shape == p1.shape and s0 == s1 and list(pad0) == list(pad1)
+    assert np.abs(h0 - h1).max() < 1e-3 and np.abs(p0 - p1).max() < 1e-3

@@ -247,3 +247,30 @@ def test_pose_convert_matches_reference_golden():
         assert np.array_equal(pk[0, :n].cpu().numpy(), g["pose_%s_kpts" % name])
         assert np.array_equal(bb[0, :n].cpu().numpy(), g["pose_%s_bbox" % name])
         assert np.array_equal(conf[0, :n].cpu().numpy().view(np.int64), g["pose_%s_conf" % name].view(np.int64))
+
+
+def test_resize_pad_u8_bit_exact_vs_cv2_generic_golden():
+    """lwp_resize_pad_u8 (row f1: the camera frame's cubic resize + centred pad on the GPU) against cv2 golden hashes (generic
+    path) on 720x1280 -> 256x455 (+ pad to 256x456) and 480x640 -> 368x491 (+ pad to 368x496), and against the oracle with pad."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import golden_cases as gc
+    import lwpose_b200  # noqa: F401
+    from lwpose_b200 import postproc
+    from oracle import postproc as orc
+    g = gc.load("u8_golden.npz")
+    mg = gc._mg()
+    for i, (h, w, num, den) in enumerate(mg.U8_CASES):
+        img = mg.u8_input(i)
+        d = torch.from_numpy(np.stack([img, img[::-1].copy()])).cuda()
+        out = postproc.resize_pad_u8(d, fx=num / den, fy=num / den).cpu().numpy()
+        assert gc.sha(out[0]) == str(g["u8_%d_sha" % i]), i
+        assert np.array_equal(out[1], orc.resize_pad_u8(img[::-1].copy(), fx=num / den, fy=num / den))
+    for (h, w, hn) in ((720, 1280, 256), (480, 640, 368)):
+        scale, (H, W), (Hp, Wp), pad = postproc.infer_fast_geometry(h, w, hn)
+        assert (Hp, Wp) == ((256, 456) if hn == 256 else (368, 496))
+        img = np.random.default_rng(h).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        got = postproc.resize_pad_u8(torch.from_numpy(img[None]).cuda(), fx=scale, fy=scale, padded=(Hp, Wp), top=pad[0], left=pad[1])
+        want = orc.resize_pad_u8(img, fx=scale, fy=scale, padded=(Hp, Wp), top=pad[0], left=pad[1])
+        assert np.array_equal(got[0].cpu().numpy(), want)
