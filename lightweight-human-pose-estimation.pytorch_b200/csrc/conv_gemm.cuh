@@ -72,7 +72,8 @@ int conv_gemm_init();
 int heads_fused_launch(const CUtensorMap &tmX, const CUtensorMap &tmW1, const CUtensorMap &tmW2, int n_px, int c_in,
                        int c_mid, const float *scale1, const float *shift1, const float *scale2, const float *shift2,
                        float *out_f32, int out_f32_ld, void *out_bf16, int out_ld, int *err_flag, cudaStream_t st);
-size_t heads_fused_smem_bytes(int k1_blocks, int chunks);
+size_t heads_fused_smem_bytes(int c_in, int c_mid);
+int heads_fused_chunk_cols(int c_mid);   // rows of one W1 TMA box
 size_t conv_gemm3_smem_bytes(const GemmParams &p);
 int conv_gemm3_init();
 int conv_gemm3_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,

@@ -645,7 +645,7 @@ extern "C" int lwp_plan_add_heads_fused(lwp_plan *p, const void *in, int in_ld, 
   LWP_REQUIRE(out_f32_ld >= 64 && out_f32_ld % 4 == 0 && (uintptr_t)out_f32 % 16 == 0, "lwp_plan_add_heads_fused: bad out_f32");
   LWP_REQUIRE(!out || (out_ld >= 64 && out_ld % 8 == 0 && (uintptr_t)out % 16 == 0), "lwp_plan_add_heads_fused: bad out");
   LWP_REQUIRE(((uintptr_t)in % 16) == 0 && ((uintptr_t)w1 % 16) == 0 && ((uintptr_t)w2 % 16) == 0, "lwp_plan_add_heads_fused: unaligned pointer");
-  if (heads_fused_smem_bytes(c_in / 64, c_mid / 64) > 232448) { set_error("lwp_plan_add_heads_fused: tiles do not fit in shared memory"); return LWP_ECAP; }
+  if (heads_fused_smem_bytes(c_in, c_mid) > 232448) { set_error("lwp_plan_add_heads_fused: tiles do not fit in shared memory"); return LWP_ECAP; }
   Op op;
   op.kind = OP_HEADS;
   op.hd_px = n_pixels; op.hd_cin = c_in; op.hd_cmid = c_mid; op.hd_out_ld = out_ld; op.hd_f32_ld = out_f32_ld;
@@ -665,7 +665,7 @@ extern "C" int lwp_plan_add_heads_fused(lwp_plan *p, const void *in, int in_ld, 
   {
     cuuint64_t dims[2] = {(cuuint64_t)c_in, (cuuint64_t)c_mid};
     cuuint64_t strides[1] = {(cuuint64_t)c_in * 2};
-    cuuint32_t box[2] = {64, 64};
+    cuuint32_t box[2] = {64, (cuuint32_t)heads_fused_chunk_cols(c_mid)};
     CUresult r = enc(&op.tmB, dt, 2, const_cast<void *>(w1), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(heads W1) failed: %d", (int)r); return LWP_ECUDA; }
