@@ -197,6 +197,21 @@ int lwp_plan_add_stem_u8(lwp_plan *p, const float *w, const float *scale, const 
                          int W, const double *img_mean3, double img_scale);
 
 /*
+ * The full-resolution front end of the backbone as one kernel (bf16 plans): model[0] conv(3, 32, stride=2), model[1]
+ * conv_dw(32, 64) and the depthwise half of model[2] conv_dw(64, 128, stride=2) of models/with_mobilenet.py:92-95
+ * (Conv2d + BatchNorm2d + ReLU each, modules/conv.py:4-22); with input_u8 also val.normalize (val.py:30-33) of the raw
+ * uint8 [n][H][W][3] frame, as lwp_plan_add_stem_u8.  The 32- and 64-channel maps at H/2 x W/2 never reach HBM; the
+ * result is bit-identical to the four separate ops.  stem_w: [32][27] float32 (OIHW flattened); dw*_w: [9][C] float32
+ * tap-major (C = 32, 64); pw_w: [64][32] in the plan dtype, K-major; *_scale / *_shift: folded BN, float32.
+ * out: NHWC [n][H/4][W/4][64] of the plan dtype (the input of model[2]'s 1x1 conv).  H, W multiples of 4.
+ */
+int lwp_plan_add_frontend(lwp_plan *p, const float *stem_w, const float *stem_scale, const float *stem_shift,
+                          const float *dw1_w, const float *dw1_scale, const float *dw1_shift, const void *pw_w,
+                          const float *pw_scale, const float *pw_shift, const float *dw2_w, const float *dw2_scale,
+                          const float *dw2_shift, void *out, int n, int H, int W, int input_u8, const double *img_mean3,
+                          double img_scale);
+
+/*
  * Depthwise 3x3 conv (groups == channels, bias=False) + per-channel scale/shift + activation
  * (modules/conv.py:15-17 conv_dw, :27-28 conv_dw_no_bn).  NHWC in / NHWC out, plan dtype.
  * w: [9][C] float32, tap-major (tap = ky*3 + kx; the host mirror transposes the state_dict's [C][1][3][3]);

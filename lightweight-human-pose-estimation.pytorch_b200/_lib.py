@@ -53,6 +53,8 @@ SIGNATURES = {
     "lwp_plan_add_stem": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
     "lwp_plan_add_stem_u8": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
                                       ctypes.POINTER(_c_double), _c_double]),
+    "lwp_plan_add_frontend": (_c_int, [_c_void_p] + [_c_void_p] * 13 + [_c_int, _c_int, _c_int, _c_int, ctypes.POINTER(_c_double),
+                                                              _c_double]),
     "lwp_plan_add_depthwise": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
                                         _c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
     "lwp_plan_add_heads_fused": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p,

@@ -139,6 +139,9 @@ extern "C" int lwp_net_load(const void *blob, size_t bytes, lwp_net **out) {
                                       I(13), I(14)); break;
       case 7: if (na != 9) { rc = LWP_EINVAL; break; }
         rc = lwp_plan_add_nhwc_to_nchw(pl, P(0), I(1), I(2), I(3), I(4), (float *)P(5), I(6), I(7), I(8)); break;
+      case 8: if (na != 19) { rc = LWP_EINVAL; break; }
+        rc = lwp_plan_add_frontend(pl, FP(0), FP(1), FP(2), FP(3), FP(4), FP(5), P(6), FP(7), FP(8), FP(9), FP(10), FP(11), P(12),
+                                   I(13), I(14), I(15), I(16), a[17].d3, a[18].d); break;
       default: rc = LWP_EINVAL;
     }
 #undef P

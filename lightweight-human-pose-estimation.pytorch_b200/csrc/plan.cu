@@ -6,6 +6,7 @@
 #include "conv_direct.cuh"
 #include "conv_gemm.cuh"
 #include "dwpw_gemm.cuh"
+#include "frontend_fused.cuh"
 #include "sepconv_gemm.cuh"
 #include "tcgen05.cuh"
 
@@ -43,7 +44,7 @@ static int gemm_smem_cap() {
   return cap;
 }
 
-enum OpKind { OP_STEM, OP_DW, OP_GEMM, OP_NCHW, OP_DWPW, OP_HEADS, OP_SEP };
+enum OpKind { OP_STEM, OP_DW, OP_GEMM, OP_NCHW, OP_DWPW, OP_HEADS, OP_SEP, OP_FRONTEND };
 
 struct Op {
   OpKind kind;
@@ -70,6 +71,7 @@ struct Op {
   const float *hd_scale1 = nullptr, *hd_shift1 = nullptr, *hd_scale2 = nullptr, *hd_shift2 = nullptr;
   float *hd_out_f32 = nullptr;
   void *hd_out = nullptr;
+  FrontendArgs fe;   // fused front end
 };
 
 }  // namespace lwp
@@ -142,6 +144,32 @@ extern "C" int lwp_plan_add_stem_u8(lwp_plan *p, const float *w, const float *sc
   op.stem_u8 = true;
   op.mean[0] = img_mean3[0]; op.mean[1] = img_mean3[1]; op.mean[2] = img_mean3[2];
   op.img_scale = img_scale;
+  return LWP_OK;
+}
+
+extern "C" int lwp_plan_add_frontend(lwp_plan *p, const float *stem_w, const float *stem_scale, const float *stem_shift,
+                                     const float *dw1_w, const float *dw1_scale, const float *dw1_shift, const void *pw_w,
+                                     const float *pw_scale, const float *pw_shift, const float *dw2_w,
+                                     const float *dw2_scale, const float *dw2_shift, void *out, int n, int H, int W,
+                                     int input_u8, const double *img_mean3, double img_scale) {
+  LWP_REQUIRE(p && stem_w && stem_scale && stem_shift && dw1_w && dw1_scale && dw1_shift && pw_w && pw_scale && pw_shift &&
+                  dw2_w && dw2_scale && dw2_shift && out, "lwp_plan_add_frontend: null pointer");
+  LWP_REQUIRE(p->dtype == LWP_DTYPE_BF16, "lwp_plan_add_frontend: bf16 plans only");
+  LWP_REQUIRE(n > 0 && H > 0 && W > 0 && H % 4 == 0 && W % 4 == 0, "lwp_plan_add_frontend: H and W must be multiples of 4");
+  LWP_REQUIRE(((uintptr_t)pw_w % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dw1_w % 16) == 0 && ((uintptr_t)dw2_w % 16) == 0,
+              "lwp_plan_add_frontend: unaligned pointer");
+  LWP_REQUIRE(!input_u8 || img_mean3 != nullptr, "lwp_plan_add_frontend: null mean");
+  Op op;
+  op.kind = OP_FRONTEND;
+  FrontendArgs &a = op.fe;
+  a.x_is_u8 = input_u8 != 0;
+  if (input_u8) { a.mean[0] = img_mean3[0]; a.mean[1] = img_mean3[1]; a.mean[2] = img_mean3[2]; a.img_scale = img_scale; }
+  a.stem_w = stem_w; a.stem_scale = stem_scale; a.stem_shift = stem_shift;
+  a.dw1_w = dw1_w; a.dw1_scale = dw1_scale; a.dw1_shift = dw1_shift;
+  a.pw_w = pw_w; a.pw_scale = pw_scale; a.pw_shift = pw_shift;
+  a.dw2_w = dw2_w; a.dw2_scale = dw2_scale; a.dw2_shift = dw2_shift;
+  a.out = out; a.n = n; a.H = H; a.W = W;
+  p->ops.push_back(op);
   return LWP_OK;
 }
 
@@ -723,6 +751,13 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const void *x, int first, int las
                                 op.hd_scale2, op.hd_shift2, op.hd_out_f32, op.hd_f32_ld, op.hd_out, op.hd_out_ld, p->err_flag,
                                 st);
         break;
+      case OP_FRONTEND: {
+        LWP_REQUIRE(x != nullptr, "lwp_plan_run: the plan has a front end but x is NULL");
+        FrontendArgs a = op.fe;
+        a.x = x;
+        rc = frontend_fused_launch(a, p->err_flag, st);
+        break;
+      }
       case OP_NCHW:
         rc = nhwc_to_nchw_launch(op.in_f32 != 0, op.in, op.ld, op.c0, op.C, (float *)op.out, op.n, op.H * op.W, st);
         break;

@@ -176,7 +176,8 @@ class _RecordingLib:
 
 # function ids of the blob format (csrc/net_blob.cu must agree)
 _BLOB_FUNCS = {"lwp_plan_add_stem": 0, "lwp_plan_add_stem_u8": 1, "lwp_plan_add_depthwise": 2, "lwp_plan_add_conv_gemm": 3,
-               "lwp_plan_add_dwpw": 4, "lwp_plan_add_sepconv": 5, "lwp_plan_add_heads_fused": 6, "lwp_plan_add_nhwc_to_nchw": 7}
+               "lwp_plan_add_dwpw": 4, "lwp_plan_add_sepconv": 5, "lwp_plan_add_heads_fused": 6, "lwp_plan_add_nhwc_to_nchw": 7,
+               "lwp_plan_add_frontend": 8}
 
 
 def _all_tensors(obj, out, seen):
@@ -372,7 +373,34 @@ class Plan:
         pp = [self._buf(biggest), self._buf(biggest)]
 
         w_, s_, b_ = P.stem
-        if self.input_u8 is None:
+        es_ = 2 if self.tdtype == torch.bfloat16 else 4
+        # fused front end (frontend_fused.cu): stem + model.1 (dw + pw) + the depthwise half of model.2 as one kernel on
+        # bf16 plans -- the 32- / 64-channel maps at H/2 x W/2 never reach HBM (ncu: 276 MB of DRAM traffic instead of
+        # 2.1 GB) and the result is bit-identical.  OPT-IN (LWP_FRONTEND_FUSION=1): measured on 64 x 368x656 it takes 546 us
+        # (float frames) / 587 us (uint8) against 471 / 503 us for the four HBM-bound kernels -- it is bound by the CUDA
+        # cores' instruction issue (31 k warp instructions per 8x16 output tile at 46 % issue utilisation with the one
+        # 512-thread CTA an SM can hold; DESIGN.md section 3.2e, profiles/r02k_*).
+        dw1, pw1 = P.backbone[0]
+        dw2, _pw2 = P.backbone[1]
+        self.frontend_fused = (self.tdtype == torch.bfloat16 and os.environ.get("LWP_FRONTEND_FUSION", "0") not in ("", "0")
+                               and not self.fuse_dwpw and not self.use_sepconv
+                               and dw1.c == 32 and dw1.stride == 1 and dw1.dilation == 1 and dw1.act == ACT_RELU
+                               and pw1.cin == 32 and pw1.cout == 64 and pw1.taps == 1 and pw1.act == ACT_RELU
+                               and dw2.c == 64 and dw2.stride == 2 and dw2.dilation == 1 and dw2.act == ACT_RELU)
+        if self.frontend_fused:
+            mean3, img_scale = self.input_u8 if self.input_u8 is not None else ((0.0, 0.0, 0.0), 1.0)
+            mean_arr = (_lib._c_double * 3)(*[float(m) for m in mean3])
+            _lib.check(self.lib.lwp_plan_add_frontend(
+                self.handle, w_.data_ptr(), s_.data_ptr(), b_.data_ptr(), dw1.w.data_ptr(), dw1.scale.data_ptr(),
+                dw1.shift.data_ptr(), pw1.w.data_ptr(), pw1.scale.data_ptr(), pw1.shift.data_ptr(), dw2.w.data_ptr(),
+                dw2.scale.data_ptr(), dw2.shift.data_ptr(), pp[0].data_ptr(), n, H, W, 0 if self.input_u8 is None else 1,
+                mean_arr, float(img_scale)), "lwp_plan_add_frontend")
+            self.op_names.append("model.0-2.frontend")
+            px2, px4 = n * (H // 2) * (W // 2), n * (H // 4) * (W // 4)
+            in_bytes = n * 3 * H * W * (4 if self.input_u8 is None else 1)
+            self.op_meta.append(dict(kind="frontend", flops=2.0 * (27 * 32 + 9 * 32 + 32 * 64) * px2 + 2.0 * 9 * 64 * px4,
+                                     bytes=float(in_bytes + px4 * 64 * es_)))
+        elif self.input_u8 is None:
             _lib.check(self.lib.lwp_plan_add_stem(self.handle, w_.data_ptr(), s_.data_ptr(), b_.data_ptr(),
                                                   pp[0].data_ptr(), n, H, W), "lwp_plan_add_stem")
         else:
@@ -381,13 +409,21 @@ class Plan:
             _lib.check(self.lib.lwp_plan_add_stem_u8(self.handle, w_.data_ptr(), s_.data_ptr(), b_.data_ptr(),
                                                      pp[0].data_ptr(), n, H, W, mean_arr, float(img_scale)),
                        "lwp_plan_add_stem_u8")
-        self.op_names.append("model.0")
-        es_ = 2 if self.tdtype == torch.bfloat16 else 4
-        self.op_meta.append(dict(kind="stem", flops=2.0 * 27 * 32 * n * (H // 2) * (W // 2),
-                                 bytes=float(n * 3 * H * W * 4 + n * (H // 2) * (W // 2) * 32 * es_)))
+        if not self.frontend_fused:
+            self.op_names.append("model.0")
+            self.op_meta.append(dict(kind="stem", flops=2.0 * 27 * 32 * n * (H // 2) * (W // 2),
+                                     bytes=float(n * 3 * H * W * 4 + n * (H // 2) * (W // 2) * 32 * es_)))
         hh, ww, c, cur = H // 2, W // 2, 32, 0
         for i, (dw, pw) in enumerate(P.backbone):
             ho, wo = (hh - 1) // dw.stride + 1, (ww - 1) // dw.stride + 1
+            if self.frontend_fused and i == 0:     # model.1 is inside the front-end kernel ...
+                hh, ww, c = ho, wo, pw.cout
+                continue
+            if self.frontend_fused and i == 1:     # ... and so is model.2's depthwise conv: pp[0] holds its output
+                self._gemm("model.2.pw", pp[0], c, pw, n, ho, wo, out=pp[1], out_ld=pw.cout_pad)
+                cur = 1
+                hh, ww, c = ho, wo, pw.cout
+                continue
             # fused: the depthwise result goes straight into the GEMM's smem A operand
             if self._fusable(dw, pw, "model.%d.dwpw" % (i + 1)) and self._dwpw("model.%d.dwpw" % (i + 1), pp[cur], dw, pw, n, hh, ww, pp[cur ^ 1],
                                                     pw.cout_pad):

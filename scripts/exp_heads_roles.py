@@ -1,3 +1,5 @@
+"""Per-role cycle accounting of heads_fused_kernel (total / waiting cycles per role, mean over CTAs).
+Needs a library built with LWP_NVCC_EXTRA=-DLWP_TIMING_EXPERIMENTS and LWP_ALLOW_TIMING_EXPERIMENTS=1."""
 import ctypes, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

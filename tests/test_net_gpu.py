@@ -508,3 +508,42 @@ def test_c_entry_points_run_the_network_without_the_python_engine(env, precision
     blob = open(path, "rb").read()
     with pytest.raises(_lib.LwpError):
         cnet.CNet(blob[:len(blob) // 2])
+
+
+@pytest.mark.parametrize("u8", [False, True], ids=["f32", "u8"])
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 72, 104), (3, 256, 456 - 456 % 8), (2, 368, 656)], ids=lambda s: "%dx%dx%d" % s)
+def test_frontend_fused_bit_identical_to_separate_ops(env, shape, u8, monkeypatch):
+    """frontend_fused.cu (stem + model.1 dw/pw + model.2 dw as one kernel) rounds at the same points and in the same
+    operation order as the four separate kernels: the 64-channel stride-4 map and the final heads must be BIT-identical
+    (partial tiles in both directions, tiles on every image border, float32 and uint8 frames).  The fused kernel is
+    opt-in (LWP_FRONTEND_FUSION=1): it is slower than the four HBM-bound kernels it replaces."""
+    torch, _lib, engine = env
+    from lwpose_b200 import synth
+    n, H, W = shape
+    net = _build_net(torch, "r1_64x96", 1, 1.0).cuda()
+    if u8:
+        x = torch.from_numpy(synth.synthetic_frames(n, H, W, seed=5)).cuda()
+        fmt = ((128.0, 128.0, 128.0), 1.0 / 256)
+    else:
+        x = synth.synthetic_net_input(n, H, W, seed=5).cuda()
+        fmt = None
+    eng = engine.NetEngine(net)
+    monkeypatch.setenv("LWP_FRONTEND_FUSION", "0")
+    ref = eng.new_plan("bf16", n, H, W, input_u8=fmt)
+    monkeypatch.setenv("LWP_FRONTEND_FUSION", "1")
+    fused = eng.new_plan("bf16", n, H, W, input_u8=fmt)
+    assert not ref.frontend_fused and fused.frontend_fused
+    assert ref.op_names[:4] == ["model.0", "model.1.dw", "model.1.pw", "model.2.dw"] and fused.op_names[0] == "model.0-2.frontend"
+    q = n * (H // 4) * (W // 4) * 64
+    ref.run(x, 0, 4)          # stem -> pp[0], dw -> pp[1], pw -> pp[0], dw (stride 2) -> pp[1]
+    fused.run(x, 0, 1)        # -> pp[0]
+    torch.cuda.synchronize()
+    a, b = ref.bufs[1][:q].view(torch.int16).cpu(), fused.bufs[0][:q].view(torch.int16).cpu()
+    assert fused.error_flag() == 0 and ref.error_flag() == 0
+    bad = (a != b).nonzero()
+    assert bad.numel() == 0, (int(bad.numel()), [int(v) for v in bad[:8].flatten()])
+    ref.run_compute(x)
+    fused.run_compute(x)
+    torch.cuda.synchronize()
+    for ha, hb in zip(ref.heads_f32, fused.heads_f32):
+        assert torch.equal(ha.view(torch.int32), hb.view(torch.int32))
