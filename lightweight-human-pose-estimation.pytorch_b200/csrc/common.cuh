@@ -72,6 +72,14 @@ static inline int debug_env(const char *) { return 0; }
 // LWP_NO_PDL=1 launches everything as ordinary stream-ordered kernels (then both device calls are no-ops).
 bool pdl_enabled();
 #ifdef __CUDACC__
+// ELU(alpha = 1) = x > 0 ? x : exp(x) - 1 with ONE MUFU: ex2.approx.ftz of x * log2(e) (abs error ~1e-7; very negative x
+// flushes to 0 -> -1).  __expf() wraps the same instruction in a denormal-input rescue (FSETP / PLOP3 / 2 x FMUL) that
+// doubled the instruction count of the ELU epilogues -- the Cpm trunk kernels are instruction-issue-bound.
+__device__ __forceinline__ float lwp_elu(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+  return v > 0.f ? v : e - 1.f;
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -250,7 +250,7 @@ struct DwTileParams {
 __device__ __forceinline__ float2 bf16x2_to_f32x2(uint32_t x) {  // PRMT + LOP3: keeps the FMA pipe for the FFMA2s
   return make_float2(__uint_as_float(__byte_perm(x, 0u, 0x1044)), __uint_as_float(x & 0xffff0000u));
 }
-__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : __expf(v) - 1.f; }  // ELU(alpha = 1) as in the fused block: abs error ~1e-7
+__device__ __forceinline__ float elu1(float v) { return lwp_elu(v); }  // ELU(alpha = 1) as in the fused block: abs error ~1e-7
 #ifndef LWP_DW_STCS
 #define LWP_DW_STCS 0
 #endif

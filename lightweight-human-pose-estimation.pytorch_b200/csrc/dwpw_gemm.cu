@@ -50,7 +50,7 @@ size_t dwpw_smem_bytes(const DwpwParams &p) { return (size_t)dwpw_smem_layout(p)
 
 __device__ __forceinline__ float dw_act(float v, int act) {
   if (act == LWP_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == LWP_ACT_ELU) return v > 0.f ? v : __expf(v) - 1.f;
+  if (act == LWP_ACT_ELU) return lwp_elu(v);
   return v;
 }
 
@@ -127,8 +127,8 @@ __device__ __forceinline__ void dw_block(const uint8_t *in0, int row_bytes, cons
     for (int j = 0; j < 4; ++j) {
       y[j] = __ffma2_rn(acc[a][j], sc[j], sh[j]);
       if constexpr (ACT == LWP_ACT_ELU) {
-        y[j].x = y[j].x > 0.f ? y[j].x : __expf(y[j].x) - 1.f;
-        y[j].y = y[j].y > 0.f ? y[j].y : __expf(y[j].y) - 1.f;
+        y[j].x = lwp_elu(y[j].x);
+        y[j].y = lwp_elu(y[j].y);
       } else if constexpr (ACT == LWP_ACT_RELU && kTf32) {
         y[j].x = fmaxf(y[j].x, 0.f);
         y[j].y = fmaxf(y[j].y, 0.f);

@@ -66,7 +66,7 @@ __device__ __forceinline__ void epilogue_unit(const uint32_t (&r)[32], uint8_t *
       for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
     } else if (act == LWP_ACT_ELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : __expf(v[j]) - 1.f;  // ELU(alpha=1); abs error ~1e-7
+      for (int j = 0; j < 8; ++j) v[j] = lwp_elu(v[j]);  // ELU(alpha=1); abs error ~1e-7
     }
     if (res_ok) {
       if constexpr (kTf32) {

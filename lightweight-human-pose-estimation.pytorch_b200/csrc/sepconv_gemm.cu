@@ -140,8 +140,8 @@ __device__ __forceinline__ void sep_dw_item(uint32_t win, uint32_t row_bytes, co
     for (int c = 0; c < CC; ++c) {
       float2 y0 = __ffma2_rn(acc[r][c][0], sc0, sh0), y1 = __ffma2_rn(acc[r][c][1], sc1, sh1);
       if constexpr (ACT == LWP_ACT_ELU) {
-        y0.x = y0.x > 0.f ? y0.x : __expf(y0.x) - 1.f; y0.y = y0.y > 0.f ? y0.y : __expf(y0.y) - 1.f;
-        y1.x = y1.x > 0.f ? y1.x : __expf(y1.x) - 1.f; y1.y = y1.y > 0.f ? y1.y : __expf(y1.y) - 1.f;
+        y0.x = lwp_elu(y0.x); y0.y = lwp_elu(y0.y);
+        y1.x = lwp_elu(y1.x); y1.y = lwp_elu(y1.y);
       }
       const uint32_t dst = abuf_s + a_off[r][c];
       if constexpr (kTf32) {
@@ -195,7 +195,7 @@ __device__ __forceinline__ void sep_unit16(const uint32_t (&r)[16], uint8_t *sro
       for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
     } else if (act == LWP_ACT_ELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : __expf(v[j]) - 1.f;
+      for (int j = 0; j < 8; ++j) v[j] = lwp_elu(v[j]);
     }
     if constexpr (kTf32) {
       if (res_ok) {
