@@ -413,7 +413,9 @@ class Plan:
             self.op_names.append("model.0")
             self.op_meta.append(dict(kind="stem", flops=2.0 * 27 * 32 * n * (H // 2) * (W // 2),
                                      bytes=float(n * 3 * H * W * 4 + n * (H // 2) * (W // 2) * 32 * es_)))
-        hh, ww, c, cur = H // 2, W // 2, 32, 0
+        hh, ww, c, cur, cur_off = H // 2, W // 2, 32, 0, 0
+        pair_chunks = int(os.environ.get("LWP_PAIR_CHUNKS", "0") or 0)
+        pair_from = int(os.environ.get("LWP_PAIR_CHUNK_FROM", "2") or 2)
         for i, (dw, pw) in enumerate(P.backbone):
             ho, wo = (hh - 1) // dw.stride + 1, (ww - 1) // dw.stride + 1
             if self.frontend_fused and i == 0:     # model.1 is inside the front-end kernel ...
@@ -430,12 +432,35 @@ class Plan:
                 cur ^= 1
             elif self._sepconv("model.%d.sep" % (i + 1), pp[cur], dw, pw, n, hh, ww, pp[cur ^ 1], pw.cout_pad):
                 cur ^= 1
+            elif pair_chunks > 1 and i >= pair_from and n >= pair_chunks:
+                # L2-resident sub-batches (experiment, LWP_PAIR_CHUNKS=S): the pair runs S times on n / S frames each, the
+                # depthwise output of a sub-batch goes to one of two small scratch slots (re-written every other sub-batch,
+                # so its dirty lines can stay in the 126 MB L2) and is read back by the 1x1 conv of the same sub-batch.
+                # Input: pp[cur][cur_off:]; scratch and output both live in the other buffer.
+                k = (n + pair_chunks - 1) // pair_chunks
+                scratch = k * ho * wo * c
+                out_off = 2 * scratch
+                assert out_off + n * ho * wo * pw.cout_pad <= pp[cur ^ 1].numel()
+                for sb in range(pair_chunks):
+                    lo = sb * k
+                    cnt = min(k, n - lo)
+                    if cnt <= 0:
+                        break
+                    src = pp[cur][cur_off + lo * hh * ww * c:]
+                    mid = pp[cur ^ 1][(sb & 1) * scratch:]
+                    dst = pp[cur ^ 1][out_off + lo * ho * wo * pw.cout_pad:]
+                    self._dw("model.%d.dw#%d" % (i + 1, sb), src, mid, dw, cnt, hh, ww)
+                    self._gemm("model.%d.pw#%d" % (i + 1, sb), mid, c, pw, cnt, ho, wo, out=dst, out_ld=pw.cout_pad)
+                cur ^= 1
+                cur_off = out_off
             else:
-                self._dw("model.%d.dw" % (i + 1), pp[cur], pp[cur ^ 1], dw, n, hh, ww)
+                src = pp[cur][cur_off:]
+                self._dw("model.%d.dw" % (i + 1), src, pp[cur ^ 1], dw, n, hh, ww)
                 self._gemm("model.%d.pw" % (i + 1), pp[cur ^ 1], c, pw, n, ho, wo, out=pp[cur], out_ld=pw.cout_pad)
+                cur_off = 0
             hh, ww, c = ho, wo, pw.cout
         assert (hh, ww) == (self.h, self.w) and c == 512
-        feat = pp[cur]
+        feat = pp[cur][cur_off:]
         h, w = self.h, self.w
         px = n * h * w
         nc = P.cpm_align.cout  # 128
