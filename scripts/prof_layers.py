@@ -27,10 +27,16 @@ def main():
     torch.cuda.synchronize()
     c = pipe.chunks[0]
     plan = c.plan
+    layer_names = [nm for nm in names if nm != "postproc"]
     torch.cuda.profiler.start()
     for nm in names:
         if nm == "postproc":
-            c.enqueue_postproc(c.heads)
+            if layer_names:   # the single-layer runs above overwrote the heads: restore a full pass with the person maps
+                torch.cuda.profiler.stop()
+                pipe.run_device(x)
+                torch.cuda.synchronize()
+                torch.cuda.profiler.start()
+            c.enqueue_postproc(c.heads_pp if pipe.overlap_postproc and not pipe.graph else c.heads)
         else:
             i = plan.op_names.index(nm)
             plan.run(x, i, i + 1)
