@@ -236,6 +236,18 @@ int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, const void *w
                            float *out_f32, int out_f32_ld, int n, int H, int W, int Cin, int Cout, int taps,
                            int dilation, int act);
 
+/*
+ * A RefinementStageBlock's second 3x3 conv (+ BN + ReLU + the residual add, models/with_mobilenet.py:53-60) and the
+ * `initial` 1x1 conv of the NEXT block (:52,57) as one back-to-back tcgen05 kernel (bf16 plans, 128 -> 128 -> 128): the
+ * block output stays in tensor memory, only the 1x1's output [pixels][out_ld] is written.  Bit-identical to the two
+ * separate lwp_plan_add_conv_gemm ops.  w: [128][9*Cin], w2: [128][128], both K-major in the plan dtype.  Returns
+ * LWP_ECAP (nothing recorded) when the 3x3 cannot run on the CTA-pair strip kernel; the caller then records two ops.
+ */
+int lwp_plan_add_conv3x3_pw(lwp_plan *p, const void *in, int in_ld, const void *w, const float *scale, const float *shift,
+                            const void *residual, int res_ld, int act, const void *w2, const float *scale2,
+                            const float *shift2, int act2, void *out, int out_ld, int n, int H, int W, int Cin,
+                            int dilation);
+
 /* Both 1x1 layers of a stage's heads (models/with_mobilenet.py:33-38,74-79: conv 128->512|128 + ReLU, conv ->19|38,
    the two heads stacked / block-diagonal) as ONE back-to-back GEMM kernel: the c_mid-channel intermediate never leaves
    the SM.  bf16 plans only.  in: [n_pixels][in_ld] plan dtype; w1: [c_mid][c_in], w2: [64][c_mid] (K-major, plan

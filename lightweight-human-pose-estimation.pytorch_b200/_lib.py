@@ -55,6 +55,9 @@ SIGNATURES = {
                                       ctypes.POINTER(_c_double), _c_double]),
     "lwp_plan_add_frontend": (_c_int, [_c_void_p] + [_c_void_p] * 13 + [_c_int, _c_int, _c_int, _c_int, ctypes.POINTER(_c_double),
                                                               _c_double]),
+    "lwp_plan_add_conv3x3_pw": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                                         _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int,
+                                         _c_int, _c_int]),
     "lwp_plan_add_depthwise": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
                                         _c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
     "lwp_plan_add_heads_fused": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p,

@@ -57,6 +57,10 @@ struct GemmParams {
   int kbps;                // K blocks per pipeline stage (1 or 2): one barrier round trip then covers 4 or 8 MMAs;
                            // a stage is kbps consecutive [A tile | B tile] pairs (conv_gemm_kernel only)
   int c3_a_stages, c3_b_stages;   // conv3x3_pair_kernel: activation-strip / weight-tile ring depths
+  // conv3x3_pair_kernel with a fused trailing 1x1 conv (bf16, Cout = 128 -> 128): out = act2((act(conv3x3 + ...) + residual) W2^T * scale2 + shift2)
+  int fuse_pw;             // 0 / 1
+  const float *scale2, *shift2;
+  int act2;
   int staging_bufs;        // 1 or 2 staging buffers per epilogue warp (2: the next chunk is converted while the
                            // tensor store of the previous one still reads its buffer); conv_gemm_kernel only
 };
@@ -78,6 +82,8 @@ size_t conv_gemm3_smem_bytes(const GemmParams &p);
 int conv_gemm3_init();
 int conv_gemm3_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
                       const GemmParams &p, int grid, cudaStream_t st);
+int conv_gemm3_pw_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const CUtensorMap &tmW2,
+                         const GemmParams &p, int grid, cudaStream_t st);
 size_t conv_gemm2_smem_bytes(const GemmParams &p);
 int conv_gemm2_init();
 int conv_gemm2_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,

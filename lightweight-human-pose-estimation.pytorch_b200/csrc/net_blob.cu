@@ -142,6 +142,9 @@ extern "C" int lwp_net_load(const void *blob, size_t bytes, lwp_net **out) {
       case 8: if (na != 19) { rc = LWP_EINVAL; break; }
         rc = lwp_plan_add_frontend(pl, FP(0), FP(1), FP(2), FP(3), FP(4), FP(5), P(6), FP(7), FP(8), FP(9), FP(10), FP(11), P(12),
                                    I(13), I(14), I(15), I(16), a[17].d3, a[18].d); break;
+      case 9: if (na != 19) { rc = LWP_EINVAL; break; }
+        rc = lwp_plan_add_conv3x3_pw(pl, P(0), I(1), P(2), FP(3), FP(4), P(5), I(6), I(7), P(8), FP(9), FP(10), I(11), P(12), I(13),
+                                     I(14), I(15), I(16), I(17), I(18)); break;
       default: rc = LWP_EINVAL;
     }
 #undef P

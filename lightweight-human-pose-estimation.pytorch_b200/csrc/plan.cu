@@ -72,6 +72,7 @@ struct Op {
   float *hd_out_f32 = nullptr;
   void *hd_out = nullptr;
   FrontendArgs fe;   // fused front end
+  CUtensorMap tmD;   // fused 3x3 + 1x1: the 1x1's weights
 };
 
 }  // namespace lwp
@@ -251,6 +252,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   Op op;
   op.kind = OP_GEMM;
   GemmParams &g = op.gp;
+  g.fuse_pw = 0; g.scale2 = nullptr; g.shift2 = nullptr; g.act2 = 0;
   g.taps = taps; g.dil = dilation; g.cin = Cin; g.kb_elems = kb_elems; g.kb_bytes = kb_bytes;
   g.kblocks_per_tap = (Cin + kb_elems - 1) / kb_elems;
   g.cout_pad = cout_pad;
@@ -413,6 +415,47 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
     g.tma_store = 1;
   }
   p->ops.push_back(op);
+  return LWP_OK;
+}
+
+extern "C" int lwp_plan_add_conv3x3_pw(lwp_plan *p, const void *in, int in_ld, const void *w, const float *scale,
+                                       const float *shift, const void *residual, int res_ld, int act, const void *w2,
+                                       const float *scale2, const float *shift2, int act2, void *out, int out_ld, int n,
+                                       int H, int W, int Cin, int dilation) {
+  LWP_REQUIRE(p && w2 && scale2 && shift2 && out, "lwp_plan_add_conv3x3_pw: null pointer");
+  LWP_REQUIRE(p->dtype == LWP_DTYPE_BF16, "lwp_plan_add_conv3x3_pw: bf16 plans only");
+  LWP_REQUIRE(((uintptr_t)w2 % 16) == 0, "lwp_plan_add_conv3x3_pw: unaligned pointer");
+  // record the 3x3 as usual (its output map then describes the 1x1's output), and turn the op into the fused form
+  const size_t before = p->ops.size();
+  int rc = lwp_plan_add_conv_gemm(p, in, in_ld, w, scale, shift, residual, res_ld, out, out_ld, nullptr, 0, n, H, W, Cin, 128, 9,
+                                  dilation, act);
+  if (rc != LWP_OK) return rc;
+  Op &op = p->ops.back();
+  if (!op.strips || op.gp.n_store != 128 || op.gp.tma_store == 0) {   // not the strip kernel: the caller records two ops
+    p->ops.resize(before);
+    set_error("lwp_plan_add_conv3x3_pw: the layer does not run on the strip kernel");
+    return LWP_ECAP;
+  }
+  GemmParams &g = op.gp;
+  g.fuse_pw = 1; g.scale2 = scale2; g.shift2 = shift2; g.act2 = act2;
+  g.acc_stages = 2;   // TMEM: 2 x 128 (3x3 accumulators) + 64 (A2) + 128 (1x1 accumulator)
+  g.c3_a_stages = 4; g.c3_b_stages = 8;
+  while (g.c3_b_stages > 3 && conv_gemm3_smem_bytes(g) > (size_t)gemm_smem_cap()) --g.c3_b_stages;
+  while (g.c3_a_stages > 2 && conv_gemm3_smem_bytes(g) > (size_t)gemm_smem_cap()) --g.c3_a_stages;
+  if (conv_gemm3_smem_bytes(g) > (size_t)gemm_smem_cap()) {
+    p->ops.resize(before);
+    set_error("lwp_plan_add_conv3x3_pw: tiles do not fit in shared memory");
+    return LWP_ECAP;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  cuuint64_t dims[2] = {128, 128};
+  cuuint64_t strides[1] = {128 * 2};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&op.tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(w2), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { p->ops.resize(before); set_error("cuTensorMapEncodeTiled(W2) failed: %d", (int)r); return LWP_ECUDA; }
   return LWP_OK;
 }
 
@@ -736,7 +779,8 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const void *x, int first, int las
                                 op.dil, op.act, st);
         break;
       case OP_GEMM:
-        rc = op.strips    ? conv_gemm3_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st)
+        rc = op.gp.fuse_pw ? conv_gemm3_pw_launch(op.tmA, op.tmB, op.tmC, op.tmD, op.gp, op.grid, st)
+             : op.strips  ? conv_gemm3_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st)
              : op.two_cta ? conv_gemm2_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st)
                           : conv_gemm_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st);
         break;

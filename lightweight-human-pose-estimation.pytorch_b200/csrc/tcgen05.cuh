@@ -223,6 +223,15 @@ __device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint
         : "memory");
   }
 }
+// D[tmem of both CTAs] (+)= A[tmem of both CTAs: 128 rows each, packed 16-bit K-major] * B[both CTAs' smem, N/2 rows each]^T
+__device__ __forceinline__ void umma_pair_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrive, on the same barrier offset in both CTAs of the pair, once the issued MMAs have completed
 __device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
   asm volatile(

@@ -177,7 +177,7 @@ class _RecordingLib:
 # function ids of the blob format (csrc/net_blob.cu must agree)
 _BLOB_FUNCS = {"lwp_plan_add_stem": 0, "lwp_plan_add_stem_u8": 1, "lwp_plan_add_depthwise": 2, "lwp_plan_add_conv_gemm": 3,
                "lwp_plan_add_dwpw": 4, "lwp_plan_add_sepconv": 5, "lwp_plan_add_heads_fused": 6, "lwp_plan_add_nhwc_to_nchw": 7,
-               "lwp_plan_add_frontend": 8}
+               "lwp_plan_add_frontend": 8, "lwp_plan_add_conv3x3_pw": 9}
 
 
 def _all_tensors(obj, out, seen):
@@ -500,15 +500,41 @@ class Plan:
         self._heads("initial_stage.heads", t0, nc, P.init_heads, n, h, w, big, concat if more else None, nc,
                     self.heads_f32[0])
         # refinement stages
+        # bf16 plans: the second 3x3 of block k (+ residual) and the `initial` 1x1 of block k + 1 run as ONE kernel
+        # (lwp_plan_add_conv3x3_pw: the block output never leaves tensor memory); LWP_CONV3_PW=0 keeps the two ops
+        fuse_pw = self.tdtype == torch.bfloat16 and os.environ.get("LWP_CONV3_PW", "1") != "0"
+        i0b = self._buf(px * nc) if (fuse_pw and len(P.refine) > 0) else None
+        es = 2
         for s, (blks, heads) in enumerate(P.refine):
             src, src_ld = concat, CONCAT_LD
+            ibuf = [i0, i0b]
+            have_initial = False     # True when the previous block's fused kernel already produced this block's initial features
             for k, (ini, c0, c1) in enumerate(blks):
-                self._gemm("refinement_stages.%d.trunk.%d.initial" % (s, k), src, src_ld, ini, n, h, w, out=i0,
-                           out_ld=nc)
-                self._gemm("refinement_stages.%d.trunk.%d.trunk.0" % (s, k), i0, nc, c0, n, h, w, out=t0, out_ld=nc)
+                cur_i = ibuf[k & 1] if fuse_pw else i0
+                if not have_initial:
+                    self._gemm("refinement_stages.%d.trunk.%d.initial" % (s, k), src, src_ld, ini, n, h, w, out=cur_i,
+                               out_ld=nc)
+                self._gemm("refinement_stages.%d.trunk.%d.trunk.0" % (s, k), cur_i, nc, c0, n, h, w, out=t0, out_ld=nc)
+                have_initial = False
+                if fuse_pw and k + 1 < len(blks):
+                    nxt = blks[k + 1][0]
+                    nxt_i = ibuf[(k + 1) & 1]
+                    rc = self.lib.lwp_plan_add_conv3x3_pw(
+                        self.handle, t0.data_ptr(), nc, c1.w.data_ptr(), c1.scale.data_ptr(), c1.shift.data_ptr(),
+                        cur_i.data_ptr(), nc, c1.act, nxt.w.data_ptr(), nxt.scale.data_ptr(), nxt.shift.data_ptr(), nxt.act,
+                        nxt_i.data_ptr(), nc, n, h, w, c1.cin, c1.dilation) if (
+                            c1.taps == 9 and c1.cout == 128 and nxt.taps == 1 and nxt.cin == 128 and nxt.cout == 128) else 3
+                    if rc != 3:   # LWP_ECAP: two ops
+                        _lib.check(rc, "lwp_plan_add_conv3x3_pw")
+                        self.op_names.append("refinement_stages.%d.trunk.%d.trunk.1+%d.initial" % (s, k, k + 1))
+                        pxs = n * h * w
+                        self.op_meta.append(dict(kind="gemm3x3", flops=pxs * (2.0 * 9 * c1.cin * c1.cout + 2.0 * nxt.cin * nxt.cout),
+                                                 bytes=float(pxs * (c1.cin + 2 * c1.cout) * es + (9 * c1.cin * c1.cout + nxt.cin * nxt.cout) * es)))
+                        have_initial = True
+                        continue
                 dst = r[k & 1]
                 self._gemm("refinement_stages.%d.trunk.%d.trunk.1" % (s, k), t0, nc, c1, n, h, w, out=dst, out_ld=nc,
-                           residual=i0, res_ld=nc)  # initial_features + trunk_features
+                           residual=cur_i, res_ld=nc)  # initial_features + trunk_features
                 src, src_ld = dst, nc
             more = s + 1 < len(P.refine)
             self._heads("refinement_stages.%d.heads" % s, src, nc, heads, n, h, w, big, concat if more else None, nc,

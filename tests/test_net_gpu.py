@@ -547,3 +547,29 @@ def test_frontend_fused_bit_identical_to_separate_ops(env, shape, u8, monkeypatc
     torch.cuda.synchronize()
     for ha, hb in zip(ref.heads_f32, fused.heads_f32):
         assert torch.equal(ha.view(torch.int32), hb.view(torch.int32))
+
+
+@pytest.mark.parametrize("case", [(1, 2, 128, 192), (3, 1, 120, 200), (1, 3, 368, 656)], ids=lambda c: "R%d_%dx%dx%d" % c)
+def test_conv3x3_pw_fused_bit_identical_to_two_ops(env, case, monkeypatch):
+    """lwp_plan_add_conv3x3_pw (second 3x3 of a RefinementStageBlock + residual, then the next block's `initial` 1x1, as one
+    back-to-back tcgen05 kernel with the block output in tensor memory) rounds exactly where the two separate kernels
+    round: every stage's heads must be BIT-identical (R = 1 and 3, ragged tiles, the benchmarked map size)."""
+    torch, _lib, engine = env
+    from lwpose_b200 import synth
+    R, n, H, W = case
+    net = _build_net(torch, "r%d" % R, R, 1.0).cuda()
+    x = synth.synthetic_net_input(n, H, W, seed=9).cuda()
+    eng = engine.NetEngine(net)
+    monkeypatch.setenv("LWP_CONV3_PW", "0")
+    ref = eng.new_plan("bf16", n, H, W)
+    monkeypatch.setenv("LWP_CONV3_PW", "1")
+    fused = eng.new_plan("bf16", n, H, W)
+    assert not any("+" in nm for nm in ref.op_names)
+    assert sum("trunk.1+" in nm for nm in fused.op_names) == 4 * R and len(fused.op_names) == len(ref.op_names) - 4 * R
+    ref.run_compute(x)
+    fused.run_compute(x)
+    torch.cuda.synchronize()
+    assert fused.error_flag() == 0 and ref.error_flag() == 0
+    for s, (ha, hb) in enumerate(zip(ref.heads_f32, fused.heads_f32)):
+        a, b = ha.view(torch.int32), hb.view(torch.int32)
+        assert torch.equal(a, b), (s, int((a != b).sum()), float((ha - hb).abs().max()))
