@@ -157,12 +157,15 @@ class _Chunk:
         cv = self.pipe.convert
         if cv is None:
             return
-        pad, scale = cv["pad"], cv["scale"]
-        if np.ndim(scale) > 0:   # per-frame transforms: this chunk's slice
-            pad, scale = np.asarray(pad)[self.lo:self.lo + self.n], np.asarray(scale)[self.lo:self.lo + self.n]
+        if getattr(self, "_xform", None) is None:   # once: the upload is a pageable copy that blocks the host until the
+            pad, scale = cv["pad"], cv["scale"]     # stream reaches it -- per batch it serialised submit() with the network
+            if np.ndim(scale) > 0:   # per-frame transforms: this chunk's slice
+                pad, scale = np.asarray(pad)[self.lo:self.lo + self.n], np.asarray(scale)[self.lo:self.lo + self.n]
+            self._xform = postproc.pose_convert_xform(self.n, pad, scale, self.pose_entries.device)
+            torch.cuda.synchronize(self.pose_entries.device)
         postproc.pose_convert(self.pose_entries, self.n_poses, self.kb, stride=cv.get("stride", 8),
-                              upsample_ratio=self.pipe.ratio, pad=pad, scale=scale,
-                              out=(self.pose_kpts, self.bbox, self.confidence))
+                              upsample_ratio=self.pipe.ratio, out=(self.pose_kpts, self.bbox, self.confidence),
+                              xform=self._xform)
 
 
 class _Slot:

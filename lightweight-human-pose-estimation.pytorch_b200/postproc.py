@@ -211,7 +211,19 @@ def group_keypoints_fused(kb, maps, ratio, channel_offset=19, demo=False, min_pa
     return pose_entries, n_poses
 
 
-def pose_convert(pose_entries, n_poses, kb, stride=8, upsample_ratio=4, pad=(0, 0, 0, 0), scale=1.0, out=None):
+def pose_convert_xform(n, pad, scale, device):
+    """Per-image (left pad, top pad, scale) table of pose_convert on the device.  Uploading it is a pageable, host-blocking
+    copy: callers that convert every batch with the same geometry (PosePipeline) build it once."""
+    pads = np.asarray(pad, np.float64).reshape(-1, 4)
+    scales = np.asarray(scale, np.float64).reshape(-1)
+    xf = np.empty((n, 3), np.float64)
+    xf[:, 0] = pads[:, 1] if pads.shape[0] == n else pads[0, 1]
+    xf[:, 1] = pads[:, 0] if pads.shape[0] == n else pads[0, 0]
+    xf[:, 2] = scales if scales.shape[0] == n else scales[0]
+    return torch.from_numpy(xf).to(device)
+
+
+def pose_convert(pose_entries, n_poses, kb, stride=8, upsample_ratio=4, pad=(0, 0, 0, 0), scale=1.0, out=None, xform=None):
     """Batched result post-conversion on the device (reference demo.py:101-115 + modules/pose.py:30-39).
     pose_entries float64 [n, cap, 20] / n_poses int32 [n] as returned by group_keypoints_*; kb: the KeypointBatch.
     pad = [top, left, bottom, right] and scale as returned by infer_fast -- one pair for the whole batch, or per-image
@@ -219,13 +231,8 @@ def pose_convert(pose_entries, n_poses, kb, stride=8, upsample_ratio=4, pad=(0, 
     L = _lib.load()
     n, cap = pose_entries.shape[0], pose_entries.shape[1]
     dev = pose_entries.device
-    pads = np.asarray(pad, np.float64).reshape(-1, 4)
-    scales = np.asarray(scale, np.float64).reshape(-1)
-    xf = np.empty((n, 3), np.float64)
-    xf[:, 0] = pads[:, 1] if pads.shape[0] == n else pads[0, 1]
-    xf[:, 1] = pads[:, 0] if pads.shape[0] == n else pads[0, 0]
-    xf[:, 2] = scales if scales.shape[0] == n else scales[0]
-    xform = torch.from_numpy(xf).to(dev)
+    if xform is None:
+        xform = pose_convert_xform(n, pad, scale, dev)
     if out is None:
         out = (torch.empty((n, cap, NUM_KPT_TYPES, 2), dtype=torch.int32, device=dev),
                torch.empty((n, cap, 4), dtype=torch.int32, device=dev),
