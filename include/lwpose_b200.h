@@ -89,6 +89,15 @@ typedef struct lwp_keypoint {
  */
 int lwp_upsample_cubic(const float *src, int n, int h, int w, int c, int src_ld, float *dst, int H, int W,
                        double inv_scale_x, double inv_scale_y, void *stream);
+/*
+ * The same resize with (a) a source that is a cropped VIEW of a larger map -- rows src_row_pitch floats apart, images
+ * src_img_pitch floats apart (val.py:99,106 crop the x8 maps before resizing them to the image size) -- and (b) an optional
+ * running-average destination: accumulate_divisor != 0 makes it dst += resized / accumulate_divisor in float32, one
+ * rounding per operation (val.py:101,108: avg_heatmaps = avg_heatmaps + heatmaps / len(scales)); 0 = plain store.
+ */
+int lwp_upsample_cubic_ex(const float *src, int n, int h, int w, int c, int src_ld, long long src_row_pitch,
+                          long long src_img_pitch, float *dst, int H, int W, double inv_scale_x, double inv_scale_y,
+                          float accumulate_divisor, void *stream);
 
 /* bytes of scratch lwp_extract_keypoints needs */
 size_t lwp_extract_workspace_bytes(int n, int n_ch, int cap_candidates);

@@ -19,6 +19,8 @@ SIGNATURES = {
     "lwp_check_device": (_c_int, [_c_int]),
     "lwp_resize_pad_u8": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                    _c_double, _c_double, _c_int, _c_int, _c_int, _c_void_p]),
+    "lwp_upsample_cubic_ex": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, ctypes.c_longlong, ctypes.c_longlong,
+                                       _c_void_p, _c_int, _c_int, _c_double, _c_double, ctypes.c_float, _c_void_p]),
     "lwp_upsample_cubic": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_int,
                                     _c_double, _c_double, _c_void_p]),
     "lwp_extract_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),

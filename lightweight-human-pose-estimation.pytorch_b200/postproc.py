@@ -23,27 +23,35 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
-def upsample_cubic(src, channels=None, fx=None, fy=None, dsize=None, out=None, channel_offset=0):
+def upsample_cubic(src, channels=None, fx=None, fy=None, dsize=None, out=None, channel_offset=0, crop=None,
+                   accumulate_divisor=None):
     """src: float32 cuda tensor [n, h, w, ld] (NHWC; channels [channel_offset, channel_offset + channels)
     of every pixel are resized).  Either fx/fy (like cv2.resize(src, (0, 0), fx=, fy=)) or dsize=(W, H).
+    crop=(top, left, bottom, right): resize src[:, top:h-bottom, left:w-right] without copying it (val.py:99,106);
+    accumulate_divisor=k (with out=): out += resized / k in float32 (the running average of val.py:101,108).
     Returns [n, H, W, channels] float32."""
     L = _lib.load()
     assert src.is_cuda and src.dtype == torch.float32 and src.dim() == 4 and src.is_contiguous()
     n, h, w, ld = src.shape
     c = ld - channel_offset if channels is None else int(channels)
     assert 0 <= channel_offset and channel_offset + c <= ld
+    top, left, bottom, right = (0, 0, 0, 0) if crop is None else [int(v) for v in crop]
+    hc, wc = h - top - bottom, w - left - right
+    assert hc > 0 and wc > 0
     if dsize is None:
         inv_x, inv_y = float(fx), float(fy)
-        W, H = int(np.rint(w * inv_x)), int(np.rint(h * inv_y))
+        W, H = int(np.rint(wc * inv_x)), int(np.rint(hc * inv_y))
     else:
         W, H = int(dsize[0]), int(dsize[1])
-        inv_x, inv_y = W / w, H / h
+        inv_x, inv_y = W / wc, H / hc
     if out is None:
+        assert accumulate_divisor is None
         out = torch.empty((n, H, W, c), dtype=torch.float32, device=src.device)
     else:
         assert out.shape == (n, H, W, c) and out.is_contiguous() and out.dtype == torch.float32
-    _lib.check(L.lwp_upsample_cubic(_ptr(src) + 4 * channel_offset, n, h, w, c, ld, _ptr(out), H, W, inv_x, inv_y,
-                                    _lib.current_stream()), "lwp_upsample_cubic")
+    _lib.check(L.lwp_upsample_cubic_ex(_ptr(src) + 4 * (channel_offset + (top * w + left) * ld), n, hc, wc, c, ld, w * ld, h * w * ld,
+                                       _ptr(out), H, W, inv_x, inv_y, float(accumulate_divisor or 0.0), _lib.current_stream()),
+               "lwp_upsample_cubic")
     return out
 
 

@@ -52,19 +52,17 @@ def infer(net, img, scales, base_height, stride, pad_value=(0, 0, 0), img_mean=(
     normed = normalize(img, img_mean, img_scale)
     height, width = normed.shape[0], normed.shape[1]
     ratios = [s * base_height / float(height) for s in scales]
-    avg_h = torch.zeros((height, width, 19), dtype=torch.float32, device="cuda")
-    avg_p = torch.zeros((height, width, 38), dtype=torch.float32, device="cuda")
-    count = torch.tensor(float(len(ratios)), dtype=torch.float32, device="cuda")
+    avg_h = torch.zeros((1, height, width, 19), dtype=torch.float32, device="cuda")
+    avg_p = torch.zeros((1, height, width, 38), dtype=torch.float32, device="cuda")
     for ratio in ratios:
         scaled = cv2.resize(normed, (0, 0), fx=ratio, fy=ratio, interpolation=cv2.INTER_CUBIC)
         padded, pad = pad_width(scaled, stride, pad_value, [base_height, max(scaled.shape[1], base_height)])
         heads = _heads_on_device(net, padded)
         for off, ch, avg in ((0, 19, avg_h), (19, 38, avg_p)):
             up = postproc.upsample_cubic(heads, channels=ch, fx=stride, fy=stride, channel_offset=off)
-            crop = up[:, pad[0]:up.shape[1] - pad[2], pad[1]:up.shape[2] - pad[3], :].contiguous()
-            full = postproc.upsample_cubic(crop, dsize=(width, height))
-            avg.add_(torch.div(full[0], count))  # avg = avg + maps / len(scales), float32 true division
-    return avg_h.cpu().numpy(), avg_p.cpu().numpy()
+            # crop (a view), resize to the image size and avg = avg + maps / len(scales) (float32 true division) in one kernel
+            postproc.upsample_cubic(up, dsize=(width, height), crop=pad, out=avg, accumulate_divisor=len(ratios))
+    return avg_h[0].cpu().numpy(), avg_p[0].cpu().numpy()
 
 
 def convert_to_coco_format(pose_entries, all_keypoints):
@@ -124,7 +122,6 @@ def infer_batch(net, frames, scales, base_height, stride, img_mean=(128, 128, 12
     normed = ((x8.float() - mean) * float(img_scale)).contiguous()          # exact in float32 for uint8 pixels
     avg_h = torch.zeros((B, height, width, 19), dtype=torch.float32, device=dev)
     avg_p = torch.zeros((B, height, width, 38), dtype=torch.float32, device=dev)
-    count = torch.tensor(float(len(scales)), dtype=torch.float32, device=dev)
     eng = net.engine()
     for ratio, (hs, ws), (H, W), pad in scale_geometry(height, width, scales, base_height, stride):
         scaled = postproc.upsample_cubic(normed, channels=3, fx=ratio, fy=ratio)
@@ -138,10 +135,9 @@ def infer_batch(net, frames, scales, base_height, stride, img_mean=(128, 128, 12
         heads = plan.heads_f32[-1].view(B, H // 8, W // 8, HEAD_LD)
         for off, ch, avg in ((0, 19, avg_h), (19, 38, avg_p)):
             up = postproc.upsample_cubic(heads, channels=ch, fx=stride, fy=stride, channel_offset=off)
-            crop = up[:, pad[0]:up.shape[1] - pad[2], pad[1]:up.shape[2] - pad[3], :].contiguous()
-            full = postproc.upsample_cubic(crop, dsize=(width, height))
-            avg.add_(torch.div(full, count))
-            del up, crop, full
+            # crop (a view: no copy), resize to the frame size and avg += resized / len(scales) in ONE kernel
+            postproc.upsample_cubic(up, dsize=(width, height), crop=pad, out=avg, accumulate_divisor=len(scales))
+            del up
     return avg_h, avg_p
 
 
