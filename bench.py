@@ -523,7 +523,7 @@ def config4(args, net, dev, rank, world, barrier):
     import numpy as np
     import torch
     from lwpose_b200 import parallel, postproc, synth, val
-    Hf, Wf, chunk = 480, 640, 8
+    Hf, Wf, chunk = 480, 640, int(os.environ.get("LWP_CONFIG4_CHUNK", "16"))
     scales = [0.5, 1.0, 1.5, 2.0]
     lo, hi = parallel.shard_range(args.config4_frames, rank, world)
     per = hi - lo
