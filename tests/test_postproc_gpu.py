@@ -45,6 +45,44 @@ def test_upsample_strided_source_and_batch(torch_cuda):
         assert np.array_equal(got[b].view(np.int32), ref.view(np.int32))
 
 
+@pytest.mark.parametrize("ratio", [2, 4, 8])
+def test_upsample_pow2_kernel_equals_generic_kernel_and_oracle(torch_cuda, ratio, monkeypatch):
+    """The periodic-geometry kernel for x2 / x4 / x8 (one thread = one channel of one source cell, R x R outputs), the generic
+    materialising kernel and the oracle agree bit for bit (19- and 38-channel layouts out of a 64-wide pixel, odd sizes)."""
+    torch = torch_cuda
+    from lwpose_b200 import postproc
+    from oracle import postproc as orc
+    rng = np.random.default_rng(17 + ratio)
+    src = rng.standard_normal((2, 23, 41, 64)).astype(np.float32)
+    d = torch.from_numpy(src).cuda()
+    for off, ch in ((0, 19), (19, 38)):
+        monkeypatch.delenv("LWP_UPSAMPLE_GENERIC", raising=False)
+        fast = postproc.upsample_cubic(d, channels=ch, fx=ratio, fy=ratio, channel_offset=off).cpu().numpy()
+        monkeypatch.setenv("LWP_UPSAMPLE_GENERIC", "1")
+        slow = postproc.upsample_cubic(d, channels=ch, fx=ratio, fy=ratio, channel_offset=off).cpu().numpy()
+        assert np.array_equal(fast.view(np.int32), slow.view(np.int32))
+        ref = orc.resize_cubic(np.ascontiguousarray(src[0, :, :, off:off + ch]), fx=ratio, fy=ratio)
+        assert np.array_equal(fast[0].view(np.int32), ref.view(np.int32))
+
+
+def test_upsample_cropped_view_and_running_average(torch_cuda):
+    """lwp_upsample_cubic_ex: resizing a cropped VIEW equals resizing the cropped copy, and the accumulate mode equals
+    avg + resized / k in float32 (val.py:99-101), bit for bit."""
+    torch = torch_cuda
+    from lwpose_b200 import postproc
+    rng = np.random.default_rng(23)
+    d = torch.from_numpy(rng.standard_normal((2, 40, 56, 38)).astype(np.float32)).cuda()
+    pad = (3, 5, 2, 7)
+    crop = d[:, pad[0]:40 - pad[2], pad[1]:56 - pad[3], :].contiguous()
+    ref = postproc.upsample_cubic(crop, dsize=(61, 47))
+    got = postproc.upsample_cubic(d, dsize=(61, 47), crop=pad)
+    assert torch.equal(ref.view(torch.int32), got.view(torch.int32))
+    avg = torch.from_numpy(rng.standard_normal((2, 47, 61, 38)).astype(np.float32)).cuda()
+    want = avg + torch.div(ref, torch.tensor(4.0, device="cuda"))
+    postproc.upsample_cubic(d, dsize=(61, 47), crop=pad, out=avg, accumulate_divisor=4)
+    assert torch.equal(want.view(torch.int32), avg.view(torch.int32))
+
+
 def _device_postproc(torch, hm, paf, demo, cap_kpts=256, cap_cand=4096, cap_poses=256, cap_conn=4096):
     from lwpose_b200 import postproc
     hm_d = torch.from_numpy(np.ascontiguousarray(hm.transpose(0, 2, 3, 1))).cuda()
