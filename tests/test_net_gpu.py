@@ -463,18 +463,24 @@ def test_sepconv_network(env, monkeypatch):
         assert _rel(y.cpu(), ref) < NET_TOL["bf16"] * gain, i
 
 
-@pytest.mark.parametrize("precision,R", [("bf16", 1), ("tf32", 2)])
-def test_c_entry_points_run_the_network_without_the_python_engine(env, precision, R, tmp_path):
+@pytest.mark.parametrize("precision,R,shape", [("bf16", 1, (2, 64, 96)), ("tf32", 2, (2, 64, 96)), ("bf16", 2, (1, 128, 192))],
+                         ids=["bf16-R1", "tf32-R2", "bf16-R2-fused-blocks"])
+def test_c_entry_points_run_the_network_without_the_python_engine(env, precision, R, shape, tmp_path, monkeypatch):
     """lwp_net_load / lwp_net_forward / lwp_net_heads (the three-call C API): a blob exported once from the module
     gives, through ctypes only, bit-identical heads and NCHW outputs to the Python engine; lwp_postprocess on those
     heads gives the same tables as the two-call form; the on-disk cache is keyed by the checkpoint hash."""
     torch, _lib, engine = env
     from lwpose_b200 import cnet, postproc, synth
-    B, H, W = 2, 64, 96
+    B, H, W = shape
+    if H * W >= 128 * 192:   # large enough for the strip kernel: the blob then carries the fused 3x3 + 1x1 ops, and (opted in
+        monkeypatch.setenv("LWP_FRONTEND_FUSION", "1")   # here) the fused front end, i.e. every op kind of the blob format
     net = _build_net(torch, "c", R, 4.0).cuda()
     net.precision = precision
     x = synth.synthetic_net_input(B, H, W, seed=9).cuda()
     want = [o.clone() for o in net(x)]
+    if H * W >= 128 * 192:
+        names = net.engine().plan(precision, B, H, W).op_names
+        assert names[0] == "model.0-2.frontend" and any("trunk.1+" in nm for nm in names)
     want_heads = net.engine().plan(precision, B, H, W).heads_f32[-1].view(B, H // 8, W // 8, 64).clone()
     path = cnet.cached_blob(net, precision, B, H, W, cache_dir=str(tmp_path))
     assert cnet.cached_blob(net, precision, B, H, W, cache_dir=str(tmp_path)) == path and len(list(tmp_path.iterdir())) == 1
