@@ -198,7 +198,8 @@ def _all_tensors(obj, out, seen):
 class Plan:
     """One recorded launch list + its buffers for a fixed (precision, N, H, W)."""
 
-    def __init__(self, packed, precision, n, H, W, n_stages_out, num_heatmaps, num_pafs, device, input_u8=None):
+    def __init__(self, packed, precision, n, H, W, n_stages_out, num_heatmaps, num_pafs, device, input_u8=None,
+                 double_heads=False):
         if H % 8 or W % 8:
             raise ValueError("input height/width must be multiples of 8 (got %dx%d)" % (H, W))
         self.call_log = []
@@ -212,6 +213,11 @@ class Plan:
         self.packed = packed  # keeps the packed weights alive
         # input_u8 = (mean3, scale): the stem reads uint8 [n,H,W,3] frames and applies val.normalize on the fly
         self.input_u8 = input_u8
+        # double_heads: the last stage's heads op is recorded a second time (at the END of the op list) writing to a second
+        # float32 buffer; run_compute(x, alt=1) runs that one instead.  PosePipeline alternates between the two so the
+        # post-processing of batch i can still read its heads while the network of batch i + 1 runs -- without a copy.
+        self.double_heads = bool(double_heads)
+        self.heads_alt = None
         handle = _lib._c_void_p()
         _lib.check(self.lib.lwp_plan_create(code, handle), "lwp_plan_create")
         self.handle = handle
@@ -497,8 +503,9 @@ class Plan:
         for i, g in enumerate(P.init_trunk):
             self._gemm("initial_stage.trunk.%d" % i, srcs[i][0], srcs[i][1], g, n, h, w, out=dsts[i], out_ld=nc)
         more = len(P.refine) > 0
-        self._heads("initial_stage.heads", t0, nc, P.init_heads, n, h, w, big, concat if more else None, nc,
-                    self.heads_f32[0])
+        last_heads = ("initial_stage.heads", t0, nc, P.init_heads, n, h, w, big, concat if more else None, nc)
+        i_last = len(self.op_names)
+        self._heads(*last_heads, self.heads_f32[0])
         # refinement stages
         # bf16 plans: the second 3x3 of block k (+ residual) and the `initial` 1x1 of block k + 1 run as ONE kernel
         # (lwp_plan_add_conv3x3_pw: the block output never leaves tensor memory); LWP_CONV3_PW=0 keeps the two ops
@@ -537,9 +544,11 @@ class Plan:
                            residual=cur_i, res_ld=nc)  # initial_features + trunk_features
                 src, src_ld = dst, nc
             more = s + 1 < len(P.refine)
-            self._heads("refinement_stages.%d.heads" % s, src, nc, heads, n, h, w, big, concat if more else None, nc,
-                        self.heads_f32[s + 1])
+            last_heads = ("refinement_stages.%d.heads" % s, src, nc, heads, n, h, w, big, concat if more else None, nc)
+            i_last = len(self.op_names)
+            self._heads(*last_heads, self.heads_f32[s + 1])
         self.num_compute_ops = len(self.op_names)
+        self._last_heads, self._last_heads_span = last_heads, (i_last, self.num_compute_ops)
         # NCHW float32 tensors handed back by forward()
         self.outputs = []
         for s in range(n_stages_out):
@@ -552,6 +561,12 @@ class Plan:
                 self.op_names.append("to_nchw.%d" % s)
                 self.op_meta.append(dict(kind="layout", flops=0.0, bytes=float(2 * n * cc * h * w * 4)))
             self.outputs += [hm, paf]
+        self._alt_span = None
+        if self.double_heads:
+            self.heads_alt = self._buf(px * HEAD_LD, dtype=torch.float32, zero=True)
+            a0 = len(self.op_names)
+            self._heads(*self._last_heads, self.heads_alt)
+            self._alt_span = (a0, len(self.op_names))
 
     # -- export -------------------------------------------------------------------------------
     def export_blob(self):
@@ -617,9 +632,14 @@ class Plan:
         _lib.check(self.lib.lwp_plan_run_range(self.handle, x.data_ptr(), first, last, _lib.current_stream()),
                    "lwp_plan_run")
 
-    def run_compute(self, x):
-        """All layers, without the NCHW hand-off copies (the fused pipeline reads heads_f32 directly)."""
-        self.run(x, 0, self.num_compute_ops)
+    def run_compute(self, x, alt=0):
+        """All layers, without the NCHW hand-off copies (the fused pipeline reads heads_f32 directly).  alt=1 (plans built
+        with double_heads): the last stage's heads go to self.heads_alt instead of self.heads_f32[-1]."""
+        if alt and self._alt_span is not None:
+            self.run(x, 0, self._last_heads_span[0])
+            self.run(x, self._alt_span[0], self._alt_span[1])
+        else:
+            self.run(x, 0, self.num_compute_ops)
 
     def error_flag(self):
         return self.lib.lwp_plan_error_flag(self.handle)
@@ -647,14 +667,14 @@ class NetEngine:
         self._packed = {}
         self._plans = collections.OrderedDict()
 
-    def new_plan(self, precision, n, H, W, input_u8=None):
+    def new_plan(self, precision, n, H, W, input_u8=None, double_heads=False):
         """A private, uncached plan (own activation buffers): every PosePipeline chunk takes one, so two pipelines
         (or a pipeline and net.forward) of the same shape never share buffers across streams; it lives as long as
         its owner."""
         net = self.net
         with torch.cuda.device(self.device):
             return Plan(self.packed(precision), precision, n, H, W, 1 + len(net.refinement_stages),
-                        net.num_heatmaps, net.num_pafs, self.device, input_u8=input_u8)
+                        net.num_heatmaps, net.num_pafs, self.device, input_u8=input_u8, double_heads=double_heads)
 
     def packed(self, precision):
         if precision not in _PREC:

@@ -77,7 +77,11 @@ class _Chunk:
         self.pipe, self.lo, self.n = pipe, lo, n
         dev = pipe.device
         eng = pipe.net.engine()
-        self.plan = eng.new_plan(pipe.precision, n, pipe.H, pipe.W, input_u8=pipe.input_u8)   # private buffers
+        # private buffers; with the post-processing on its own stream the plan writes the last stage's heads alternately
+        # into two buffers, so post-processing (batch i) and network (batch i + 1) never touch the same one -- no copy
+        self.double = bool(pipe.overlap_postproc and not pipe.graph)
+        self.plan = eng.new_plan(pipe.precision, n, pipe.H, pipe.W, input_u8=pipe.input_u8, double_heads=self.double)
+        self._alt, self._last_alt = 0, 0
         ck, cc, cp, cn = pipe.caps
         L = pipe.L
         if not pipe.fused:
@@ -88,27 +92,34 @@ class _Chunk:
         self.n_poses = torch.empty((n,), dtype=torch.int32, device=dev)
         self.ws_extract = torch.empty((L.lwp_extract_workspace_bytes(n, 18, cc),), dtype=torch.uint8, device=dev)
         self.ws_group = torch.empty((L.lwp_group_workspace_bytes(n, ck, cn, cp),), dtype=torch.uint8, device=dev)
-        # the post-processing runs on its own stream on a private copy of the heads, so the network of the next
-        # batch (which overwrites the plan's head buffer) can start while this batch is still being grouped
-        self.heads_pp = torch.empty((n, pipe.h, pipe.w, HEAD_LD), dtype=torch.float32, device=dev)
         if pipe.convert is not None:
             self.pose_kpts = torch.empty((n, cp, postproc.NUM_KPT_TYPES, 2), dtype=torch.int32, device=dev)
             self.bbox = torch.empty((n, cp, 4), dtype=torch.int32, device=dev)
             self.confidence = torch.empty((n, cp), dtype=torch.float64, device=dev)
         self.net_done = torch.cuda.Event()
-        self.pp_done = torch.cuda.Event()
+        self.pp_done_buf = [torch.cuda.Event(), torch.cuda.Event()]   # post-processing that read heads buffer 0 / 1 has finished
+        self.pp_done = self.pp_done_buf[0]                            # ... of the most recent batch
+
+    def _heads_buf(self, alt):
+        t = self.plan.heads_alt if alt else self.plan.heads_f32[-1]
+        return t.view(self.n, self.pipe.h, self.pipe.w, HEAD_LD)
 
     @property
     def heads(self):
-        return self.plan.heads_f32[-1].view(self.n, self.pipe.h, self.pipe.w, HEAD_LD)
+        """The heads of the most recent pass."""
+        return self._heads_buf(self._last_alt)
 
     def enqueue(self, x_dev):
         """One pass of the hot path for this chunk: network on the current stream, post-processing on the
         pipeline's post-processing stream (ordered after it by events)."""
         pipe = self.pipe
         cur = torch.cuda.current_stream()
-        self.plan.run_compute(x_dev)
-        heads = self.heads
+        alt = self._alt if self.double else 0
+        if self.double:
+            cur.wait_event(self.pp_done_buf[alt])   # the post-processing that last read this heads buffer (two batches ago)
+        self.plan.run_compute(x_dev, alt)
+        self._last_alt = alt
+        heads = self._heads_buf(alt)
         if pipe.heads_hook is not None:
             pipe.heads_hook(heads, self.lo)
         if pipe.graph:   # one stream, no events: the whole pass is (or is being captured into) one CUDA graph
@@ -118,13 +129,13 @@ class _Chunk:
             self.enqueue_postproc(heads)
             self.pp_done.record(cur)
             return
-        cur.wait_event(self.pp_done)          # the previous batch's post-processing has finished reading heads_pp
-        self.heads_pp.copy_(heads)
         self.net_done.record(cur)
         with torch.cuda.stream(pipe.pp_stream):
             pipe.pp_stream.wait_event(self.net_done)
-            self.enqueue_postproc(self.heads_pp)
+            self.enqueue_postproc(heads)
+            self.pp_done = self.pp_done_buf[alt]
             self.pp_done.record(pipe.pp_stream)
+        self._alt ^= 1
 
     def enqueue_postproc(self, heads, stage=None):
         pipe = self.pipe
@@ -386,7 +397,7 @@ class PosePipeline:
                     slot.h_counts[sl].copy_(c.kb.counts, non_blocking=True)
                     slot.h_kpt_start[sl].copy_(c.kb.kpt_start, non_blocking=True)
                     slot.h_overflow[sl].copy_(c.kb.overflow, non_blocking=True)
-                    src = c.heads_pp if (self.overlap_postproc and not self.graph) else c.heads
+                    src = c.heads
                     _lib.check(self.L.lwp_copy_flagged(src.data_ptr(), slot.heads_keep[sl].data_ptr(), c.kb.overflow.data_ptr(),
                                                        c.n, self.h * self.w * HEAD_LD * 4, _lib.current_stream()),
                                "lwp_copy_flagged")

@@ -36,7 +36,7 @@ def main():
                 pipe.run_device(x)
                 torch.cuda.synchronize()
                 torch.cuda.profiler.start()
-            c.enqueue_postproc(c.heads_pp if pipe.overlap_postproc and not pipe.graph else c.heads)
+            c.enqueue_postproc(c.heads)
         else:
             i = plan.op_names.index(nm)
             plan.run(x, i, i + 1)
