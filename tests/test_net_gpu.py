@@ -579,3 +579,28 @@ def test_conv3x3_pw_fused_bit_identical_to_two_ops(env, case, monkeypatch):
     for s, (ha, hb) in enumerate(zip(ref.heads_f32, fused.heads_f32)):
         a, b = ha.view(torch.int32), hb.view(torch.int32)
         assert torch.equal(a, b), (s, int((a != b).sum()), float((ha - hb).abs().max()))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_double_heads_plan_writes_identical_heads_to_both_buffers(env, precision):
+    """Plan(double_heads=True) (what every PosePipeline chunk uses): run_compute(x, alt=1) runs the same network but its
+    last stage writes to heads_alt -- bit-identical to heads_f32[-1] of the alt=0 pass, and the other buffer is untouched."""
+    torch, _lib, engine = env
+    from lwpose_b200 import synth
+    n, H, W = 2, 128, 192
+    net = _build_net(torch, "dh", 1, 1.0).cuda()
+    eng = engine.NetEngine(net)
+    plan = eng.new_plan(precision, n, H, W, double_heads=True)
+    xa = synth.synthetic_net_input(n, H, W, seed=1).cuda()
+    xb = synth.synthetic_net_input(n, H, W, seed=2).cuda()
+    plan.run_compute(xa, 0)
+    torch.cuda.synchronize()
+    a0 = plan.heads_f32[-1].clone()
+    plan.run_compute(xb, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(plan.heads_f32[-1], a0)                  # the alt pass left buffer 0 alone
+    b1 = plan.heads_alt.clone()
+    plan.run_compute(xb, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(plan.heads_f32[-1].view(torch.int32), b1.view(torch.int32))
+    assert not torch.equal(a0, b1) and plan.error_flag() == 0
