@@ -63,6 +63,7 @@ struct GemmParams {
   int act2;
   int staging_bufs;        // 1 or 2 staging buffers per epilogue warp (2: the next chunk is converted while the
                            // tensor store of the previous one still reads its buffer); conv_gemm_kernel only
+  int wres_sub;            // conv_gemm_wres_kernel: 128-pixel tiles per pipeline stage (0 = another kernel runs the layer)
 };
 
 constexpr int kStagingBytes = kEpiWarps * kStageOutBytes;  // one staging buffer per epilogue warp
@@ -84,6 +85,11 @@ int conv_gemm3_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB,
                       const GemmParams &p, int grid, cudaStream_t st);
 int conv_gemm3_pw_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const CUtensorMap &tmW2,
                          const GemmParams &p, int grid, cudaStream_t st);
+// weight-resident thin 1x1 layers, several M tiles per stage (conv_gemm_wres.cu)
+size_t conv_gemm_wres_smem_bytes(const GemmParams &p);
+int conv_gemm_wres_init();
+int conv_gemm_wres_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+                          const GemmParams &p, int grid, cudaStream_t st);
 size_t conv_gemm2_smem_bytes(const GemmParams &p);
 int conv_gemm2_init();
 int conv_gemm2_launch(bool tf32, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,

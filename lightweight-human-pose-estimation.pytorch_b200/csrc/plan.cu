@@ -252,7 +252,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   Op op;
   op.kind = OP_GEMM;
   GemmParams &g = op.gp;
-  g.fuse_pw = 0; g.scale2 = nullptr; g.shift2 = nullptr; g.act2 = 0;
+  g.fuse_pw = 0; g.scale2 = nullptr; g.shift2 = nullptr; g.act2 = 0; g.wres_sub = 0;
   g.taps = taps; g.dil = dilation; g.cin = Cin; g.kb_elems = kb_elems; g.kb_bytes = kb_bytes;
   g.kblocks_per_tap = (Cin + kb_elems - 1) / kb_elems;
   g.cout_pad = cout_pad;
@@ -349,6 +349,37 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
       long long gr = 2 * pairs;
       const int cap = num_sms() / 2 * 2;
       op.grid = (int)(gr < cap ? gr : cap);
+    }
+  }
+
+  // thin 1x1 layers (whole weight matrix <= 32 KB, one N tile): weights resident in shared memory, S = 256 / N tiles
+  // per pipeline stage (conv_gemm_wres.cu).  LWP_GEMM_WRES=0 never, 1 every eligible layer, unset: single-K-block layers
+  // with enough super-tiles per SM that the coarser work unit does not cost a tail (measured, 64 x 368x656 bf16:
+  // 32->64 165 -> 129 us, 64->128 72 -> 65 us; two-K-block layers +-1 us: 128->128 @92x164 88 -> 90, Cpm trunk 32 -> 31)
+  {
+    const char *ew = getenv("LWP_GEMM_WRES");
+    const int mode = ew ? atoi(ew) : -1;
+    const bool plain = out != nullptr && out_f32 == nullptr && g.n_store % (kKBlockBytes / es) == 0 &&
+                       getenv("LWP_NO_TMA_STORE") == nullptr;
+    if (mode != 0 && taps == 1 && plain && !op.two_cta && g.n_tiles == 1 && g.block_n <= 128 && g.kblocks_per_tap <= 2 &&
+        Cin % kb_elems == 0) {
+      GemmParams w = g;
+      w.wres_sub = 256 / g.block_n;
+      w.kbps = 1;
+      w.acc_stages = 2;
+      const int wres_stage = w.wres_sub * w.kblocks_per_tap * kBlockM * kb_bytes;
+      const int b_bytes = (w.kblocks_per_tap * g.block_n * kb_bytes + 1023) / 1024 * 1024;
+      int st = (gemm_smem_cap() - 2048 - kStagingBytes - b_bytes - 2 * cout_pad * 4 - 512) / wres_stage;
+      if (st > kMaxStages) st = kMaxStages;
+      if (const char *sv = getenv("LWP_GEMM_STAGES")) { int v = atoi(sv); if (v >= 2 && v < st) st = v; }
+      w.num_stages = st;
+      const long long supers = ((long long)g.m_tiles + w.wres_sub - 1) / w.wres_sub;
+      const int min_per_sm = mode > 1 ? mode : 16;
+      if (st >= 2 && (mode == 1 || (w.kblocks_per_tap == 1 && supers >= (long long)min_per_sm * num_sms())) &&
+          conv_gemm_wres_init() == LWP_OK) {
+        g = w;
+        op.grid = (int)(supers < num_sms() ? supers : num_sms());
+      }
     }
   }
 
@@ -782,6 +813,7 @@ extern "C" int lwp_plan_run_range(lwp_plan *p, const void *x, int first, int las
         rc = op.gp.fuse_pw ? conv_gemm3_pw_launch(op.tmA, op.tmB, op.tmC, op.tmD, op.gp, op.grid, st)
              : op.strips  ? conv_gemm3_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st)
              : op.two_cta ? conv_gemm2_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st)
+             : op.gp.wres_sub ? conv_gemm_wres_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st)
                           : conv_gemm_launch(f32, op.tmA, op.tmB, op.tmC, op.gp, op.grid, st);
         break;
       case OP_DWPW:

@@ -413,6 +413,83 @@ def test_cta_pair_gemm_network(env, precision, monkeypatch):
         assert _rel(y.cpu(), ref) < tol, i
 
 
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("shape", [
+    # (n, H, W, Cin, Cout, act, residual)
+    (1, 23, 41, 32, 64, 1, False),       # 8 tiles (ragged last one) = 2 super-tiles of 4
+    (3, 23, 41, 32, 64, 1, False),       # 23 tiles: the last super-tile holds 3
+    (2, 23, 41, 64, 128, 1, False),      # one 128-byte K block (bf16), two chunks per tile
+    (2, 23, 41, 128, 128, 2, True),      # two K blocks (bf16), ELU + residual (the Cpm trunk's last 1x1)
+    (1, 46, 82, 128, 128, 1, False),
+    (31, 92, 164, 32, 64, 1, False),     # > stages super-tiles per CTA: the stage ring and both accumulator stages wrap
+    (9, 92, 164, 64, 128, 0, False),
+])
+def test_conv_gemm_wres_vs_torch_and_generic_kernel(env, precision, shape, monkeypatch):
+    """conv_gemm_wres_kernel (weights resident in shared memory, several 128-pixel tiles per pipeline stage), forced on
+    with LWP_GEMM_WRES=1: against torch fp64 on operands rounded to the storage type, and bit-identical to
+    conv_gemm_kernel (LWP_GEMM_WRES=0) -- both issue the same MMAs in the same order."""
+    torch, _lib, engine = env
+    n, H, W, Cin, Cout, act, use_res = shape
+    tdtype = engine._PREC[precision][1]
+    if precision == "tf32" and Cin > 64:
+        pytest.skip("more than two fp32 K blocks: the generic kernel runs this layer")
+    g = torch.Generator().manual_seed(hash(shape) % (2 ** 31))
+    x = torch.randn(n, Cin, H, W, generator=g)
+    wt = torch.randn(Cout, Cin, 1, 1, generator=g) * (1.0 / np.sqrt(Cin))
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g) * 0.1
+    res = torch.randn(n, Cout, H, W, generator=g) if use_res else None
+    xq, wq = x.to(tdtype).float(), wt.to(tdtype).float()
+    ref = torch.nn.functional.conv2d(xq.double(), wq.double()).float()
+    ref = ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    ref = torch.relu(ref) if act == 1 else torch.nn.functional.elu(ref) if act == 2 else ref
+    if use_res:
+        ref = ref + res.to(tdtype).float()
+    gw = engine._GemmW(wt.cuda(), scale.cuda(), shift.cuda(), act, tdtype, 1)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(tdtype).cuda()
+    resd = res.permute(0, 2, 3, 1).contiguous().to(tdtype).cuda() if use_res else None
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LWP_GEMM_WRES", mode)
+        out = torch.full((n, H, W, gw.cout_pad), 7.0, dtype=tdtype, device="cuda")
+        p = OnePlan(env, precision)
+        _lib.check(p.L.lwp_plan_add_conv_gemm(p.h, xd.data_ptr(), Cin, gw.w.data_ptr(), gw.scale.data_ptr(),
+                                              gw.shift.data_ptr(), resd.data_ptr() if use_res else None, Cout,
+                                              out.data_ptr(), gw.cout_pad, None, 0, n, H, W, Cin, Cout, 1, 1, act), "add")
+        p.run()
+        p.close()
+        outs[mode] = out
+    assert torch.equal(outs["1"], outs["0"]), "weight-resident kernel differs from conv_gemm_kernel"
+    got = outs["1"][..., :Cout].permute(0, 3, 1, 2).float().cpu()
+    tol = 6e-3 if precision == "tf32" else 2e-2
+    assert _rel(got, ref) < tol * max(1.0, float(ref.abs().max())), _rel(got, ref)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_wres_gemm_network(env, precision, monkeypatch):
+    """Every structurally eligible 1x1 layer on the weight-resident kernel (LWP_GEMM_WRES=1, also the layers the
+    default policy leaves on conv_gemm_kernel because they have too few tiles): the whole network still matches the
+    reference golden outputs, and its heads are bit-identical to a plan built with LWP_GEMM_WRES=0."""
+    torch, _lib, engine = env
+    from lwpose_b200 import synth
+    name, R, H, W, B, gain = gc.net_cases()[1]
+    g = gc.load("net_golden.npz")
+    x = synth.synthetic_net_input(B, H, W, seed=3).cuda()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LWP_GEMM_WRES", mode)
+        net = _build_net(torch, name, R, gain).cuda()
+        net.precision = precision
+        res[mode] = [y.clone() for y in net(x)]
+        torch.cuda.synchronize()
+        assert net.engine().plan(precision, B, H, W).error_flag() == 0
+    tol = NET_TOL[precision] * gain
+    for i, y in enumerate(res["1"]):
+        ref = torch.from_numpy(g["net_%s_out%d" % (name, i)])
+        assert _rel(y.cpu(), ref) < tol, i
+        assert torch.equal(y, res["0"][i]), i
+
+
 @pytest.mark.parametrize("precision", ["bf16", "tf32"])
 def test_network_full_config1_vs_oracle(env, precision):
     """BASELINE.json configs[1] at FULL size -- the benchmarked shape: 64 x 3 x 368 x 656 through every production
