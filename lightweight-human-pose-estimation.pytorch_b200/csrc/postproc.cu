@@ -389,6 +389,11 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
   const bool border = (sx < 1) || (sx + 2 >= u.w);
   const int rx0 = col_ok ? sx - 1 - sx_lo : 0;
   const int rowlen = u.W * u.c_layout, body = rowlen - (rowlen & 3);
+  // x4 in y with an exact 1/4 scale: the row geometry is periodic (see the vertical pass); weights of the four phases
+  const bool periodic4 = u.scale_y == 0.25 && u.H == 4 * u.h;
+  float cy4p[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cubic_coeffs(0.125f + 0.25f * (float)j, cy4p[j]);
   for (int c = warp; c < n_ch; c += kPkWarps) {   // a warp takes its channels one at a time: both passes, then the next
     if (__int_as_float(s_cmax[c]) < kHopeless) continue;
     __syncwarp();   // the previous channel's vertical pass has finished reading s_T
@@ -409,6 +414,50 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
     // 3. vertical pass streamed down the rows + strict 4-neighbour test on the row in the middle
     const bool simd_body = d * u.c_layout + c < body;
     float v0 = 0.f, v1 = 0.f;  // rows i-2, i-1
+    // centre row e_c (values v0 / v1 / v2 = rows e_c - 1, e_c, e_c + 1): interior lanes only; rows without any value >= 0.1
+    // (the common case) skip the neighbour exchange altogether
+    auto test_centre = [&](int e_c, float up_v, float mid_v, float down_v) {
+      if (__any_sync(0xffffffffu, mid_v > 0.f)) {
+        const float vl = __shfl_up_sync(0xffffffffu, mid_v, 1), vr = __shfl_down_sync(0xffffffffu, mid_v, 1);
+        if (lane >= 1 && lane <= kPkCols && col_ok && mid_v > 0.f && mid_v > vl && mid_v > vr && mid_v > up_v &&
+            mid_v > down_v && e_c < u.H) {
+          int slot = atomicAdd(&cand_count[img * n_ch + c], 1);
+          if (slot < cap) {
+            unsigned long long key =
+                ((unsigned long long)(((unsigned)d << 16) | (unsigned)e_c) << 32) | __float_as_uint(mid_v);
+            cand[((size_t)img * n_ch + c) * cap + slot] = key;
+          }
+        }
+      }
+    };
+    if (periodic4 && __all_sync(0xffffffffu, simd_body || !col_ok)) {
+      // x4 (demo.py:72): output row e = 4 k + 2 + j has source row k and fraction (j + 0.5) / 4 exactly, whatever k, so
+      // the four weight sets are constants and the loop needs neither the per-row geometry tables nor a source-row
+      // comparison: per source row one load shifts the window, then four output rows of 4 products + 3 sums each
+      // (VResizeCubicVec_32f body order -- the scalar-tail columns, if the map has any, take the generic loop below).
+      const int k0 = (oy0 >> 2) - 1;                      // source row of the tile's first row e = oy0 - 1 (phase 1)
+      const float *tp = s_T + (k0 - 1 - sy_lo) * 32 + lane;
+      float T0 = tp[0], T1 = tp[32], T2 = tp[64], T3 = tp[96];
+      int e = oy0 - 2;                                    // phase 0 of k0: one row above the halo row, skipped below
+#pragma unroll 1
+      for (int kk = 0; kk < 9; ++kk) {
+        if (kk > 0) { T0 = T1; T1 = T2; T2 = T3; T3 = tp[(kk + 3) * 32]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j, ++e) {
+          if ((kk == 0 && j == 0) || (kk == 8 && j == 3)) continue;   // rows oy0 - 2 and oy0 + 33 are not part of the tile
+          float v2 = 0.f;
+          if (e >= 0 && e < u.H && col_ok) {
+            float o = __fadd_rn(__fmul_rn(T2, cy4p[j][2]), __fmul_rn(T3, cy4p[j][3]));
+            o = __fadd_rn(__fmul_rn(T1, cy4p[j][1]), o);
+            o = __fadd_rn(__fmul_rn(T0, cy4p[j][0]), o);
+            v2 = thr01(o);
+          }
+          if (e >= oy0 + 1) test_centre(e - 1, v0, v1, v2);
+          v0 = v1; v1 = v2;
+        }
+      }
+      continue;
+    }
     // the four horizontally-resized source rows of the current output row stay in registers: consecutive output
     // rows share them (x4: four rows per source row), a step of one source row shifts the window by one load
     float T[4] = {0.f, 0.f, 0.f, 0.f};
@@ -430,22 +479,8 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
         const float cyv[4] = {cy4.x, cy4.y, cy4.z, cy4.w};
         if (col_ok) v2 = thr01(cubic_vsum(T, cyv, simd_body));
       }
-      // centre = row i-1 (tile rows are i-1 in [1, kPkRows]), interior lanes only; rows without any value >= 0.1
-      // (the common case) skip the neighbour exchange altogether
-      if (i >= 2 && __any_sync(0xffffffffu, v1 > 0.f)) {
-        const float vl = __shfl_up_sync(0xffffffffu, v1, 1), vr = __shfl_down_sync(0xffffffffu, v1, 1);
-        if (lane >= 1 && lane <= kPkCols && col_ok && v1 > 0.f && v1 > vl && v1 > vr && v1 > v0 && v1 > v2) {
-          const int e = oy0 - 1 + (i - 1);
-          if (e < u.H) {
-            int slot = atomicAdd(&cand_count[img * n_ch + c], 1);
-            if (slot < cap) {
-              unsigned long long key =
-                  ((unsigned long long)(((unsigned)d << 16) | (unsigned)e) << 32) | __float_as_uint(v1);
-              cand[((size_t)img * n_ch + c) * cap + slot] = key;
-            }
-          }
-        }
-      }
+      // centre = row i-1 (tile rows are i-1 in [1, kPkRows])
+      if (i >= 2) test_centre(oy0 - 1 + (i - 1), v0, v1, v2);
       v0 = v1; v1 = v2;
     }
   }
