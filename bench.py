@@ -702,11 +702,14 @@ def roofline_pass(pipe, x_dev, args, precision=None, brief=False):
     plan0 = pipe.chunks[0].plan
     nops = plan0.num_compute_ops
     times = [0.0] * nops
+    # per op: MEDIAN over the repetitions (a host-side hiccup between two launches idles the GPU inside one event
+    # interval; one such outlier in a mean of <= 10 would distort that layer's -- and its roofline object's -- number)
     for c in pipe.chunks:
         plan, xc = c.plan, x_dev[c.lo:c.lo + c.n]
         for i in range(nops):
             plan.run(xc, i, i + 1)  # warm
         torch.cuda.synchronize()
+        samples = [[] for _ in range(nops)]
         for _ in range(reps):
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(nops + 1)]
             evs[0].record()
@@ -715,7 +718,9 @@ def roofline_pass(pipe, x_dev, args, precision=None, brief=False):
                 evs[i + 1].record()
             torch.cuda.synchronize()
             for i in range(nops):
-                times[i] += evs[i].elapsed_time(evs[i + 1]) / reps
+                samples[i].append(evs[i].elapsed_time(evs[i + 1]))
+        for i in range(nops):
+            times[i] += sorted(samples[i])[len(samples[i]) // 2]
     agg = {}
     for i, t in enumerate(times):
         kind = plan0.op_meta[i]["kind"]

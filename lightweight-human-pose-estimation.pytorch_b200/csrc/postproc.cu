@@ -435,26 +435,46 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
       // the four weight sets are constants and the loop needs neither the per-row geometry tables nor a source-row
       // comparison: per source row one load shifts the window, then four output rows of 4 products + 3 sums each
       // (VResizeCubicVec_32f body order -- the scalar-tail columns, if the map has any, take the generic loop below).
+      // Lanes outside the image hold T = 0 and so produce 0; rows outside the image are forced to 0 by the row test;
+      // the neighbour exchange is voted on once per group of four rows.
       const int k0 = (oy0 >> 2) - 1;                      // source row of the tile's first row e = oy0 - 1 (phase 1)
       const float *tp = s_T + (k0 - 1 - sy_lo) * 32 + lane;
       float T0 = tp[0], T1 = tp[32], T2 = tp[64], T3 = tp[96];
-      int e = oy0 - 2;                                    // phase 0 of k0: one row above the halo row, skipped below
-#pragma unroll 1
-      for (int kk = 0; kk < 9; ++kk) {
-        if (kk > 0) { T0 = T1; T1 = T2; T2 = T3; T3 = tp[(kk + 3) * 32]; }
-#pragma unroll
-        for (int j = 0; j < 4; ++j, ++e) {
-          if ((kk == 0 && j == 0) || (kk == 8 && j == 3)) continue;   // rows oy0 - 2 and oy0 + 33 are not part of the tile
-          float v2 = 0.f;
-          if (e >= 0 && e < u.H && col_ok) {
-            float o = __fadd_rn(__fmul_rn(T2, cy4p[j][2]), __fmul_rn(T3, cy4p[j][3]));
-            o = __fadd_rn(__fmul_rn(T1, cy4p[j][1]), o);
-            o = __fadd_rn(__fmul_rn(T0, cy4p[j][0]), o);
-            v2 = thr01(o);
+      const int e_lo = oy0 > 0 ? oy0 - 1 : 0;
+      const unsigned e_span = (unsigned)(min(u.H - 1, oy0 + kPkRows) - e_lo);   // valid rows: e_lo .. e_lo + e_span
+      float pm2 = 0.f, pm1 = 0.f;                         // rows e - 2, e - 1 of the current group
+      auto centre4 = [&](int e_c, float up_v, float mid_v, float down_v) {
+        const float vl = __shfl_up_sync(0xffffffffu, mid_v, 1), vr = __shfl_down_sync(0xffffffffu, mid_v, 1);
+        if (lane >= 1 && lane <= kPkCols && mid_v > 0.f && mid_v > vl && mid_v > vr && mid_v > up_v && mid_v > down_v &&
+            e_c >= oy0 && e_c < oy0 + kPkRows) {
+          int slot = atomicAdd(&cand_count[img * n_ch + c], 1);
+          if (slot < cap) {
+            unsigned long long key =
+                ((unsigned long long)(((unsigned)d << 16) | (unsigned)e_c) << 32) | __float_as_uint(mid_v);
+            cand[((size_t)img * n_ch + c) * cap + slot] = key;
           }
-          if (e >= oy0 + 1) test_centre(e - 1, v0, v1, v2);
-          v0 = v1; v1 = v2;
         }
+      };
+#pragma unroll 1
+      for (int kk = 0; kk < 9; ++kk) {                    // group kk: rows e .. e + 3, e = oy0 - 2 + 4 kk (source row k0 + kk)
+        if (kk > 0) { T0 = T1; T1 = T2; T2 = T3; T3 = tp[(kk + 3) * 32]; }
+        const int e = oy0 - 2 + 4 * kk;
+        float a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float o = __fadd_rn(__fmul_rn(T2, cy4p[j][2]), __fmul_rn(T3, cy4p[j][3]));
+          o = __fadd_rn(__fmul_rn(T1, cy4p[j][1]), o);
+          o = __fadd_rn(__fmul_rn(T0, cy4p[j][0]), o);
+          a[j] = ((unsigned)(e + j - e_lo) <= e_span && !(o < 0.1f)) ? o : 0.f;   // thr01 + zero outside the image
+        }
+        // centres e - 1 .. e + 2 (rows oy0 - 2 and oy0 + 33 are only ever neighbours of rows that are not centres)
+        if (__any_sync(0xffffffffu, fmaxf(fmaxf(pm1, a[0]), fmaxf(a[1], a[2])) > 0.f)) {
+          centre4(e - 1, pm2, pm1, a[0]);
+          centre4(e, pm1, a[0], a[1]);
+          centre4(e + 1, a[0], a[1], a[2]);
+          centre4(e + 2, a[1], a[2], a[3]);
+        }
+        pm2 = a[2]; pm1 = a[3];
       }
       continue;
     }
