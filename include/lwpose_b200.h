@@ -130,6 +130,14 @@ int lwp_extract_keypoints_fused(const float *src, int n, int h, int w, int ld, i
                                 size_t workspace_bytes, int32_t *overflow, void *stream);
 
 size_t lwp_group_workspace_bytes(int n, int cap_kpts, int cap_connections, int cap_poses);
+/*
+ * Optional extra workspace of lwp_group_keypoints_fused / lwp_postprocess for n images with h x w stride-8 maps:
+ * when the workspace handed in is at least lwp_group_workspace_bytes(...) (resp. lwp_postprocess_workspace_bytes(...))
+ * + lwp_paf_pack_bytes(n, h, w) bytes, the PAF channel pairs are first re-packed per limb ([n][19][h*w] float2) so
+ * that the line-integral kernel (modules/keypoints.py:94-139) stages a limb's two channels as one contiguous copy and
+ * spreads crowded frames over several blocks.  Results are identical with and without it.
+ */
+size_t lwp_paf_pack_bytes(int n, int h, int w);
 
 /*
  * Replaces group_keypoints(all_keypoints_by_type, pafs, 20, min_paf_score, demo)

@@ -33,6 +33,7 @@ SIGNATURES = {
                                            _c_int, _c_int, _c_int, _c_double, _c_double, _c_int, _c_double, _c_void_p,
                                            _c_void_p, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p, _c_void_p]),
     "lwp_group_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
+    "lwp_paf_pack_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "lwp_group_keypoints": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int,
                                      _c_int, _c_int, _c_double, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
                                      _c_size_t, _c_void_p, _c_void_p]),

@@ -655,9 +655,35 @@ __device__ __forceinline__ double paf_sample(const float *paf, int W, int ld, co
   return __dadd_rn(__dmul_rn(ux, (double)pv[0]), __dmul_rn(uy, (double)pv[1]));
 }
 
+// Re-pack of the stride-8 PAF channels for paf_score_kernel<true, true>: [img][pixel][ld] float (38 PAF channels among the
+// 64 of a head row) -> [img][limb][pixel] float2 = the limb's (x, y) channel pair.  Every (limb, image) block of the
+// scoring kernel stages its two channels in shared memory; read straight from the head rows that is 8 useful bytes
+// per 32-byte sector at a 256-byte pitch, 1 216 blocks x 241 KB of sector traffic per 64-frame batch, and it was 29 %
+// of that kernel's stall samples.  Packed, the same staging is one contiguous 30 KB copy.
+constexpr int kPackPx = 128;
+__global__ void __launch_bounds__(256)
+paf_pack_kernel(const UpSrc up, float2 *__restrict__ packed, int plane_stride) {
+  __shared__ float s[kPackPx][39];   // 38 channels + 1 pad: conflict-free column reads
+  const int img = blockIdx.y, px0 = blockIdx.x * kPackPx, npx = up.h * up.w;
+  const float *src = up.src + ((size_t)img * npx + px0) * up.ld;
+  for (int idx = threadIdx.x; idx < kPackPx * 38; idx += blockDim.x) {
+    const int p = idx / 38, c = idx - p * 38;
+    if (px0 + p < npx) s[p][c] = __ldg(src + (size_t)p * up.ld + c);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kPackPx * LWP_NUM_LIMBS; idx += blockDim.x) {
+    const int limb = idx / kPackPx, p = idx - limb * kPackPx;
+    if (px0 + p < npx)
+      packed[((size_t)img * LWP_NUM_LIMBS + limb) * plane_stride + px0 + p] =
+          make_float2(s[p][c_paf_ids[limb][0]], s[p][c_paf_ids[limb][1]]);
+  }
+}
+
 // PAF line integral in two phases.  A connection needs at least 9 of its 10 samples above min_paf_score
-// (success_ratio > 0.8, keypoints.py:137), so a pair whose two probe samples (k = 3 and k = 6, interior points of
-// the segment) both fail can never be one: phase 1 gives every lane one candidate pair and evaluates only the probes;
+// (success_ratio > 0.8, keypoints.py:137), so a pair with two failing samples can never be one: phase 1 gives every lane
+// one candidate pair and evaluates up to four probe samples (k = 3, 6, 1, 8), stopping at the second failure (on sparse
+// PAFs that is after two probes; on the noisy maps of a random-init network four probes leave ~13 % of the pairs
+// where two left ~58 %);
 // phase 2 scores the surviving pairs in full, 3 at a time, 10 lanes per pair, lane k taking sample k of linspace2d;
 // the sum is then re-done in k order so the float64 result is the reference's.  Which pairs are connections and
 // their ratios are exactly the reference's; only work on hopeless pairs is skipped.
@@ -666,7 +692,8 @@ template <bool kFused, bool kSmem>   // kSmem (fused only): the limb's two strid
 __global__ void __launch_bounds__(256)
 paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ counts, int cap_kpts,
                  const float *__restrict__ pafs, int H, int W, int ld, const UpSrc up, int demo,
-                 double min_paf_score, Conn *__restrict__ conn, int *__restrict__ conn_count, int cap_conn) {
+                 double min_paf_score, Conn *__restrict__ conn, int *__restrict__ conn_count, int cap_conn,
+                 const float2 *__restrict__ packed, int plane_stride) {
   const int limb = blockIdx.y, img = blockIdx.z;
   const int ka = c_kpt_ids[limb][0], kb = c_kpt_ids[limb][1];
   const int nA = counts[img * LWP_NUM_KPT_TYPES + ka], nB = counts[img * LWP_NUM_KPT_TYPES + kb];
@@ -686,10 +713,16 @@ paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ 
   const float2 *s_src = reinterpret_cast<const float2 *>(ps_smem);
   if constexpr (kFused && kSmem) {
     float2 *s_w = reinterpret_cast<float2 *>(ps_smem);
-    const float *src = up.src + (size_t)img * up.h * up.w * up.ld;
-    for (int idx = threadIdx.x; idx < up.h * up.w; idx += blockDim.x) {
-      const float *pp = src + (size_t)idx * up.ld;
-      s_w[idx] = make_float2(__ldg(pp + cx), __ldg(pp + cy));
+    if (packed != nullptr) {   // the limb's plane as paf_pack_kernel wrote it: one contiguous, fully coalesced copy
+      const float4 *src4 = reinterpret_cast<const float4 *>(packed + ((size_t)img * LWP_NUM_LIMBS + limb) * plane_stride);
+      float4 *dst4 = reinterpret_cast<float4 *>(ps_smem);
+      for (int idx = threadIdx.x; idx < plane_stride / 2; idx += blockDim.x) dst4[idx] = __ldg(src4 + idx);
+    } else {
+      const float *src = up.src + (size_t)img * up.h * up.w * up.ld;
+      for (int idx = threadIdx.x; idx < up.h * up.w; idx += blockDim.x) {
+        const float *pp = src + (size_t)idx * up.ld;
+        s_w[idx] = make_float2(__ldg(pp + cx), __ldg(pp + cy));
+      }
     }
     __syncthreads();
   }
@@ -705,9 +738,15 @@ paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ 
       const double norm = __dsqrt_rn((double)((long long)vx * vx + (long long)vy * vy));
       if (norm != 0.0) {
         const double ux = __ddiv_rn((double)vx, norm), uy = __ddiv_rn((double)vy, norm);
-        survive = paf_sample<kFused, kSmem>(paf, W, ld, up, s_src, img, demo, a.x, a.y, vx, vy, ux, uy, 3, cx, cy) > min_paf_score;
-        if (!survive)
-          survive = paf_sample<kFused, kSmem>(paf, W, ld, up, s_src, img, demo, a.x, a.y, vx, vy, ux, uy, 6, cx, cy) > min_paf_score;
+        // up to four probes (k = 3, 6, 1, 8); the pair is dropped at its second failing sample
+        int fails = 0;
+#pragma unroll 1
+        for (int q = 0; q < 4 && fails < 2; ++q) {
+          const int kq = (0x8163 >> (4 * q)) & 15;
+          if (!(paf_sample<kFused, kSmem>(paf, W, ld, up, s_src, img, demo, a.x, a.y, vx, vy, ux, uy, kq, cx, cy) > min_paf_score))
+            ++fails;
+        }
+        survive = fails < 2;
       }
     }
     unsigned alive = __ballot_sync(0xffffffffu, survive);
@@ -1195,6 +1234,12 @@ extern "C" size_t lwp_group_workspace_bytes(int n, int cap_kpts, int cap_connect
   return carve_group_ws(nullptr, n, cap_kpts, cap_connections, cap_poses).bytes;
 }
 
+extern "C" size_t lwp_paf_pack_bytes(int n, int h, int w) {
+  if (n <= 0 || h <= 0 || w <= 0) return 0;
+  const size_t plane_stride = ((size_t)h * w + 1) & ~(size_t)1;
+  return 256 + align_up((size_t)n * LWP_NUM_LIMBS * plane_stride * sizeof(float2), 256);   // 256: alignment of the part before it
+}
+
 static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *counts, const int32_t *kpt_start,
                         int cap_kpts, const float *pafs, const UpSrc *up, int n, int H, int W, int paf_ld, int demo,
                         double min_paf_score, double *pose_entries, int32_t *n_poses, int cap_poses,
@@ -1226,16 +1271,34 @@ static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *cou
     // fill the GPU (batches: one block of 8 warps walks all pairs; a single image: up to 8 blocks per limb)
     int bs = ceil_div(4 * num_sms(), LWP_NUM_LIMBS * n);
     bs = bs < 1 ? 1 : (bs > 8 ? 8 : bs);
+    // a workspace with lwp_paf_pack_bytes(n, h, w) extra bytes behind the lwp_group_workspace_bytes() part enables the
+    // packed staging (paf_pack_kernel): same results, the limb's channels then arrive as one coalesced copy, which also
+    // makes it affordable to spread a (limb, image) with many candidate pairs over several blocks (blocks without pairs
+    // return before staging)
+    const int plane_stride = (up->h * up->w + 1) & ~1;
+    const size_t base_bytes = align_up(w.bytes, 256);
+    float2 *packed = nullptr;
+    if (src_bytes <= 200 * 1024 && workspace_bytes >= base_bytes + lwp_paf_pack_bytes(n, up->h, up->w) &&
+        getenv("LWP_NO_PAF_PACK") == nullptr) {
+      packed = reinterpret_cast<float2 *>((char *)workspace + base_bytes);
+      paf_pack_kernel<<<dim3(ceil_div(up->h * up->w, kPackPx), n), 256, 0, st>>>(*up, packed, plane_stride);
+      LWP_LAUNCH_CHECK();
+      bs = ceil_div(16 * num_sms(), LWP_NUM_LIMBS * n);
+      bs = bs < 1 ? 1 : (bs > 8 ? 8 : bs);
+      if (const char *e = getenv("LWP_PAF_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= 32) bs = v; }
+    }
     if (src_bytes <= 200 * 1024)
-      paf_score_kernel<true, true><<<dim3(bs, LWP_NUM_LIMBS, n), 256, src_bytes, st>>>(
-          kpts, counts, cap_kpts, nullptr, H, W, paf_ld, *up, demo, min_paf_score, w.conn, w.conn_count, cap_connections);
+      paf_score_kernel<true, true><<<dim3(bs, LWP_NUM_LIMBS, n), 256, (size_t)plane_stride * sizeof(float2), st>>>(
+          kpts, counts, cap_kpts, nullptr, H, W, paf_ld, *up, demo, min_paf_score, w.conn, w.conn_count, cap_connections,
+          packed, plane_stride);
     else
       paf_score_kernel<true, false><<<dim3(bx, LWP_NUM_LIMBS, n), 128, 0, st>>>(
-          kpts, counts, cap_kpts, nullptr, H, W, paf_ld, *up, demo, min_paf_score, w.conn, w.conn_count, cap_connections);
+          kpts, counts, cap_kpts, nullptr, H, W, paf_ld, *up, demo, min_paf_score, w.conn, w.conn_count, cap_connections,
+          nullptr, 0);
   } else {
     paf_score_kernel<false, false><<<dim3(bx, LWP_NUM_LIMBS, n), 128, 0, st>>>(kpts, counts, cap_kpts, pafs, H, W, paf_ld, u0,
                                                                                demo, min_paf_score, w.conn, w.conn_count,
-                                                                               cap_connections);
+                                                                               cap_connections, nullptr, 0);
   }
   LWP_LAUNCH_CHECK();
   static DeviceOnce attr_set;

@@ -91,7 +91,9 @@ class _Chunk:
         self.pose_entries = torch.empty((n, cp, postproc.POSE_ENTRY), dtype=torch.float64, device=dev)
         self.n_poses = torch.empty((n,), dtype=torch.int32, device=dev)
         self.ws_extract = torch.empty((L.lwp_extract_workspace_bytes(n, 18, cc),), dtype=torch.uint8, device=dev)
-        self.ws_group = torch.empty((L.lwp_group_workspace_bytes(n, ck, cn, cp),), dtype=torch.uint8, device=dev)
+        # + the optional re-packed PAF planes (fused path: a limb's two channels staged by one contiguous copy)
+        pack = L.lwp_paf_pack_bytes(n, pipe.H // 8, pipe.W // 8) if pipe.fused else 0
+        self.ws_group = torch.empty((L.lwp_group_workspace_bytes(n, ck, cn, cp) + pack,), dtype=torch.uint8, device=dev)
         if pipe.convert is not None:
             self.pose_kpts = torch.empty((n, cp, postproc.NUM_KPT_TYPES, 2), dtype=torch.int32, device=dev)
             self.bbox = torch.empty((n, cp, 4), dtype=torch.int32, device=dev)

@@ -206,7 +206,7 @@ def group_keypoints_fused(kb, maps, ratio, channel_offset=19, demo=False, min_pa
         n_poses = torch.empty((n,), dtype=torch.int32, device=maps.device)
     else:
         pose_entries, n_poses = out
-    ws_bytes = L.lwp_group_workspace_bytes(n, kb.cap_kpts, cap_connections, cap_poses)
+    ws_bytes = L.lwp_group_workspace_bytes(n, kb.cap_kpts, cap_connections, cap_poses) + L.lwp_paf_pack_bytes(n, h, w)
     if workspace is None or workspace.numel() < ws_bytes:
         workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=maps.device)
     _lib.check(L.lwp_group_keypoints_fused(_ptr(kb.kpts), _ptr(kb.counts), _ptr(kb.kpt_start), kb.cap_kpts,

@@ -203,6 +203,23 @@ def test_fused_postproc_bit_exact_vs_reference_golden(torch_cuda, case, demo):
     assert np.array_equal(poses.view(np.int64), g[tag + "_poses"].view(np.int64))
 
 
+@pytest.mark.parametrize("variant", [{"LWP_NO_PAF_PACK": "1"}, {"LWP_PAF_BLOCKS": "1"}, {"LWP_PAF_BLOCKS": "5"}],
+                         ids=["unpacked", "packed_1_block", "packed_5_blocks"])
+def test_paf_staging_variants_give_identical_pose_tables(torch_cuda, variant, monkeypatch):
+    """The PAF line integral with the limb's channels staged from the re-packed planes (default when the workspace has
+    lwp_paf_pack_bytes extra), straight from the head rows (LWP_NO_PAF_PACK=1), and with a (limb, image) spread over
+    1 / 5 blocks: the same pose tables, bit for bit, on crowded noisy frames (odd map size: padded plane stride)."""
+    from lwpose_b200 import synth
+    hm, paf, _ = synth.synthetic_pose_maps(6, 45, 81, seed=11, noise=0.05, max_persons=30)
+    ref = _fused_postproc(torch_cuda, hm, paf, True)
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    got = _fused_postproc(torch_cuda, hm, paf, True)
+    for a, b in zip(ref, got):
+        assert np.array_equal(np.asarray(a).view(np.uint8), np.asarray(b).view(np.uint8))
+    assert int(ref[4].sum()) > 20
+
+
 @pytest.mark.parametrize("demo", [True, False])
 def test_config3_batch256_bit_exact_vs_oracle(torch_cuda, demo):
     """BASELINE.json configs[2] at full size: 256 synthetic frames of 19 heat-maps / 38 PAFs at 46x82 with 1..30
