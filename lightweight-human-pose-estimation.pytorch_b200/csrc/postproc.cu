@@ -1283,7 +1283,7 @@ static int group_common(bool fused, const lwp_keypoint *kpts, const int32_t *cou
       packed = reinterpret_cast<float2 *>((char *)workspace + base_bytes);
       paf_pack_kernel<<<dim3(ceil_div(up->h * up->w, kPackPx), n), 256, 0, st>>>(*up, packed, plane_stride);
       LWP_LAUNCH_CHECK();
-      bs = ceil_div(16 * num_sms(), LWP_NUM_LIMBS * n);
+      bs = ceil_div(24 * num_sms(), LWP_NUM_LIMBS * n);   // 64 frames: 3 (measured 1 / 2 / 3 / 4 / 8 blocks: 205 / 188 / 183 / 186 / 187 us for the grouping)
       bs = bs < 1 ? 1 : (bs > 8 ? 8 : bs);
       if (const char *e = getenv("LWP_PAF_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= 32) bs = v; }
     }

@@ -115,9 +115,14 @@ def test_conv_gemm_vs_torch(env, precision, shape):
     # (n, H, W, C, stride, dil, act)
     (2, 24, 40, 32, 1, 1, 1), (1, 23, 41, 64, 2, 1, 1), (2, 46, 82, 512, 1, 2, 1), (1, 13, 9, 128, 1, 1, 2),
     (1, 184, 328, 32, 1, 1, 1), (1, 92, 164, 128, 2, 1, 1),
+    (3, 21, 37, 128, 1, 2, 1), (1, 9, 70, 256, 1, 2, 2),      # dilated (interleaved thread mapping), ragged tiles
+    (3, 21, 37, 128, 1, 2, 1, "regstore"), (2, 23, 41, 64, 1, 1, 1, "regstore"),   # register-store epilogue (LWP_DW_TMA_STORE=0)
 ])
-def test_depthwise_vs_torch(env, precision, shape):
+def test_depthwise_vs_torch(env, precision, shape, monkeypatch):
     torch, _lib, engine = env
+    if len(shape) == 8:
+        monkeypatch.setenv("LWP_DW_TMA_STORE", "0")
+        shape = shape[:7]
     n, H, W, C, stride, dil, act = shape
     g = torch.Generator().manual_seed(hash(shape) % (2 ** 31))
     tdtype = engine._PREC[precision][1]
