@@ -1,5 +1,5 @@
 """Device time of selected layers of one bench step (CUDA events on the launching stream, each layer alone,
-inputs of the step resident).  Usage: python scripts/time_layers.py [--reps R] [--precision bf16|tf32] [substr ...]
+inputs of the step resident).  Usage: python scripts/time_layers.py [--reps R] [--precision bf16|tf32] [--u8] [substr ...]
 (a layer is timed when any substring matches its op name; no substrings = all layers)."""
 import json
 import os
@@ -14,21 +14,27 @@ import bench  # noqa: E402
 
 def main():
     args = sys.argv[1:]
-    reps, precision, subs = 20, "bf16", []
+    reps, precision, subs, u8 = 20, "bf16", [], False
     while args:
         a = args.pop(0)
         if a == "--reps":
             reps = int(args.pop(0))
         elif a == "--precision":
             precision = args.pop(0)
+        elif a == "--u8":      # uint8 NHWC frames (val.normalize fused into the stem)
+            u8 = True
         else:
             subs.append(a)
     import lwpose_b200  # noqa: F401
     from lwpose_b200 import synth
     from lwpose_b200.pipeline import PosePipeline
     net = bench.make_net().cuda()
-    pipe = PosePipeline(net, 64, bench.HEIGHT, bench.WIDTH, precision=precision, demo=True)
-    x = synth.synthetic_net_input(64, bench.HEIGHT, bench.WIDTH, seed=1).cuda()
+    pipe = PosePipeline(net, 64, bench.HEIGHT, bench.WIDTH, precision=precision, demo=True,
+                        **({"input_format": "u8_nhwc"} if u8 else {}))
+    if u8:
+        x = torch.from_numpy(synth.synthetic_frames(64, bench.HEIGHT, bench.WIDTH, seed=1)).cuda()
+    else:
+        x = synth.synthetic_net_input(64, bench.HEIGHT, bench.WIDTH, seed=1).cuda()
     for _ in range(2):
         pipe.run_device(x)
     torch.cuda.synchronize()
