@@ -737,7 +737,7 @@ def roofline_pass(pipe, x_dev, args, precision=None, brief=False):
     precision = precision or args.precision
     peak = pk["bf16"] if precision == "bf16" else pk["bf16"] / 2.0
     traffic, traffic_src = ncu_traffic(("conv_gemm", "conv3x3_pair", "dwpw_gemm_kernel"))
-    res = {"roofline": {"kernel": "tcgen05 implicit-GEMM kernels conv_gemm_kernel / conv_gemm2_kernel / conv3x3_pair_kernel%s (all %d launches of a "
+    res = {"roofline": {"kernel": "tcgen05 implicit-GEMM kernels conv_gemm_kernel / conv_gemm_wres_kernel / conv_gemm2_kernel / conv3x3_pair_kernel%s (all %d launches of a "
                                   "step; %.0f %% of the network time)" % (" / dwpw_gemm_kernel" if "dwpw" in agg else "", gemm_launches,
                                                                          100.0 * gemm_ms / max(sum(times), 1e-9)),
                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -755,7 +755,7 @@ def roofline_pass(pipe, x_dev, args, precision=None, brief=False):
     if "gemm1x1" in agg:
         d = agg["gemm1x1"]
         tf = d["flops"] / (d["ms"] * 1e-3) / 1e12
-        res["roofline_pointwise"] = {"kernel": "conv_gemm_kernel / conv_gemm2_kernel (CTA pairs), 1x1 layers (%d launches)" % d["launches"],
+        res["roofline_pointwise"] = {"kernel": "conv_gemm_kernel / conv_gemm_wres_kernel (thin layers) / conv_gemm2_kernel (CTA pairs), 1x1 layers (%d launches)" % d["launches"],
                                      "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
                                      "ms_per_step": d["ms"]}
         big = [(plan0.op_meta[i]["flops"] * len(pipe.chunks), times[i]) for i in range(nops)

@@ -17,7 +17,7 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size"]
-POSTPROC = ["peak_candidates_fused", "peak_nms", "keypoint_ids", "paf_score", "limb_match", "pose_assemble"]
+POSTPROC = ["peak_candidates_fused", "peak_nms", "keypoint_ids", "paf_pack", "paf_score", "limb_match", "pose_assemble"]
 
 
 def main():
