@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--no-u8", action="store_true", help="skip the uint8-frame end-to-end run")
     ap.add_argument("--no-other-precision", action="store_true", help="skip the device-resident run on the other precision")
     ap.add_argument("--chunk", type=int, default=0, help="frames per pipeline chunk (0 = whole batch)")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="batches in flight in the end-to-end (submit / collect) runs")
     ap.add_argument("--no-overlap-postproc", action="store_true", help="post-processing on the network's stream")
     ap.add_argument("--unfused-postproc", action="store_true", help="materialise the up-sampled maps like the reference")
     ap.add_argument("--steady-seconds", type=float, default=2.0, help="length of the extra steady-state run (0 = skip)")
@@ -256,7 +257,7 @@ def main():
     pipe = PosePipeline(net, args.batch, HEIGHT, WIDTH, precision=args.precision, demo=True,
                         heads_hook=lambda heads, lo: heads.add_(inject[lo:lo + heads.shape[0]]),
                         fused=not args.unfused_postproc, chunk=args.chunk or None,
-                        overlap_postproc=not args.no_overlap_postproc)
+                        overlap_postproc=not args.no_overlap_postproc, depth=args.e2e_depth)
     x_host = synth.synthetic_net_input(args.batch, HEIGHT, WIDTH, seed=1 + rank).pin_memory()
     x_dev = x_host.to(dev)
 
@@ -307,18 +308,14 @@ def main():
         gpu_heads[args.precision] = raw_heads(pipe, x_dev, cpu_n)
 
     # ---- end to end through the public API: pinned host frames in, host pose tables out --------------
-    # streaming use of PosePipeline (submit / collect, 2 batches in flight): every step's H2D copy and
+    # streaming use of PosePipeline (submit / collect, --e2e-depth batches in flight): every step's H2D copy and
     # result read-back are inside the timed region; the copy of step i+1 overlaps the kernels of step i
     for _ in range(2):
         pipe(x_host)
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
-    pipe.submit(x_host)
-    for _ in range(args.steps - 1):
-        pipe.submit(x_host)
-        res = pipe.collect()
-    res = pipe.collect()
+    res = stream_steps(pipe, x_host, args.steps)
     s1.record()
     s1.synchronize()
     barrier()
@@ -332,18 +329,14 @@ def main():
         pipe8 = PosePipeline(net, args.batch, HEIGHT, WIDTH, precision=args.precision, demo=True,
                              heads_hook=lambda heads, lo: heads.add_(inject[lo:lo + heads.shape[0]]),
                              fused=not args.unfused_postproc, chunk=args.chunk or None,
-                             overlap_postproc=not args.no_overlap_postproc, input_format="u8_nhwc")
+                             overlap_postproc=not args.no_overlap_postproc, input_format="u8_nhwc", depth=args.e2e_depth)
         x8 = torch.from_numpy(synth.synthetic_frames(args.batch, HEIGHT, WIDTH, seed=1 + rank)).pin_memory()
         for _ in range(2):
             pipe8(x8)
         barrier()
         u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         u0.record()
-        pipe8.submit(x8)
-        for _ in range(args.steps - 1):
-            pipe8.submit(x8)
-            pipe8.collect()
-        pipe8.collect().check()
+        stream_steps(pipe8, x8, args.steps).check()
         u1.record()
         u1.synchronize()
         barrier()
@@ -363,18 +356,14 @@ def main():
                               heads_hook=lambda heads, lo: heads.add_(inject[lo:lo + heads.shape[0]]),
                               fused=not args.unfused_postproc, chunk=args.chunk or None,
                               overlap_postproc=not args.no_overlap_postproc, input_format="u8_raw", raw_size=(720, 1280),
-                              convert=dict(pad=rpad, scale=rscale))
+                              convert=dict(pad=rpad, scale=rscale), depth=args.e2e_depth)
         xr = torch.from_numpy(synth.synthetic_frames(args.batch, 720, 1280, seed=1 + rank)).pin_memory()
         for _ in range(2):
             pipe_r(xr)
         barrier()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
-        pipe_r.submit(xr)
-        for _ in range(args.steps - 1):
-            pipe_r.submit(xr)
-            pipe_r.collect()
-        rres = pipe_r.collect().check()
+        rres = stream_steps(pipe_r, xr, args.steps).check()
         r1.record()
         r1.synchronize()
         barrier()
@@ -418,7 +407,7 @@ def main():
     sync_ms = (time.perf_counter() - t0) / 3 * 1000.0
 
     e2e_f32 = {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": pipe.h2d_bytes,
-               "d2h_bytes_per_step": pipe.d2h_bytes, "mode": "PosePipeline.submit/collect, 2 batches in flight",
+               "d2h_bytes_per_step": pipe.d2h_bytes, "mode": "PosePipeline.submit/collect, %d batches in flight" % len(pipe.slots),
                "input": "float32 NCHW frames [n,3,368,656], already normalised on the host", "sync_call_ms": sync_ms}
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -429,7 +418,7 @@ def main():
         # (demo.py:54 infer_fast(net, img, ...)) -- in pinned host memory, pose tables back in host memory.  The float32
         # NCHW variant (the tensor the reference builds on the host before its own H2D copy, 4x the bytes: 185 MB per
         # step, which is PCIe time comparable to the whole step) is reported next to it.
-        "e2e": dict(e2e_u8, mode="PosePipeline.submit/collect, 2 batches in flight") if e2e_u8 is not None else e2e_f32,
+        "e2e": dict(e2e_u8, mode="PosePipeline.submit/collect, %d batches in flight" % args.e2e_depth) if e2e_u8 is not None else e2e_f32,
         "e2e_f32": e2e_f32,
         "e2e_raw_frames": e2e_raw,
         "steady_state": steady,
@@ -690,6 +679,20 @@ def ncu_traffic(prefixes):
         return None, None
     return sum(vals) / len(vals), "%s (mean over the %d captured launches)" % (
         os.path.relpath(files[-1], ROOT).replace("dram_traffic_bytes.json", "ncu_full_layers.csv"), len(vals))
+
+
+def stream_steps(pipe, frames, steps):
+    """`steps` batches through submit()/collect() with as many in flight as the pipeline has slots; returns the last
+    PoseResult.  Every batch's H2D copy and result read-back happen inside the caller's timed region."""
+    depth = len(pipe.slots)
+    res, submitted, collected = None, 0, 0
+    while collected < steps:
+        while submitted < steps and submitted - collected < depth:
+            pipe.submit(frames)
+            submitted += 1
+        res = pipe.collect()
+        collected += 1
+    return res
 
 
 def roofline_pass(pipe, x_dev, args, precision=None, brief=False):

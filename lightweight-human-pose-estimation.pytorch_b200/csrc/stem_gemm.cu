@@ -12,6 +12,9 @@
 // cores move data (about 60 instructions per output pixel instead of ~550 for the direct FFMA form), the 864
 // MACs per pixel go to the tensor pipe, and the kernel becomes a streaming read of the frames and write of the
 // first activation.  Several small CTAs per SM (each with its own 64 TMEM columns) hide the load latency.
+#include <math.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "conv_direct.cuh"
 #include "conv_gemm.cuh"
@@ -34,6 +37,10 @@ struct StemGemmParams {
   int tiles;
   uint32_t idesc;
   double mean[3], img_scale;
+  // uint8 frames whose normalisation is exact in float32 (integer means, power-of-two scale -- the reference's 128 and
+  // 1/256): v = fma(float(8388608 + b), nscale, noff[ci]) with the byte OR-ed into the mantissa of 2^23, no conversions
+  int fast_norm;
+  float nscale, noff[3];
   int *err_flag;
 };
 
@@ -56,7 +63,7 @@ __device__ __forceinline__ void stem_store_row(uint8_t *tile, int r, const float
   }
 }
 
-template <bool kTf32, bool kU8>
+template <bool kTf32, int kU8>   // kU8: 0 float32 NCHW frames, 1 uint8 frames (float64 normalisation), 2 uint8 frames (exact float32 short cut)
 __global__ void __launch_bounds__(kStemThreads, 5)
 stem_gemm_kernel(const StemGemmParams p) {
   extern __shared__ uint8_t stem_smem_raw[];
@@ -115,7 +122,7 @@ stem_gemm_kernel(const StemGemmParams p) {
       const int yi0 = 2 * yo - 1, xi0 = 2 * xo - 1;
       // H and W are even, so only the first row / column of the window can fall outside (yo == 0 / xo == 0)
       const bool top = yo == 0, left = xo == 0;
-      if constexpr (kU8) {
+      if constexpr (kU8 != 0) {
         const uint8_t *base = x8 + (((long long)img * p.H + yi0) * p.W + xi0) * 3;   // may point before the frame: guarded
         const int rowb = p.W * 3;
 #pragma unroll
@@ -126,9 +133,14 @@ stem_gemm_kernel(const StemGemmParams p) {
           for (int kx = 0; kx < 3; ++kx) {
             if (kx == 0 && left) continue;   // zero padding applies to the NORMALISED image (pad value 0 after normalize)
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci)
-              v[ci * 9 + ky * 3 + kx] =
-                  __double2float_rn(__dmul_rn(__dsub_rn((double)__ldg(row + kx * 3 + ci), p.mean[ci]), p.img_scale));
+            for (int ci = 0; ci < 3; ++ci) {
+              const uint32_t b = __ldg(row + kx * 3 + ci);
+              // val.normalize in float64 like the reference (two conversions + two FP64 operations per tap: the
+              // conversion pipe made this variant 30 us slower than the float32 one) -- or, when that is exact in
+              // float32, one LOP3 + one FFMA with the same bits
+              if constexpr (kU8 == 2) v[ci * 9 + ky * 3 + kx] = __fmaf_rn(__uint_as_float(0x4B000000u | b), p.nscale, p.noff[ci]);
+              else v[ci * 9 + ky * 3 + kx] = __double2float_rn(__dmul_rn(__dsub_rn((double)b, p.mean[ci]), p.img_scale));
+            }
           }
         }
       } else {
@@ -244,27 +256,41 @@ int stem_gemm_launch(bool f32, const void *x, bool x_is_u8, const double *mean3,
   p.idesc = make_umma_idesc(f32, kBlockM, kStemN);
   p.mean[0] = mean3 ? mean3[0] : 0; p.mean[1] = mean3 ? mean3[1] : 0; p.mean[2] = mean3 ? mean3[2] : 0;
   p.img_scale = img_scale;
+  {
+    int e = 0;
+    bool ok = img_scale > 0 && frexp(img_scale, &e) == 0.5 && e > -100 && e < 100;
+    for (int c = 0; c < 3; ++c) ok = ok && p.mean[c] == floor(p.mean[c]) && p.mean[c] >= 0 && p.mean[c] <= 1048576.0;
+    if (getenv("LWP_STEM_F64_NORM") != nullptr) ok = false;   // (tests: the float64 path on the default constants)
+    p.fast_norm = ok ? 1 : 0;
+    p.nscale = (float)img_scale;
+    for (int c = 0; c < 3; ++c) p.noff[c] = (float)(-(8388608.0 + p.mean[c]) * img_scale);
+  }
   p.err_flag = err_flag;
   const size_t smem = 1024 + kStemStages * kATileBytes + kStemN * kKBlockBytes + 2 * kStemN * sizeof(float) + 64;
   static DeviceOnce attr;
   int attr_slot;
   if (attr.pending(&attr_slot)) {
-    LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LWP_CUDA_CHECK(cudaFuncSetAttribute(stem_gemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr.done[attr_slot] = true;
   }
   int per_sm = 5;   // 5 x (38 KB smem, 64 TMEM columns, 128 threads) per SM
   if (const char *e = getenv("LWP_STEM_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
   int grid = num_sms() * per_sm;
   if (grid > p.tiles) grid = p.tiles;
+  const int mode = !x_is_u8 ? 0 : (p.fast_norm ? 2 : 1);
   if (f32) {
-    if (x_is_u8) LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<true, true>, grid, kStemThreads, smem, st, 1, p));
-    else LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<true, false>, grid, kStemThreads, smem, st, 1, p));
+    if (mode == 2) LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<true, 2>, grid, kStemThreads, smem, st, 1, p));
+    else if (mode == 1) LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<true, 1>, grid, kStemThreads, smem, st, 1, p));
+    else LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<true, 0>, grid, kStemThreads, smem, st, 1, p));
   } else {
-    if (x_is_u8) LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<false, true>, grid, kStemThreads, smem, st, 1, p));
-    else LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<false, false>, grid, kStemThreads, smem, st, 1, p));
+    if (mode == 2) LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<false, 2>, grid, kStemThreads, smem, st, 1, p));
+    else if (mode == 1) LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<false, 1>, grid, kStemThreads, smem, st, 1, p));
+    else LWP_CUDA_CHECK(launch_pdl(stem_gemm_kernel<false, 0>, grid, kStemThreads, smem, st, 1, p));
   }
   return LWP_OK;
 }

@@ -212,17 +212,24 @@ def test_streaming_submit_collect_order(env):
             assert np.array_equal(r.pose_entries[b, :n], expect[k][1][b, :n])
 
 
-def test_uint8_frames_equal_normalised_float_input(env):
+@pytest.mark.parametrize("norm", [((128, 128, 128), 1 / 256, False), ((128, 128, 128), 1 / 256, True),
+                                  ((104.5, 117.0, 123.25), 1 / 255.0, False), ((0, 255, 7), 0.5, False)],
+                         ids=["default_f32_exact", "default_forced_f64", "general_f64", "pow2_f32_exact"])
+def test_uint8_frames_equal_normalised_float_input(env, norm, monkeypatch):
     """input_format='u8_nhwc': raw BGR frames with val.normalize fused into the stem give bit-identical heads and pose
-    tables to feeding the reference's normalised float32 NCHW tensor."""
+    tables to feeding the reference's normalised float32 NCHW tensor -- on the exact float32 short cut the stem takes
+    for integer means and a power-of-two scale (the reference's constants) and on the general float64 path."""
     torch, net = env
     from lwpose_b200 import synth, val
     from lwpose_b200.pipeline import PosePipeline
+    mean, scale, force_f64 = norm
+    if force_f64:
+        monkeypatch.setenv("LWP_STEM_F64_NORM", "1")
     B, H, W = 3, 64, 96
     frames = synth.synthetic_frames(B, H, W, seed=3)
-    x_f32 = torch.from_numpy(np.stack([val.normalize(f, (128, 128, 128), 1 / 256) for f in frames])).permute(0, 3, 1, 2).float().contiguous()
+    x_f32 = torch.from_numpy(np.stack([val.normalize(f, mean, scale) for f in frames])).permute(0, 3, 1, 2).float().contiguous()
     pf = PosePipeline(net, B, H, W, precision="bf16")
-    p8 = PosePipeline(net, B, H, W, precision="bf16", input_format="u8_nhwc")
+    p8 = PosePipeline(net, B, H, W, precision="bf16", input_format="u8_nhwc", img_mean=mean, img_scale=scale)
     rf = pf(x_f32.pin_memory()).check()
     hf = pf.heads.cpu().numpy()
     r8 = p8(torch.from_numpy(frames).pin_memory()).check()
