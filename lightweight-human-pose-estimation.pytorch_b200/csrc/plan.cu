@@ -354,7 +354,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
 
   // thin 1x1 layers (whole weight matrix <= 32 KB, one N tile): weights resident in shared memory, S = 256 / N tiles
   // per pipeline stage (conv_gemm_wres.cu).  LWP_GEMM_WRES=0 never, 1 every eligible layer, unset: single-K-block layers
-  // with enough super-tiles per SM that the coarser work unit does not cost a tail (measured, 64 x 368x656 bf16:
+  // with at least four super-tiles per SM, so that the coarser work unit costs little tail (measured, 64 x 368x656 bf16:
   // 32->64 165 -> 129 us, 64->128 72 -> 65 us; two-K-block layers +-1 us: 128->128 @92x164 88 -> 90, Cpm trunk 32 -> 31)
   {
     const char *ew = getenv("LWP_GEMM_WRES");
@@ -374,7 +374,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
       if (const char *sv = getenv("LWP_GEMM_STAGES")) { int v = atoi(sv); if (v >= 2 && v < st) st = v; }
       w.num_stages = st;
       const long long supers = ((long long)g.m_tiles + w.wres_sub - 1) / w.wres_sub;
-      const int min_per_sm = mode > 1 ? mode : 16;
+      const int min_per_sm = mode > 1 ? mode : 4;
       if (st >= 2 && (mode == 1 || (w.kblocks_per_tap == 1 && supers >= (long long)min_per_sm * num_sms())) &&
           conv_gemm_wres_init() == LWP_OK) {
         g = w;
