@@ -11,6 +11,8 @@
 //   paf_score_kernel           modules/keypoints.py:94-139 (line integral over the PAF)
 //   limb_match_kernel          modules/keypoints.py:140-157 (sort + greedy one-to-one assignment)
 //   pose_assemble_kernel       modules/keypoints.py:63-92,159-200 (sequential pose assembly + filter)
+#include <type_traits>
+
 #include "common.cuh"
 
 #include <float.h>
@@ -364,24 +366,26 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
     if (tid == 0) overflow[img] = 1;
     return;
   }
-  // 1. source window -> smem [ry][c][rx]; replicate border by clamping the coordinates
+  // 1. source window -> smem [ry][c][rx]; replicate border by clamping the coordinates.  A thread owns one (column,
+  // channel) pair -- channel fastest, so a warp reads runs of n_ch consecutive floats -- and walks down the rows: one
+  // clamp, one load, one store and one integer max per element (the flat-index version with its mixed-radix carries
+  // and a conditional atomic per element was a fifth of the kernel's instructions).
   {
-    // (channel, column, row) of this thread's first element, then advanced by blockDim.x elements without divisions
-    int c = tid % n_ch, rx = (tid / n_ch) % ncols, ry = tid / (n_ch * ncols);
-    const int dc = (int)blockDim.x % n_ch, dpos = (int)blockDim.x / n_ch;
-    const int drx = dpos % ncols, dry = dpos / ncols;
     const float *src_img = u.src + (size_t)img * u.h * u.w * u.ld;
-    for (int idx = tid; idx < nrows * ncols * n_ch; idx += blockDim.x) {
-      const float val =
-          __ldg(src_img + (size_t)((clampi(sy_lo + ry, 0, u.h - 1) * u.w + clampi(sx_lo + rx, 0, u.w - 1)) * u.ld + c));
-      s_src[(ry * n_ch + c) * kPkSrcMax + rx] = val;
-      const int bits = __float_as_int(fabsf(val));   // non-negative floats order like their bit patterns (NaN: never skipped)
-      if (bits > s_cmax[c]) atomicMax(&s_cmax[c], bits);
-      c += dc;
-      int carry = 0;
-      if (c >= n_ch) { c -= n_ch; carry = 1; }
-      rx += drx + carry; ry += dry;
-      if (rx >= ncols) { rx -= ncols; ++ry; }
+    const int npairs = n_ch * ncols;
+    const size_t row_pitch = (size_t)u.w * u.ld;
+    for (int pr = tid; pr < npairs; pr += blockDim.x) {
+      const int rx = pr / n_ch, c = pr - rx * n_ch;
+      const float *colp = src_img + (size_t)clampi(sx_lo + rx, 0, u.w - 1) * u.ld + c;
+      float *dst = s_src + c * kPkSrcMax + rx;
+      int mbits = 0;   // max |value| as float bits: non-negative floats order like their bit patterns (NaN: never skipped)
+#pragma unroll 4
+      for (int ry = 0; ry < nrows; ++ry) {
+        const float val = __ldg(colp + (size_t)clampi(sy_lo + ry, 0, u.h - 1) * row_pitch);
+        dst[ry * n_ch * kPkSrcMax] = val;
+        mbits = max(mbits, __float_as_int(fabsf(val)));
+      }
+      atomicMax(&s_cmax[c], mbits);
     }
   }
   __syncthreads();
@@ -455,27 +459,41 @@ peak_candidates_fused_kernel(const UpSrc u, int n_ch, unsigned long long *__rest
           }
         }
       };
+      // (the shared-memory address of the window's next row is kept as an integer: with a generic pointer the compiler
+      // rebuilt the shared window base from SR_CgaCtaId in every iteration)
+      const uint32_t tq0 = (uint32_t)__cvta_generic_to_shared(tp) + 3u * 32u * 4u;
+      auto run_groups = [&](auto all_valid_tag) {
+        constexpr bool kAllValid = decltype(all_valid_tag)::value;   // every row of the tile (+ halo) lies inside the image
+        uint32_t tq = tq0;
 #pragma unroll 1
-      for (int kk = 0; kk < 9; ++kk) {                    // group kk: rows e .. e + 3, e = oy0 - 2 + 4 kk (source row k0 + kk)
-        if (kk > 0) { T0 = T1; T1 = T2; T2 = T3; T3 = tp[(kk + 3) * 32]; }
-        const int e = oy0 - 2 + 4 * kk;
-        float a[4];
+        for (int kk = 0; kk < 9; ++kk) {                  // group kk: rows e .. e + 3, e = oy0 - 2 + 4 kk (source row k0 + kk)
+          if (kk > 0) {
+            T0 = T1; T1 = T2; T2 = T3;
+            tq += 128u;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(T3) : "r"(tq));
+          }
+          const int e = oy0 - 2 + 4 * kk;
+          float a[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float o = __fadd_rn(__fmul_rn(T2, cy4p[j][2]), __fmul_rn(T3, cy4p[j][3]));
-          o = __fadd_rn(__fmul_rn(T1, cy4p[j][1]), o);
-          o = __fadd_rn(__fmul_rn(T0, cy4p[j][0]), o);
-          a[j] = ((unsigned)(e + j - e_lo) <= e_span && !(o < 0.1f)) ? o : 0.f;   // thr01 + zero outside the image
+          for (int j = 0; j < 4; ++j) {
+            float o = __fadd_rn(__fmul_rn(T2, cy4p[j][2]), __fmul_rn(T3, cy4p[j][3]));
+            o = __fadd_rn(__fmul_rn(T1, cy4p[j][1]), o);
+            o = __fadd_rn(__fmul_rn(T0, cy4p[j][0]), o);
+            // thr01 + zero outside the image
+            a[j] = ((kAllValid || (unsigned)(e + j - e_lo) <= e_span) && !(o < 0.1f)) ? o : 0.f;
+          }
+          // centres e - 1 .. e + 2 (rows oy0 - 2 and oy0 + 33 are only ever neighbours of rows that are not centres)
+          if (__any_sync(0xffffffffu, fmaxf(fmaxf(pm1, a[0]), fmaxf(a[1], a[2])) > 0.f)) {
+            centre4(e - 1, pm2, pm1, a[0]);
+            centre4(e, pm1, a[0], a[1]);
+            centre4(e + 1, a[0], a[1], a[2]);
+            centre4(e + 2, a[1], a[2], a[3]);
+          }
+          pm2 = a[2]; pm1 = a[3];
         }
-        // centres e - 1 .. e + 2 (rows oy0 - 2 and oy0 + 33 are only ever neighbours of rows that are not centres)
-        if (__any_sync(0xffffffffu, fmaxf(fmaxf(pm1, a[0]), fmaxf(a[1], a[2])) > 0.f)) {
-          centre4(e - 1, pm2, pm1, a[0]);
-          centre4(e, pm1, a[0], a[1]);
-          centre4(e + 1, a[0], a[1], a[2]);
-          centre4(e + 2, a[1], a[2], a[3]);
-        }
-        pm2 = a[2]; pm1 = a[3];
-      }
+      };
+      if (oy0 >= 1 && oy0 + kPkRows <= u.H - 1) run_groups(std::true_type{});
+      else run_groups(std::false_type{});
       continue;
     }
     // the four horizontally-resized source rows of the current output row stay in registers: consecutive output
