@@ -121,11 +121,22 @@ __device__ __forceinline__ void upsampled_at(const UpSrc &u, int img, int e, int
 
 // Same arithmetic as upsampled_at<2>, source = this block's copy of the two PAF channels in shared memory
 // ([h][w] float2): one LDS.64 per tap serves both channels.
+// cw4 != nullptr: the map is an exact x4 up-sampling in both directions, so coordinate d has source index (d - 2) >> 2 and
+// the weights of phase (d + 2) & 3 -- cw4[phase] holds cubic_coeffs(0.125 + 0.25 phase), the very values cubic_axis()
+// computes (its fraction is exactly that) -- instead of the float64 geometry + coefficient polynomials per sample.
 __device__ __forceinline__ void upsampled_at_smem2(const UpSrc &u, const float2 *s, int e, int d, int ch0, int ch1,
-                                                   float (&out)[2]) {
+                                                   float (&out)[2], const float4 *cw4 = nullptr) {
   float cx[4], cy[4];
-  const int sx = cubic_axis(d, u.scale_x, cx);
-  const int sy = cubic_axis(e, u.scale_y, cy);
+  int sx, sy;
+  if (cw4 != nullptr) {
+    const float4 wx = cw4[(d + 2) & 3], wy = cw4[(e + 2) & 3];
+    cx[0] = wx.x; cx[1] = wx.y; cx[2] = wx.z; cx[3] = wx.w;
+    cy[0] = wy.x; cy[1] = wy.y; cy[2] = wy.z; cy[3] = wy.w;
+    sx = (d - 2) >> 2; sy = (e - 2) >> 2;
+  } else {
+    sx = cubic_axis(d, u.scale_x, cx);
+    sy = cubic_axis(e, u.scale_y, cy);
+  }
   const bool border = (sx < 1) || (sx + 2 >= u.w);
   const int i0 = clampi(sx - 1, 0, u.w - 1), i1 = clampi(sx, 0, u.w - 1);
   const int i2 = clampi(sx + 1, 0, u.w - 1), i3 = clampi(sx + 2, 0, u.w - 1);
@@ -653,7 +664,7 @@ struct ConnBefore {  // ratio descending; ties keep (i, j) generation order (sta
 template <bool kFused, bool kSmem>
 __device__ __forceinline__ double paf_sample(const float *paf, int W, int ld, const UpSrc &up, const float2 *s_src, int img,
                                              int demo, int ax, int ay, int vx, int vy, double ux, double uy, int k, int cx,
-                                             int cy) {
+                                             int cy, const float4 *cw4 = nullptr) {
   const double fx = __dadd_rn(__dmul_rn(__dmul_rn(1.0 / 9, (double)vx), (double)k), (double)ax);
   const double fy = __dadd_rn(__dmul_rn(__dmul_rn(1.0 / 9, (double)vy), (double)k), (double)ay);
   const int ix = demo ? __double2int_rz(fx) : __double2int_rn(fx);
@@ -661,7 +672,7 @@ __device__ __forceinline__ double paf_sample(const float *paf, int W, int ld, co
   float pv[2];
   if constexpr (kFused) {  // the up-sampled PAF pixel is computed on the fly, bit-identical to the materialised map
     if constexpr (kSmem) {
-      upsampled_at_smem2(up, s_src, iy, ix, cx, cy, pv);
+      upsampled_at_smem2(up, s_src, iy, ix, cx, cy, pv, cw4);
     } else {
       const int ch[2] = {cx, cy};
       upsampled_at<2>(up, img, iy, ix, ch, pv);
@@ -729,7 +740,17 @@ paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ 
   if (blockIdx.x * wpb * 32 >= total) return;   // no pair for this block
   extern __shared__ __align__(16) unsigned char ps_smem[];
   const float2 *s_src = reinterpret_cast<const float2 *>(ps_smem);
+  __shared__ float4 s_cw4[4];
+  const float4 *cw4 = nullptr;
   if constexpr (kFused && kSmem) {
+    if (up.scale_x == 0.25 && up.scale_y == 0.25 && up.W == 4 * up.w && up.H == 4 * up.h) {   // x4: periodic geometry
+      if (threadIdx.x < 4) {
+        float c[4];
+        cubic_coeffs(0.125f + 0.25f * (float)threadIdx.x, c);
+        s_cw4[threadIdx.x] = make_float4(c[0], c[1], c[2], c[3]);
+      }
+      cw4 = s_cw4;
+    }
     float2 *s_w = reinterpret_cast<float2 *>(ps_smem);
     if (packed != nullptr) {   // the limb's plane as paf_pack_kernel wrote it: one contiguous, fully coalesced copy
       const float4 *src4 = reinterpret_cast<const float4 *>(packed + ((size_t)img * LWP_NUM_LIMBS + limb) * plane_stride);
@@ -749,19 +770,25 @@ paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ 
     // ---- phase 1: lane = pair, two probe samples ----
     const int p1 = base + lane;
     bool survive = false;
+    // this lane's pair: kept for phase 2, whose ten lanes per pair fetch them by shuffle instead of redoing the two
+    // loads, the integer division and the float64 square root + two divisions
+    int p_i = 0, p_j = 0, p_ax = 0, p_ay = 0, p_vx = 0, p_vy = 0;
+    double p_norm = 0.0, p_ux = 0.0, p_uy = 0.0;
     if (p1 < total) {
       const int i = p1 / nB, j = p1 - i * nB;
       const lwp_keypoint a = A[i], b = B[j];
       const int vx = b.x - a.x, vy = b.y - a.y;
       const double norm = __dsqrt_rn((double)((long long)vx * vx + (long long)vy * vy));
+      p_i = i; p_j = j; p_ax = a.x; p_ay = a.y; p_vx = vx; p_vy = vy; p_norm = norm;
       if (norm != 0.0) {
         const double ux = __ddiv_rn((double)vx, norm), uy = __ddiv_rn((double)vy, norm);
+        p_ux = ux; p_uy = uy;
         // up to four probes (k = 3, 6, 1, 8); the pair is dropped at its second failing sample
         int fails = 0;
 #pragma unroll 1
         for (int q = 0; q < 4 && fails < 2; ++q) {
           const int kq = (0x8163 >> (4 * q)) & 15;
-          if (!(paf_sample<kFused, kSmem>(paf, W, ld, up, s_src, img, demo, a.x, a.y, vx, vy, ux, uy, kq, cx, cy) > min_paf_score))
+          if (!(paf_sample<kFused, kSmem>(paf, W, ld, up, s_src, img, demo, a.x, a.y, vx, vy, ux, uy, kq, cx, cy, cw4) > min_paf_score))
             ++fails;
         }
         survive = fails < 2;
@@ -782,17 +809,16 @@ paf_score_kernel(const lwp_keypoint *__restrict__ kpts, const int *__restrict__ 
         alive = m;
       }
       const bool active = g < 3 && src >= 0;
-      const int p = base + (active ? src : 0);
-      int i = 0, j = 0;
-      double v = 0.0, norm = 0.0;
+      const int sl = src & 31;
+      const int i = __shfl_sync(0xffffffffu, p_i, sl), j = __shfl_sync(0xffffffffu, p_j, sl);
+      const int ax = __shfl_sync(0xffffffffu, p_ax, sl), ay = __shfl_sync(0xffffffffu, p_ay, sl);
+      const int vx = __shfl_sync(0xffffffffu, p_vx, sl), vy = __shfl_sync(0xffffffffu, p_vy, sl);
+      const double norm = __shfl_sync(0xffffffffu, p_norm, sl);
+      const double ux = __shfl_sync(0xffffffffu, p_ux, sl), uy = __shfl_sync(0xffffffffu, p_uy, sl);
+      double v = 0.0;
       bool pass = false;
       if (active) {
-        i = p / nB; j = p - i * nB;
-        const lwp_keypoint a = A[i], b = B[j];
-        const int vx = b.x - a.x, vy = b.y - a.y;
-        norm = __dsqrt_rn((double)((long long)vx * vx + (long long)vy * vy));
-        const double ux = __ddiv_rn((double)vx, norm), uy = __ddiv_rn((double)vy, norm);
-        v = paf_sample<kFused, kSmem>(paf, W, ld, up, s_src, img, demo, a.x, a.y, vx, vy, ux, uy, k, cx, cy);
+        v = paf_sample<kFused, kSmem>(paf, W, ld, up, s_src, img, demo, ax, ay, vx, vy, ux, uy, k, cx, cy, cw4);
         pass = v > min_paf_score;
       }
       double sum = 0.0;
