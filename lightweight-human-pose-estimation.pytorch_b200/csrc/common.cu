@@ -25,6 +25,20 @@ int num_sms() {
   return s;
 }
 
+// SMs the NETWORK kernels size their persistent grids for: all of them, minus LWP_NET_SM_RESERVE (experiment: SMs left
+// free so that the post-processing of the previous batch, which runs on its own stream, does not have to wait for --
+// and then delay -- a persistent network CTA).
+int net_sms() {
+  static int reserve = -1;
+  if (reserve < 0) {
+    const char *e = getenv("LWP_NET_SM_RESERVE");
+    reserve = e ? atoi(e) : 0;
+    if (reserve < 0 || reserve > 64) reserve = 0;
+    reserve &= ~1;   // CTA pairs: keep the count even
+  }
+  return num_sms() - reserve;
+}
+
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) on = (getenv("LWP_NO_PDL") != nullptr && atoi(getenv("LWP_NO_PDL")) != 0) ? 0 : 1;

@@ -39,6 +39,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int num_sms();   // SM count of the CURRENT device (cached per device ordinal)
+int net_sms();   // SMs the network kernels' persistent grids are sized for (num_sms() - LWP_NET_SM_RESERVE)
 
 // One-time set-up that is per DEVICE (cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is): a process that drives
 // several GPUs must repeat it on each of them.

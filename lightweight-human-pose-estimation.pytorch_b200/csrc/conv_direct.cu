@@ -496,7 +496,7 @@ nhwc_to_nchw_kernel(const T *__restrict__ in, int ld, int c0, int c, float *__re
 
 static int grid_for(long long total, int block, int per_sm) {
   long long b = (total + block - 1) / block;
-  long long cap = (long long)num_sms() * per_sm;
+  long long cap = (long long)net_sms() * per_sm;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -610,7 +610,7 @@ static int depthwise_tma_launch_t(const CUtensorMap &tm, const CUtensorMap &tm_o
   if (const char *e = getenv("LWP_DW_STAGES")) { int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
   p.stages = stages;
   const size_t smem = 128 + 128 + (size_t)stages * p.stage_bytes + stg;
-  int per_cblk = num_sms() * per_sm / p.cblocks;
+  int per_cblk = net_sms() * per_sm / p.cblocks;
   if (per_cblk < 1) per_cblk = 1;
   if (per_cblk > p.sp_tiles) per_cblk = p.sp_tiles;
   const int grid = per_cblk * p.cblocks;

@@ -551,7 +551,7 @@ int frontend_fused_launch(const FrontendArgs &a, int *err_flag, cudaStream_t st)
     LWP_CUDA_CHECK(cudaFuncSetAttribute(frontend_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr.done[attr_slot] = true;
   }
-  const int grid = p.tiles < num_sms() ? p.tiles : num_sms();
+  const int grid = p.tiles < net_sms() ? p.tiles : net_sms();
   if (a.x_is_u8) LWP_CUDA_CHECK(launch_pdl(frontend_fused_kernel<true>, grid, kFeThreads, smem, st, 1, p));
   else LWP_CUDA_CHECK(launch_pdl(frontend_fused_kernel<false>, grid, kFeThreads, smem, st, 1, p));
   return LWP_OK;

@@ -428,7 +428,7 @@ int heads_fused_launch(const CUtensorMap &tmX, const CUtensorMap &tmW1, const CU
   p.debug = debug_env("LWP_DEBUG_HEADS");
   const size_t smem = heads_fused_smem_bytes(c_in, c_mid);
   if (smem > 232448) { set_error("heads_fused: %zu bytes of shared memory", smem); return LWP_ECAP; }
-  const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
+  const int grid = p.m_tiles < net_sms() ? p.m_tiles : net_sms();
   LWP_CUDA_CHECK(launch_pdl(heads_fused_kernel, grid, kHdThreads, smem, st, 1, tmX, tmW1, tmW2, p));
   return LWP_OK;
 }

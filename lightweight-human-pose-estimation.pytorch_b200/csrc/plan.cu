@@ -327,7 +327,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
   g.tiles_y = ceil_div(g.H, g.tile_h);
   g.m_tiles = g.NIMG * g.tiles_x * g.tiles_y;
   long long total_tiles = (long long)g.m_tiles * g.n_tiles;
-  op.grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+  op.grid = (int)(total_tiles < net_sms() ? total_tiles : net_sms());
   // CTA pairs (cta_group::2, M = 256): layers whose epilogue is the plain TMA-store one and that have enough tiles
   {
     // default (measured, 64 x 368x656 bf16): pairs win on the 1x1 layers with 256-wide N tiles (512->512: 138 -> 122 us,
@@ -336,8 +336,8 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
     const int mode = e2 ? atoi(e2) : -1;   // -1 default policy, 0 off, 1: 3x3 layers, 2: every eligible layer, 3: also small layers
     const bool plain = out != nullptr && out_f32 == nullptr && g.n_store % (kKBlockBytes / es) == 0 &&
                        getenv("LWP_NO_TMA_STORE") == nullptr;   // the pair kernel only has the TMA-store epilogue
-    const bool want = thin64 ? false : mode < 0 ? (taps == 1 && g.block_n == 256 && g.m_tiles >= 2 * num_sms())
-                               : (mode > 0 && g.block_n >= (mode >= 4 ? 64 : 128) && (mode >= 3 || g.m_tiles >= 2 * num_sms()) && (mode >= 2 || taps == 9));
+    const bool want = thin64 ? false : mode < 0 ? (taps == 1 && g.block_n == 256 && g.m_tiles >= 2 * net_sms())
+                               : (mode > 0 && g.block_n >= (mode >= 4 ? 64 : 128) && (mode >= 3 || g.m_tiles >= 2 * net_sms()) && (mode >= 2 || taps == 9));
     if (want && plain && conv_gemm2_init() == LWP_OK) {
       op.two_cta = true;
       g.kbps = 1;   // conv_gemm2_kernel: one K block per stage
@@ -347,7 +347,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
       g.num_stages = st2 > kMaxStages ? kMaxStages : st2;
       const long long pairs = (long long)((g.m_tiles + 1) / 2) * g.n_tiles;
       long long gr = 2 * pairs;
-      const int cap = num_sms() / 2 * 2;
+      const int cap = net_sms() / 2 * 2;
       op.grid = (int)(gr < cap ? gr : cap);
     }
   }
@@ -375,10 +375,10 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
       w.num_stages = st;
       const long long supers = ((long long)g.m_tiles + w.wres_sub - 1) / w.wres_sub;
       const int min_per_sm = mode > 1 ? mode : 4;
-      if (st >= 2 && (mode == 1 || (w.kblocks_per_tap == 1 && supers >= (long long)min_per_sm * num_sms())) &&
+      if (st >= 2 && (mode == 1 || (w.kblocks_per_tap == 1 && supers >= (long long)min_per_sm * net_sms())) &&
           conv_gemm_wres_init() == LWP_OK) {
         g = w;
-        op.grid = (int)(supers < num_sms() ? supers : num_sms());
+        op.grid = (int)(supers < net_sms() ? supers : net_sms());
       }
     }
   }
@@ -401,7 +401,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
       while (g.c3_a_stages > 2 && conv_gemm3_smem_bytes(g) > (size_t)gemm_smem_cap()) --g.c3_a_stages;
       g.acc_stages = 4; g.tmem_cols = 512;
       const long long pairs = (g.m_tiles + 1) / 2;
-      const int cap = num_sms() / 2 * 2;
+      const int cap = net_sms() / 2 * 2;
       op.grid = (int)(2 * pairs < cap ? 2 * pairs : cap);
     }
   }
@@ -580,7 +580,7 @@ extern "C" int lwp_plan_add_dwpw(lwp_plan *p, const void *in, const float *dw_w,
     if (dwpw_smem_bytes(t) <= limit) f = t;
   }
   if (dwpw_smem_bytes(f) > limit) { set_error("lwp_plan_add_dwpw: shared memory budget exceeded"); return LWP_ECAP; }
-  op.grid = f.m_tiles < num_sms() ? f.m_tiles : num_sms();
+  op.grid = f.m_tiles < net_sms() ? f.m_tiles : net_sms();
 
   EncodeTiledFn enc = get_encode_fn();
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -700,7 +700,7 @@ extern "C" int lwp_plan_add_sepconv(lwp_plan *p, const void *in, const float *dw
   }
   rc = build_dw_consts(p, dw_w, dw_scale, dw_shift, Cin, kb_ch, f.kblocks, &f.dw_consts);
   if (rc != LWP_OK) return rc;
-  op.grid = f.m_tiles < num_sms() ? f.m_tiles : num_sms();
+  op.grid = f.m_tiles < net_sms() ? f.m_tiles : net_sms();
 
   EncodeTiledFn enc = get_encode_fn();
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;

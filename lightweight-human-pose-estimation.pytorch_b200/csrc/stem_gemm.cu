@@ -280,7 +280,7 @@ int stem_gemm_launch(bool f32, const void *x, bool x_is_u8, const double *mean3,
   }
   int per_sm = 5;   // 5 x (38 KB smem, 64 TMEM columns, 128 threads) per SM
   if (const char *e = getenv("LWP_STEM_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
-  int grid = num_sms() * per_sm;
+  int grid = net_sms() * per_sm;
   if (grid > p.tiles) grid = p.tiles;
   const int mode = !x_is_u8 ? 0 : (p.fast_norm ? 2 : 1);
   if (f32) {
