@@ -216,6 +216,77 @@ upsample_cubic_kernel(const UpSrc u, float *__restrict__ dst, int col_tiles, lon
   }
 }
 
+// Separable form of the same resize for c <= kUpMaxC channels: a block takes kUpRows output rows of a kUpCols-column
+// span and streams down them.  Each source row the rows need is resized horizontally ONCE (HResizeCubic order) into a
+// ring of four shared-memory rows -- the four rows of a vertical window r .. r + 3 fall into four different slots
+// r & 3 -- and every output row is a vertical combination (VResizeCubicVec_32f / scalar-tail order) of the ring:
+// 4 global loads per horizontally-resized value, amortised over the output rows that share the source row, plus 4
+// shared-memory loads per output, instead of 16 global loads per output.  Operation for operation the arithmetic of
+// upsample_cubic_kernel: same bits.  Used for up-scaling by 2 or more (val.py:98-108: the x8 map -> frame size resize of
+// the scales below the frame size).
+constexpr int kUpRows = 32, kUpMaxC = 38;
+__global__ void __launch_bounds__(256)
+upsample_cubic_rows_kernel(const UpSrc u, float *__restrict__ dst, int col_tiles, int row_tiles, long long row_pitch,
+                           long long img_pitch, float acc_div) {
+  __shared__ __align__(16) float s_cx[kUpCols][4];
+  __shared__ __align__(16) int s_i[kUpCols][4];      // clamped source columns, already multiplied by the pixel stride
+  __shared__ unsigned char s_border[kUpCols];
+  __shared__ __align__(16) float s_cy[kUpRows][4];
+  __shared__ int s_sy[kUpRows];
+  __shared__ float s_T[4][kUpCols * kUpMaxC];          // ring of horizontally resized source rows
+  const int tile = blockIdx.x % col_tiles;
+  const int rt = (blockIdx.x / col_tiles) % row_tiles;
+  const int img = blockIdx.x / (col_tiles * row_tiles);
+  const int d0 = tile * kUpCols, e0 = rt * kUpRows;
+  const int ncol = min(kUpCols, u.W - d0), nrow = min(kUpRows, u.H - e0);
+  const int c = u.c_layout;
+  if (threadIdx.x < ncol) {
+    float cx[4];
+    const int sx = cubic_axis(d0 + threadIdx.x, u.scale_x, cx);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s_cx[threadIdx.x][k] = cx[k];
+      s_i[threadIdx.x][k] = clampi(sx - 1 + k, 0, u.w - 1) * u.ld;
+    }
+    s_border[threadIdx.x] = (sx < 1) || (sx + 2 >= u.w);
+  } else if (threadIdx.x >= 128 && threadIdx.x < 128 + nrow) {
+    const int t = threadIdx.x - 128;
+    s_sy[t] = cubic_axis(e0 + t, u.scale_y, s_cy[t]);
+  }
+  __syncthreads();
+  const float *img_src = u.src + (size_t)img * img_pitch;   // (possibly a cropped view: rows row_pitch floats apart)
+  const int rowlen = u.W * c, body = rowlen - (rowlen & 3);
+  const int nq = ncol * c, q0 = d0 * c;
+  int next_row = INT_MIN;   // first (un-clamped) source row that is not in the ring yet; block-uniform
+  for (int t = 0; t < nrow; ++t) {
+    const int sy = s_sy[t];
+    // horizontal pass of the window rows sy - 1 .. sy + 2 that are new (source rows are needed in increasing order)
+    for (int r = max(next_row, sy - 1); r <= sy + 2; ++r) {
+      const float *rp = img_src + (size_t)clampi(r, 0, u.h - 1) * row_pitch;
+      float *Tr = s_T[r & 3];
+      for (int q = threadIdx.x; q < nq; q += 256) {
+        const int dl = q / c, ch = q - dl * c;
+        const float4 cx = *reinterpret_cast<const float4 *>(s_cx[dl]);
+        const int4 ii = *reinterpret_cast<const int4 *>(s_i[dl]);
+        const float cxv[4] = {cx.x, cx.y, cx.z, cx.w};
+        Tr[q] = cubic_hsum(rp + ch, ii.x, ii.y, ii.z, ii.w, cxv, s_border[dl] != 0);
+      }
+    }
+    next_row = sy + 3;
+    __syncthreads();
+    const float4 cy4 = *reinterpret_cast<const float4 *>(s_cy[t]);
+    const float cy[4] = {cy4.x, cy4.y, cy4.z, cy4.w};
+    const float *T0 = s_T[(sy - 1) & 3], *T1 = s_T[sy & 3], *T2 = s_T[(sy + 1) & 3], *T3 = s_T[(sy + 2) & 3];
+    float *out = dst + (((size_t)img * u.H + e0 + t) * u.W + d0) * c;
+    for (int q = threadIdx.x; q < nq; q += 256) {
+      const float T[4] = {T0[q], T1[q], T2[q], T3[q]};
+      const float v = cubic_vsum(T, cy, q0 + q < body);
+      out[q] = acc_div != 0.f ? __fadd_rn(out[q], __fdiv_rn(v, acc_div)) : v;
+    }
+    __syncthreads();   // the next row's horizontal pass may overwrite a ring slot this row still read
+  }
+}
+
 // Integer ratios that are powers of two (the x4 of demo.py:72,76 and the x8 of val.py:98,105): output pixel e = R k + R/2 + j
 // (j = 0..R-1) has source index k and fraction (j + 0.5) / R exactly, whatever k -- the geometry is periodic, so a thread
 // takes ONE channel of one source cell (ky, kx), loads its 4 x 4 source patch once and produces the R x R outputs that
@@ -1158,6 +1229,18 @@ extern "C" int lwp_upsample_cubic_ex(const float *src, int n, int h, int w, int 
   const int col_tiles = ceil_div(W, kUpCols);
   const long long blocks = (long long)n * H * col_tiles;
   LWP_REQUIRE(blocks < INT_MAX, "lwp_upsample_cubic: too many blocks");
+  // the row-streaming kernel wins where several output rows share a source row (measured, 16 x 57 channels -> 480x640:
+  // from 184x248 1.81 -> 1.33 ms; from 368x491 1.81 -> 1.78; from 552x736 / 736x984 1.86 / 1.89 -> 2.23 / 2.67 ms: with
+  // fewer output rows per source row its horizontal passes and two barriers per row cost more than 16 L1-resident loads)
+  if (c <= kUpMaxC && u.scale_y <= 0.5 && getenv("LWP_UPSAMPLE_NO_ROWS") == nullptr) {
+    const int row_tiles = ceil_div(H, kUpRows);
+    const long long blocks_r = (long long)n * row_tiles * col_tiles;
+    LWP_REQUIRE(blocks_r < INT_MAX, "lwp_upsample_cubic: too many blocks");
+    upsample_cubic_rows_kernel<<<(unsigned)blocks_r, 256, 0, (cudaStream_t)stream>>>(u, dst, col_tiles, row_tiles, src_row_pitch,
+                                                                                   src_img_pitch, accumulate_divisor);
+    LWP_LAUNCH_CHECK();
+    return LWP_OK;
+  }
   upsample_cubic_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(u, dst, col_tiles, src_row_pitch, src_img_pitch,
                                                                             accumulate_divisor);
   LWP_LAUNCH_CHECK();
