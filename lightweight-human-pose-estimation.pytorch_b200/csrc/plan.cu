@@ -345,6 +345,7 @@ extern "C" int lwp_plan_add_conv_gemm(lwp_plan *p, const void *in, int in_ld, co
       const int stage2 = kATileBytes + (g.block_n / 2) * kKBlockBytes;
       int st2 = ((gemm_smem_cap() < 200 * 1024 ? gemm_smem_cap() - 4096 : 200 * 1024) - kStagingBytes) / stage2;
       g.num_stages = st2 > kMaxStages ? kMaxStages : st2;
+      if (const char *sv = getenv("LWP_GEMM2_STAGES")) { int v = atoi(sv); if (v >= 2 && v < g.num_stages) g.num_stages = v; }   // experiment
       const long long pairs = (long long)((g.m_tiles + 1) / 2) * g.n_tiles;
       long long gr = 2 * pairs;
       const int cap = net_sms() / 2 * 2;
