@@ -110,18 +110,25 @@ stem_gemm_kernel(const StemGemmParams p) {
   const uint8_t *x8 = reinterpret_cast<const uint8_t *>(p.x);
   const int HoWo = p.Ho * p.Wo;
 
-  // gather + round + store the K row of this thread's pixel of tile t into stage s
-  auto build = [&](int t, int s) {
+  // The A row of a tile is built in two steps so that the gather's memory latency overlaps the previous tile's epilogue:
+  // gather() issues the 27 loads of this thread's pixel into registers (raw values, taps outside the image stay 0 and
+  // are flagged), commit() normalises / rounds them and writes the pixel's K row into stage s.
+  struct Taps {
+    float f[27];     // float32 frames: the values; uint8 frames: the bytes (as integers in float registers' bit patterns)
+    uint32_t skip;   // bit 0: no pixel (past the end), bit 1: window row 0 is outside, bit 2: window column 0 is outside
+  };
+  auto gather = [&](int t, Taps &g) {
     const long long pix = (long long)t * kBlockM + tid;
-    float v[32];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = 0.f;
+    for (int k = 0; k < 27; ++k) g.f[k] = 0.f;
+    g.skip = 1u;
     if (pix < p.total) {
       const int img = (int)(pix / HoWo), rem = (int)(pix - (long long)img * HoWo);
       const int yo = rem / p.Wo, xo = rem - yo * p.Wo;
       const int yi0 = 2 * yo - 1, xi0 = 2 * xo - 1;
       // H and W are even, so only the first row / column of the window can fall outside (yo == 0 / xo == 0)
       const bool top = yo == 0, left = xo == 0;
+      g.skip = (top ? 2u : 0u) | (left ? 4u : 0u);
       if constexpr (kU8 != 0) {
         const uint8_t *base = x8 + (((long long)img * p.H + yi0) * p.W + xi0) * 3;   // may point before the frame: guarded
         const int rowb = p.W * 3;
@@ -131,16 +138,9 @@ stem_gemm_kernel(const StemGemmParams p) {
           const uint8_t *row = base + ky * rowb;
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            if (kx == 0 && left) continue;   // zero padding applies to the NORMALISED image (pad value 0 after normalize)
+            if (kx == 0 && left) continue;
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
-              const uint32_t b = __ldg(row + kx * 3 + ci);
-              // val.normalize in float64 like the reference (two conversions + two FP64 operations per tap: the
-              // conversion pipe made this variant 30 us slower than the float32 one) -- or, when that is exact in
-              // float32, one LOP3 + one FFMA with the same bits
-              if constexpr (kU8 == 2) v[ci * 9 + ky * 3 + kx] = __fmaf_rn(__uint_as_float(0x4B000000u | b), p.nscale, p.noff[ci]);
-              else v[ci * 9 + ky * 3 + kx] = __double2float_rn(__dmul_rn(__dsub_rn((double)b, p.mean[ci]), p.img_scale));
-            }
+            for (int ci = 0; ci < 3; ++ci) g.f[ci * 9 + ky * 3 + kx] = __uint_as_float((uint32_t)__ldg(row + kx * 3 + ci));
           }
         }
       } else {
@@ -155,12 +155,39 @@ stem_gemm_kernel(const StemGemmParams p) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
               if (kx == 0 && left) continue;
-              v[ci * 9 + ky * 3 + kx] = __ldg(row + kx);
+              g.f[ci * 9 + ky * 3 + kx] = __ldg(row + kx);
             }
           }
         }
       }
     }
+  };
+  auto commit = [&](const Taps &g, int s) {
+    float v[32];
+#pragma unroll
+    for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int k = ci * 9 + ky * 3 + kx;
+          if constexpr (kU8 != 0) {
+            // zero padding applies to the NORMALISED image (pad value 0 after normalize)
+            const bool out = (g.skip & 1u) || (ky == 0 && (g.skip & 2u)) || (kx == 0 && (g.skip & 4u));
+            const uint32_t b = __float_as_uint(g.f[k]);
+            // val.normalize in float64 like the reference (two conversions + two FP64 operations per tap: the
+            // conversion pipe made this variant 30 us slower than the float32 one) -- or, when that is exact in
+            // float32, one LOP3 + one FFMA with the same bits
+            float nv;
+            if constexpr (kU8 == 2) nv = __fmaf_rn(__uint_as_float(0x4B000000u | b), p.nscale, p.noff[ci]);
+            else nv = __double2float_rn(__dmul_rn(__dsub_rn((double)b, p.mean[ci]), p.img_scale));
+            v[k] = out ? 0.f : nv;
+          } else {
+            v[k] = g.f[k];
+          }
+        }
     stem_store_row<kTf32>(a_tiles + s * kATileBytes, tid, v);
   };
   // one thread: the K = 32 product of stage s into accumulator stage s, completion on bars[s]
@@ -174,26 +201,19 @@ stem_gemm_kernel(const StemGemmParams p) {
   };
 
   int t = blockIdx.x;
+  Taps g;
   if (t < p.tiles) {
-    build(t, 0);
+    gather(t, g);
+    commit(g, 0);
     ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) { ptx::tc_fence_after(); mma(0); }
+    if (t + (int)gridDim.x < p.tiles) gather(t + gridDim.x, g);   // in flight during the first epilogue
   }
   uint32_t phases = 0u;   // bit s: parity the next wait on bars[s] expects
   for (int s = 0; t < p.tiles; t += gridDim.x, s ^= 1) {
     const int tn = t + gridDim.x;
-    if constexpr (!kTf32) {   // the bulk store of the previous tile has finished reading its staging rows (= stage s ^ 1)
-      if (lane == 0) ptx::bulk_wait_read<0>();
-      __syncwarp();
-    }
-    if (tn < p.tiles) {   // next tile's A rows while this tile's MMA runs; stage s^1 and its accumulator were released by
-      build(tn, s ^ 1);   // the previous iteration (its MMA was waited for, its accumulator drained)
-      ptx::fence_proxy_async();
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (tn < p.tiles && tid == 0) { ptx::tc_fence_after(); mma(s ^ 1); }
+    // ---- epilogue of tile t (its MMA was issued one iteration ago); the loads of tile tn are in flight ----
     if (!ptx::mbar_wait(&bars[s], (phases >> s) & 1u)) { atomicExch(p.err_flag, 21); break; }
     phases ^= 1u << s;
     ptx::tc_fence_after();
@@ -201,19 +221,17 @@ stem_gemm_kernel(const StemGemmParams p) {
     ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * kStemN), r);
     ptx::tmem_ld_wait(r);
     const long long pix = (long long)t * kBlockM + tid;
-    if (pix < p.total) {
+    if (kTf32 && pix < p.total) {
       float y[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) y[c] = fmaxf(fmaf(__uint_as_float(r[c]), s_scale[c], s_shift[c]), 0.f);
-      if constexpr (kTf32) {
-        float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + pix * 32);
+      float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + pix * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) op[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-      }
+      for (int j = 0; j < 8; ++j) op[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
     }
     if constexpr (!kTf32) {
       // bf16: the warp's 32 pixels are 2 KB of contiguous output.  They are staged in the warp's own rows of the A tile
-      // the MMA has just finished reading (only this warp rewrites those rows, in build() two tiles later) and leave
+      // the MMA has just finished reading (only this warp rewrites those rows, in commit() two tiles later) and leave
       // as ONE bulk copy instead of 4 x 32 scattered 16-byte stores.
       uint8_t *stg = a_tiles + s * kATileBytes + warp * 4096;
       float y[32];
@@ -235,7 +253,20 @@ stem_gemm_kernel(const StemGemmParams p) {
         ptx::bulk_store_1d(reinterpret_cast<__nv_bfloat16 *>(p.out) + pix0 * 32, stg, (uint32_t)(left < 32 ? left : 32) * 64u);
         ptx::bulk_commit();
       }
+      // stage s ^ 1 is written next: the bulk store of tile t - 1 (everything but the store just committed) must have
+      // finished reading its staging rows there
+      if (lane == 0) ptx::bulk_wait_read<1>();
+      __syncwarp();
     }
+    // ---- next tile: its A rows into stage s ^ 1 (released: MMA waited for, accumulator drained, staging read), MMA ----
+    if (tn < p.tiles) {
+      commit(g, s ^ 1);
+      ptx::fence_proxy_async();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tn < p.tiles && tid == 0) { ptx::tc_fence_after(); mma(s ^ 1); }
+    if (tn + (int)gridDim.x < p.tiles) gather(tn + gridDim.x, g);   // the tile after next: in flight during the next epilogue
   }
   if constexpr (!kTf32) {
     if (lane == 0) ptx::bulk_wait<0>();
