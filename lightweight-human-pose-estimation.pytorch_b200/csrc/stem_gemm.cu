@@ -9,7 +9,7 @@
 // K-major SWIZZLE_128B shared-memory tile (27 real + 5 zero columns = one 64-byte half row in bf16 / one whole
 // 128-byte row in tf32); one thread issues tcgen05.mma (M = 128 pixels, N = 32 channels, K = 32); the epilogue
 // reads the fp32 accumulators back from TMEM (thread = pixel) and stores the 32 channels of its pixel.  The CUDA
-// cores move data (about 400 instructions per output pixel-warp instead of ~550 per pixel for the direct FFMA form), the 864
+// cores move data (about 400 instructions per output pixel, mostly addressing, packing and the epilogue, instead of ~550 for the direct FFMA form), the 864
 // MACs per pixel go to the tensor pipe, and the kernel becomes a streaming read of the frames and write of the
 // first activation.  Several small CTAs per SM (each with its own 64 TMEM columns) hide the load latency, and inside a
 // CTA the gather is software-pipelined: the loads of the tile after next are in flight while the current tile's
